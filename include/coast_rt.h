@@ -1,0 +1,243 @@
+/*
+ * coast_rt.h -- C ABI of libcoast_rt.so, the B200 redundant-execution runtime.
+ *
+ * The reference (byuccl/coast) has NO run-time library: `opt -TMR/-DWC` inlines
+ * replicas, voters and counters into the program.  The only run-time symbols it
+ * leaves behind are
+ *     i32  TMR_ERROR_CNT            projects/dataflowProtection/synchronization.cpp:38,269-291
+ *     i64  __SYNC_COUNT             synchronization.cpp:47,103-121
+ *     void FAULT_DETECTED_DWC(void) synchronization.cpp:36,1198-1267
+ * This library exports exactly those three, plus a launch ABI that replaces
+ *     dataflowProtection::run(M, numClones)   dataflowProtection.cpp:63-164
+ *     TMR::runOnModule  -> run(M,3)           projects/TMR/TMR.cpp:29-36
+ *     DWC::runOnModule  -> run(M,2)           projects/DWC/DWC.cpp:29-36
+ * with a runtime "triplicate-and-vote" launch of a hand-written sm_100a kernel.
+ *
+ * Plain C, plain pointers and sizes.  No CUDA / torch types in any signature:
+ * device pointers are `void*` (CUdeviceptr-compatible), streams are `void*`
+ * (CUstream / cudaStream_t / torch's `cuda_stream` integer).  The library binds
+ * to libcuda.so.1 lazily (dlopen) inside coast_init(), so it LOADS on a box
+ * without a GPU and every compute entry point then fails loudly with
+ * COAST_ERR_NO_DRIVER -- there is no CPU fallback in this library.
+ *
+ * Thread-safety: like the reference's emitted code (plain load/add/store on the
+ * counters, synchronization.cpp:1428-1431) the host API is NOT thread-safe per
+ * process; device counters are warp-reduced and atomically added.
+ */
+#ifndef COAST_RT_H_
+#define COAST_RT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ */
+/* Run-time symbols the reference pass creates/uses (same names/types) */
+/* ------------------------------------------------------------------ */
+
+/* synchronization.cpp:269-291 -- i32, zero-initialised, +1 per executed TMR sync
+ * point at which any replica disagrees with r0 (when -countErrors is given).
+ * Weak here: a test that defines its own (tests/pynq/matrixMultiply.tmr/mm_tmr.c:29)
+ * wins at link time. */
+extern uint32_t TMR_ERROR_CNT;
+/* synchronization.cpp:103-121,1415-1425 -- i64, +1 per executed sync point
+ * (-countSyncs; only emitted together with the TMR error counter). */
+extern uint64_t __SYNC_COUNT;
+/* synchronization.cpp:1198-1267 -- user-overridable DWC handler; the default the
+ * pass synthesises calls abort() (:1251-1266).  Weak default here does the same. */
+void FAULT_DETECTED_DWC(void);
+
+/* ------------------------------------------------------------------ */
+/* Protected workloads              */
+/* ------------------------------------------------------------------ */
+typedef enum coast_kernel_id {
+    COAST_K_CRC16     = 0, /* tests/crc16/crc16.c:21-31                        */
+    COAST_K_SHA256    = 1, /* tests/sha256_common/sha256_common_tmr.c:28-180   */
+    COAST_K_AES128    = 2, /* tests/aes/TI_aes_128.c:107-231                   */
+    COAST_K_MM_U32    = 3, /* tests/mm_common/mm_common_tmr.c:3-20 (exact, mod 2^32;
+                              same low 32 bits as matrixMultiply.c:95-112)      */
+    COAST_K_GEMM_TF32 = 4, /* BASELINE config 4: fp32 in/out, tcgen05 kind::tf32 */
+    COAST_K_COUNT_    = 5
+} coast_kernel_id;
+
+/* numClones of dataflowProtection::run: 3 = -TMR, 2 = -DWC, 1 = unprotected
+ * single replica (the baseline the acceptance ratios are quoted against). */
+#define COAST_UNPROTECTED 1u
+#define COAST_DWC         2u
+#define COAST_TMR         3u
+
+/* OPT_PASSES tokens (dataflowProtection.cpp:14-47) that change the emitted code
+ * on this path.  coast_parse_opt_passes() maps the token string onto these. */
+#define COAST_F_COUNT_ERRORS        0x0001u /* -countErrors  synchronization.cpp:1354-1465 */
+#define COAST_F_COUNT_SYNCS         0x0002u /* -countSyncs   synchronization.cpp:1415-1425 */
+#define COAST_F_NO_MEM_REPLICATION  0x0004u /* -noMemReplication: accepted; inputs are always
+                                               ONE staged copy read by every replica (passes.rst:331) */
+#define COAST_F_INTERLEAVE          0x0008u /* -i : replicas on adjacent LANES of one warp        */
+#define COAST_F_SEGMENT             0x0010u /* -s : replicas on adjacent WARPS of one CTA (reference default,
+                                               interface.cpp:245-247); layout hint only, results identical */
+#define COAST_F_VERBOSE             0x0020u /* -verbose */
+#define COAST_F_REPORT_ERRORS_LEGACY 0x0040u /* -reportErrors (deprecated; counts AGREEING syncs,
+                                               synchronization.cpp:1323-1350).  Parsed, warned, NOT emulated. */
+#define COAST_F_MAJORITY_VOTER      0x0100u /* extension: bitwise 2-of-3 majority instead of the reference's
+                                               select voter.  Off by default (reference semantics). */
+
+/* ------------------------------------------------------------------ */
+/* Fault plan: the on-device replacement of simulation/platform         */
+/* ------------------------------------------------------------------ */
+/* Reference fault model: exactly one uniformly random single-bit flip
+ * (`val ^ (1 << randint(0, bitlen-1))`, simulation/platform/resources/injector.py:202-207)
+ * at a uniformly random location (:156-179) per run.  Here a "run" is one unit
+ * (message / block / output element).  At most one flip per unit:
+ *
+ *   mode BERNOULLI: (x0,x1,x2,x3) = Philox4x32-10(ctr = {unit_lo, unit_hi, 0, 0},
+ *                                                 key = {seed_lo, seed_hi})
+ *        inject  iff x0 < threshold            (p = threshold / 2^32)
+ *        replica = x1 % num_clones
+ *        site    = x2 % n_sites(kernel, unit_bytes)   (coast_fault_sites())
+ *        bit     = x3 % site_width_bits(kernel, site) (coast_fault_site_bits())
+ *   mode TABLE: one u32 per unit on the device, COAST_FAULT_ENTRY(replica, site, bit)
+ *        or 0 for "no fault" -- the analogue of `--forceBreak "set ADDR = VAL"`
+ *        (supervisor.py:357-359).  Entries with replica >= num_clones, site >= n_sites
+ *        or bit >= width are ignored (not counted as injected).
+ *
+ * `unit` is the GLOBAL unit index (coast_launch_desc.unit_base + local index) so a
+ * sharded multi-GPU run sees the same fault distribution as a single-GPU run.
+ * The enumerated sites (identical in oracle/ and in the kernels) are listed in
+ * DESIGN.md section "Fault sites". */
+#define COAST_PLAN_NONE      0u
+#define COAST_PLAN_BERNOULLI 1u
+#define COAST_PLAN_TABLE     2u
+#define COAST_FAULT_ENTRY(replica, site, bit) \
+    (0x80000000u | (((uint32_t)(replica) & 3u) << 29) | (((uint32_t)(site) & 0xFFFFFFu) << 5) | ((uint32_t)(bit) & 31u))
+
+typedef struct coast_fault_plan {
+    uint32_t mode;        /* COAST_PLAN_*                                   */
+    uint32_t seed_lo;     /* Philox key word 0                               */
+    uint32_t seed_hi;     /* Philox key word 1                               */
+    uint32_t threshold;   /* BERNOULLI: inject iff x0 < threshold            */
+    const void* d_table;  /* TABLE: device pointer, n_units x uint32_t       */
+} coast_fault_plan;
+
+/* ------------------------------------------------------------------ */
+/* Launch descriptor                                                   */
+/* ------------------------------------------------------------------ */
+/* Layouts (all device pointers, caller-owned, dense, unit-major):
+ *   CRC16    in : n_units x unit_bytes (1..255) message bytes   out: n_units x uint16_t
+ *   SHA256   in : n_units x unit_bytes message bytes            out: n_units x 32 digest bytes
+ *   AES128   in : n_units x 16 state bytes                      out: n_units x 16
+ *            aux: per-unit 16-byte keys (n_units x 16) if COAST_AES_KEY_PER_UNIT in `mode`,
+ *                 otherwise NULL and `key` below is the one ECB key.  mode bit0 = dir
+ *                 (0 encrypt, 1 decrypt, as TI_aes_128.c:107's `dir`; the key passed is
+ *                 always the ORIGINAL cipher key, :112-129).
+ *   MM_U32   in : A, M x K uint32 row-major; aux: B, K x N uint32 row-major
+ *            out: C, M x N uint32; a unit is one C element, n_units must be M*N
+ *   GEMM_TF32 same with float.  unit_base/rows: see row_base.
+ */
+#define COAST_AES_DECRYPT       0x1u
+#define COAST_AES_KEY_PER_UNIT  0x2u
+
+typedef struct coast_launch_desc {
+    uint32_t kernel;       /* coast_kernel_id                                    */
+    uint32_t num_clones;   /* 1, 2 (DWC) or 3 (TMR)                               */
+    uint32_t flags;        /* COAST_F_*                                           */
+    uint32_t mode;         /* kernel-specific (AES: COAST_AES_*)                  */
+    uint64_t n_units;      /* units in THIS launch                                */
+    uint64_t unit_base;    /* global index of this launch's unit 0 (fault plans)  */
+    uint32_t unit_bytes;   /* CRC16/SHA256: message length of every unit          */
+    uint32_t M, N, K;      /* MM_U32 / GEMM_TF32                                  */
+    const void* d_in;
+    void*       d_out;
+    const void* d_aux;
+    uint8_t     key[16];   /* AES single-key mode                                 */
+    const coast_fault_plan* plan; /* NULL = no injection                          */
+} coast_launch_desc;
+
+/* Counters of everything launched since the last coast_sync(). */
+typedef struct coast_stats {
+    uint64_t errors_corrected; /* TMR: sync points with !(r0==r1 && r0==r2); needs COAST_F_COUNT_ERRORS */
+    uint64_t dwc_detected;     /* DWC: units with >= 1 mismatching output element            */
+    uint64_t syncs;            /* executed sync points; needs COAST_F_COUNT_SYNCS             */
+    uint64_t injected;         /* units that received a flip                                  */
+    uint64_t first_fault_unit; /* smallest global unit index with a disagreement, or UINT64_MAX */
+} coast_stats;
+
+/* Error codes (0 = ok).  Driver errors are returned as -(CUresult). */
+#define COAST_OK              0
+#define COAST_ERR_NO_DRIVER   (-100001) /* libcuda.so.1 / a CUDA device is not available      */
+#define COAST_ERR_NOT_INIT    (-100002)
+#define COAST_ERR_BAD_ARG     (-100003)
+#define COAST_ERR_UNSUPPORTED (-100004)
+
+/* --- lifetime ------------------------------------------------------ */
+int  coast_init(int device);          /* bind libcuda, retain device's primary context, load the sm_100a module */
+int  coast_shutdown(void);
+const char* coast_last_error(void);   /* human-readable text of the last failure */
+const char* coast_version(void);
+
+/* --- the pass front end: OPT_PASSES string -> (num_clones, flags) -- */
+/* Accepts the tokens of tests/<t>/Makefile OPT_PASSES (e.g. "-TMR -verbose -countErrors").
+ * Unknown tokens are warned about on stderr and ignored, as `opt` would for passes
+ * that are not loaded.  Returns 0, or COAST_ERR_BAD_ARG if both -TMR and -DWC. */
+int  coast_parse_opt_passes(const char* opt_passes, uint32_t* num_clones, uint32_t* flags);
+
+/* --- the launch (replaces dataflowProtection::run + the emitted code) */
+int  coast_launch(const coast_launch_desc* desc, void* stream);
+
+/* Wait for `stream`, fold the device counters into *out (may be NULL) and into the
+ * reference's globals: TMR_ERROR_CNT += errors_corrected (mod 2^32), __SYNC_COUNT += syncs;
+ * then, if dwc_detected > 0, call FAULT_DETECTED_DWC() once (synchronization.cpp:1299-1302;
+ * deferred to kernel completion -- a grid cannot abort() mid-flight).  Resets the device counters. */
+int  coast_sync(void* stream, coast_stats* out);
+/* Same, but never calls FAULT_DETECTED_DWC (campaign tooling wants the count, not SIGABRT). */
+int  coast_sync_noabort(void* stream, coast_stats* out);
+/* Copy the device counters into *out asynchronously-safe form without resetting/aborting.
+ * `d_stats_out` variant: enqueue a D2D copy of the 5 counters (5 x u64) on `stream`, for
+ * callers that all-reduce them across GPUs (NCCL) before looking at them. */
+int  coast_stats_snapshot(void* stream, void* d_stats_out /* 5 x uint64_t on device */);
+int  coast_stats_reset(void* stream);
+
+/* --- fault-site geometry (shared by oracle and kernels) ------------- */
+uint32_t coast_fault_sites(uint32_t kernel, uint32_t unit_bytes, uint32_t K);
+uint32_t coast_fault_site_bits(uint32_t kernel, uint32_t unit_bytes, uint32_t K, uint32_t site);
+uint32_t coast_out_bytes_per_unit(uint32_t kernel);
+uint32_t coast_votes_per_unit(uint32_t kernel);  /* sync points per unit at the SoR exit */
+
+/* --- thin memory helpers for pure-C callers (no torch) --------------- */
+int  coast_malloc(void** d_ptr, size_t bytes);
+int  coast_free(void* d_ptr);
+int  coast_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);
+int  coast_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
+int  coast_memset(void* d_dst, int byte, size_t bytes, void* stream);
+int  coast_host_alloc(void** h_ptr, size_t bytes);   /* pinned */
+int  coast_host_free(void* h_ptr);
+int  coast_stream_create(void** stream);
+int  coast_stream_destroy(void* stream);
+int  coast_stream_sync(void* stream);
+
+/* Deterministic synthetic input: dst[i] (u32) = Philox4x32-10(ctr={i/4 (+word_base/4), 0,0,0}, key={seed,0})[i%4].
+ * Same generator in oracle/ so CPU and GPU see identical bytes. */
+int  coast_fill_philox(void* d_dst, uint64_t n_words, uint64_t word_base, uint32_t seed, void* stream);
+
+/* --- host-buffer convenience: the reference-facing call -------------- */
+/* What the reference's protected function call becomes: host in -> H2D -> xMR kernel ->
+ * D2H -> host out, counters folded as coast_sync().  Chunked and double-buffered on two
+ * internal streams.  `h_in`/`h_out`/`h_aux` are HOST pointers here (pinned or pageable). */
+int  coast_run_host(const coast_launch_desc* desc_with_host_ptrs, coast_stats* out);
+
+/* The four reference entry points, callable from the UNCHANGED tests (the BOARD=b200
+ * make flow redirects their calls here).  Protection mode comes from
+ * coast_set_opt_passes() or the COAST_OPT_PASSES environment variable. */
+int  coast_set_opt_passes(const char* opt_passes);
+unsigned short coast_xmr_crc16(const unsigned char* data_p, unsigned char length);   /* crc16.c:21 */
+void coast_xmr_sha256_hash(unsigned char ctx_data[], uint32_t ctx_bitlen[], uint32_t ctx_state[],
+                           unsigned char data[], uint32_t len, unsigned char hash[]);   /* sha256_common_tmr.c:101 */
+void coast_xmr_aes_enc_dec(unsigned char* state, unsigned char* key, unsigned char dir); /* TI_aes_128.c:107 */
+void coast_xmr_matrix_multiply_u32(const uint32_t* f, const uint32_t* s, uint32_t* r, int side); /* mm_common_tmr.c:3 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COAST_RT_H_ */

@@ -1,0 +1,462 @@
+/*
+ * coast_oracle.c -- CPU oracle (TEST INFRASTRUCTURE ONLY; see coast_oracle.h).
+ *
+ * Every function cites the reference file:line it restates.  Paths are relative
+ * to the byuccl/coast checkout (commit 397a26e).
+ */
+#include "coast_oracle.h"
+
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ */
+/* Philox4x32-10                                                        */
+/* ------------------------------------------------------------------ */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void orc_fill_philox(uint32_t* dst, uint64_t n_words, uint64_t word_base, uint32_t seed) {
+    uint32_t key[2] = { seed, 0 };
+    uint32_t ctr[4] = { 0, 0, 0, 0 }, x[4];
+    uint64_t cur = ~(uint64_t)0;
+    for (uint64_t i = 0; i < n_words; ++i) {
+        uint64_t w = word_base + i, blk = w >> 2;
+        if (blk != cur) {
+            ctr[0] = (uint32_t)blk; ctr[1] = (uint32_t)(blk >> 32);
+            orc_philox4x32_10(ctr, key, x);
+            cur = blk;
+        }
+        dst[i] = x[w & 3];
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* Fault-site geometry and the per-unit fault decision                  */
+/* (fault model: simulation/platform/resources/injector.py:202-207 --   */
+/*  one single-bit flip `val ^ (1 << bit)` per run; a run = one unit)   */
+/* ------------------------------------------------------------------ */
+#define SHA_SITES_PER_BLOCK 536u /* 16 m[] + 64*8 working vars + 8 ctx_state */
+
+static uint32_t sha_blocks(uint32_t len) { return (len + 8u) / 64u + 1u; }
+
+uint32_t orc_fault_sites(uint32_t kernel, uint32_t unit_bytes, uint32_t K) {
+    switch (kernel) {
+    case ORC_K_CRC16:     return 2u * unit_bytes;
+    case ORC_K_SHA256:    return SHA_SITES_PER_BLOCK * sha_blocks(unit_bytes);
+    case ORC_K_AES128:    return 16u + 160u;
+    case ORC_K_MM_U32:    return K;
+    case ORC_K_GEMM_TF32: return 1u;
+    default:              return 0u;
+    }
+}
+
+uint32_t orc_fault_site_bits(uint32_t kernel, uint32_t unit_bytes, uint32_t K, uint32_t site) {
+    (void)K;
+    switch (kernel) {
+    case ORC_K_CRC16:  return site < unit_bytes ? 16u : 8u;
+    case ORC_K_AES128: return 8u;
+    default:           return 32u;
+    }
+}
+
+uint32_t orc_out_bytes_per_unit(uint32_t kernel) {
+    switch (kernel) {
+    case ORC_K_CRC16: return 2; case ORC_K_SHA256: return 32; case ORC_K_AES128: return 16;
+    case ORC_K_MM_U32: case ORC_K_GEMM_TF32: return 4; default: return 0;
+    }
+}
+
+/* One vote per output element OF THE C TYPE THE REFERENCE STORES:
+ * u16 crc (crc16.c:30), u8 digest byte (sha256_common_tmr.c:169-178),
+ * u8 state byte (TI_aes_128.c:226-229), mm_t element (mm_common_tmr.c:16). */
+uint32_t orc_votes_per_unit(uint32_t kernel) {
+    switch (kernel) {
+    case ORC_K_CRC16: return 1; case ORC_K_SHA256: return 32; case ORC_K_AES128: return 16;
+    case ORC_K_MM_U32: case ORC_K_GEMM_TF32: return 1; default: return 0;
+    }
+}
+
+void orc_fault_for_unit(const orc_plan* plan, uint32_t kernel, uint32_t num_clones, uint32_t unit_bytes,
+                        uint32_t K, uint64_t unit, uint64_t local, orc_fault* f) {
+    f->active = 0; f->replica = f->site = f->bit = 0;
+    if (!plan || plan->mode == ORC_PLAN_NONE) return;
+    uint32_t ns = orc_fault_sites(kernel, unit_bytes, K);
+    if (ns == 0) return;
+    if (plan->mode == ORC_PLAN_BERNOULLI) {
+        uint32_t ctr[4] = { (uint32_t)unit, (uint32_t)(unit >> 32), 0, 0 };
+        uint32_t key[2] = { plan->seed_lo, plan->seed_hi }, x[4];
+        orc_philox4x32_10(ctr, key, x);
+        if (x[0] >= plan->threshold) return;
+        f->replica = x[1] % num_clones;
+        f->site = x[2] % ns;
+        f->bit = x[3] % orc_fault_site_bits(kernel, unit_bytes, K, f->site);
+        f->active = 1;
+    } else if (plan->mode == ORC_PLAN_TABLE && plan->table) {
+        uint32_t e = plan->table[local];
+        if (!(e & 0x80000000u)) return;
+        uint32_t rep = (e >> 29) & 3u, site = (e >> 5) & 0xFFFFFFu, bit = e & 31u;
+        if (rep >= num_clones || site >= ns) return;
+        if (bit >= orc_fault_site_bits(kernel, unit_bytes, K, site)) return;
+        f->replica = rep; f->site = site; f->bit = bit; f->active = 1;
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* a1: crc16()  tests/crc16/crc16.c:21-31                               */
+/* ------------------------------------------------------------------ */
+uint16_t orc_crc16(const uint8_t* data, uint32_t len, const orc_fault* f) {
+    uint16_t crc = 0xFFFF;                                  /* crc16.c:23 */
+    for (uint32_t n = 0; n < len; ++n) {                    /* crc16.c:25 while (length--) */
+        uint8_t b = data[n];
+        if (f && f->active && f->site == len + n) b ^= (uint8_t)(1u << f->bit);
+        uint8_t x = (uint8_t)((crc >> 8) ^ b);              /* :26 (u8 truncation) */
+        x ^= (uint8_t)(x >> 4);                             /* :27 */
+        crc = (uint16_t)((uint16_t)(crc << 8) ^ (uint16_t)((uint16_t)x << 12) ^
+                         (uint16_t)((uint16_t)x << 5) ^ (uint16_t)x); /* :28 */
+        if (f && f->active && f->site == n) crc ^= (uint16_t)(1u << f->bit);
+    }
+    return crc;                                             /* :30, the voted `ret i16` */
+}
+
+/* ------------------------------------------------------------------ */
+/* a2/a3: sha256_transform / sha256_hash                                 */
+/*        tests/sha256_common/sha256_common_tmr.c:28-98, 101-180         */
+/* ------------------------------------------------------------------ */
+static const uint32_t SHA_K[64] = { /* FIPS 180-4 4.2.2; same values as sha256_common_tmr.c:8-19 */
+    0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
+    0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
+    0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau,
+    0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u,
+    0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u,
+    0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u,
+    0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
+    0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u };
+
+static inline uint32_t rotr32(uint32_t v, unsigned n) { return (v >> n) | (v << (32u - n)); }
+
+/* One compression; `blk` = index of this compression in the message (fault sites are
+ * numbered blk*536 + s). */
+static void sha_compress(uint32_t st[8], const uint8_t blk_bytes[64], uint32_t blk, const orc_fault* f) {
+    uint32_t m[64], v[8];
+    int has = f && f->active && (f->site / SHA_SITES_PER_BLOCK) == blk;
+    uint32_t s = has ? f->site % SHA_SITES_PER_BLOCK : 0xFFFFFFFFu;
+    uint32_t mask = has ? (1u << f->bit) : 0u;
+    for (int i = 0; i < 16; ++i)                            /* :34-40 big-endian pack */
+        m[i] = ((uint32_t)blk_bytes[4 * i] << 24) | ((uint32_t)blk_bytes[4 * i + 1] << 16) |
+               ((uint32_t)blk_bytes[4 * i + 2] << 8) | (uint32_t)blk_bytes[4 * i + 3];
+    if (s < 16u) m[s] ^= mask;
+    for (int i = 16; i < 64; ++i) {                         /* :42-58 */
+        uint32_t a = m[i - 2], b = m[i - 15];
+        uint32_t s1 = rotr32(a, 17) ^ rotr32(a, 19) ^ (a >> 10);
+        uint32_t s0 = rotr32(b, 7) ^ rotr32(b, 18) ^ (b >> 3);
+        m[i] = s1 + m[i - 7] + s0 + m[i - 16];
+    }
+    for (int i = 0; i < 8; ++i) v[i] = st[i];               /* :60-67 */
+    for (uint32_t t = 0; t < 64; ++t) {                     /* :69-88 */
+        if (s >= 16u && s < 528u && (s - 16u) / 8u == t) v[(s - 16u) % 8u] ^= mask;
+        uint32_t a = v[0], b = v[1], c = v[2], e = v[4], ff = v[5], g = v[6];
+        uint32_t ep0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+        uint32_t ep1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+        uint32_t ch = (e & ff) ^ (~e & g);
+        uint32_t maj = (a & b) ^ (a & c) ^ (b & c);
+        uint32_t t1 = v[7] + ep1 + ch + SHA_K[t] + m[t];
+        uint32_t t2 = ep0 + maj;
+        v[7] = g; v[6] = ff; v[5] = e; v[4] = v[3] + t1; v[3] = c; v[2] = b; v[1] = a; v[0] = t1 + t2;
+    }
+    for (int i = 0; i < 8; ++i) st[i] += v[i];              /* :90-97 */
+    if (s >= 528u && s < 536u) st[s - 528u] ^= mask;
+}
+
+void orc_sha256(const uint8_t* data, uint32_t len, uint8_t digest[32], const orc_fault* f) {
+    uint32_t st[8] = { 0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au,   /* :108-115 */
+                       0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u };
+    uint8_t buf[64];
+    uint32_t blk = 0, off = 0;
+    while (len - off >= 64u) {                              /* :119-127 (byte feed, transform each 64) */
+        sha_compress(st, data + off, blk++, f);
+        off += 64u;
+    }
+    uint32_t rem = len - off;                               /* ctx_datalen */
+    memcpy(buf, data + off, rem);
+    buf[rem] = 0x80;                                        /* :133 / :137 */
+    if (rem < 56u) {
+        memset(buf + rem + 1, 0, 55u - rem);                /* :134-135 */
+    } else {
+        memset(buf + rem + 1, 0, 63u - rem);                /* :138-139 */
+        sha_compress(st, buf, blk++, f);                    /* :140 */
+        memset(buf, 0, 56);                                 /* :142-151 */
+    }
+    /* :155-163: bitlen = 512*full_blocks + 8*rem as a 64-bit big-endian count
+     * (DBL_INT_ADD carries bitlen[0] overflow into bitlen[1]). */
+    uint64_t bits = (uint64_t)len * 8u;
+    for (int i = 0; i < 8; ++i) buf[63 - i] = (uint8_t)(bits >> (8 * i));
+    sha_compress(st, buf, blk++, f);                        /* :164 */
+    for (int w = 0; w < 8; ++w)                             /* :169-178 big-endian digest bytes */
+        for (int i = 0; i < 4; ++i) digest[4 * w + i] = (uint8_t)(st[w] >> (24 - 8 * i));
+}
+
+/* ------------------------------------------------------------------ */
+/* a5: aes_enc_dec()  tests/aes/TI_aes_128.c:107-231                     */
+/* Tables are GENERATED (FIPS-197 5.1.1: GF(2^8) inverse + affine map)   */
+/* rather than transcribed; they equal TI_aes_128.c:44-61,64-80,83-84.   */
+/* ------------------------------------------------------------------ */
+static uint8_t AES_S[256], AES_IS[256], AES_RC[10];
+static pthread_once_t aes_once = PTHREAD_ONCE_INIT;
+
+static uint8_t gf_xtime(uint8_t v) { return (uint8_t)((v << 1) ^ ((v & 0x80) ? 0x1b : 0)); } /* galois_mul2 :88-99 */
+static uint8_t gf_mul(uint8_t a, uint8_t b) {
+    uint8_t p = 0;
+    while (b) { if (b & 1) p ^= a; a = gf_xtime(a); b >>= 1; }
+    return p;
+}
+static void aes_tables(void) {
+    for (int x = 0; x < 256; ++x) {
+        uint8_t inv = 0;
+        if (x) for (int y = 1; y < 256; ++y) if (gf_mul((uint8_t)x, (uint8_t)y) == 1) { inv = (uint8_t)y; break; }
+        uint8_t s = inv, r = inv;
+        for (int i = 0; i < 4; ++i) { r = (uint8_t)((r << 1) | (r >> 7)); s ^= r; }
+        s ^= 0x63;
+        AES_S[x] = s; AES_IS[s] = (uint8_t)x;
+    }
+    uint8_t rc = 1;
+    for (int i = 0; i < 10; ++i) { AES_RC[i] = rc; rc = gf_xtime(rc); }
+}
+
+static void aes_key_fwd(uint8_t k[16], int round) {          /* :214-221 and :114-122 */
+    k[0] ^= AES_S[k[13]] ^ AES_RC[round];
+    k[1] ^= AES_S[k[14]];
+    k[2] ^= AES_S[k[15]];
+    k[3] ^= AES_S[k[12]];
+    for (int i = 4; i < 16; ++i) k[i] ^= k[i - 4];
+}
+static void aes_key_bwd(uint8_t k[16], int round) {          /* :134-141; `round` is the Rcon index */
+    for (int i = 15; i > 3; --i) k[i] ^= k[i - 4];
+    k[0] ^= AES_S[k[13]] ^ AES_RC[round];
+    k[1] ^= AES_S[k[14]];
+    k[2] ^= AES_S[k[15]];
+    k[3] ^= AES_S[k[12]];
+}
+static void aes_shift_rows(uint8_t s[16], int inverse) {     /* :147-166 / :187-206; state[4*col+row] */
+    uint8_t t[16];
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r) {
+            int src = inverse ? ((c - r) & 3) : ((c + r) & 3);
+            t[4 * c + r] = s[4 * src + r];
+        }
+    memcpy(s, t, 16);
+}
+static void aes_mix_columns(uint8_t s[16], int inverse) {    /* :169-184 (TI's inverse = pre-multiply trick :173-177) */
+    for (int c = 0; c < 4; ++c) {
+        uint8_t* p = s + 4 * c;
+        uint8_t a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3];
+        if (!inverse) {
+            p[0] = (uint8_t)(gf_mul(a0, 2) ^ gf_mul(a1, 3) ^ a2 ^ a3);
+            p[1] = (uint8_t)(a0 ^ gf_mul(a1, 2) ^ gf_mul(a2, 3) ^ a3);
+            p[2] = (uint8_t)(a0 ^ a1 ^ gf_mul(a2, 2) ^ gf_mul(a3, 3));
+            p[3] = (uint8_t)(gf_mul(a0, 3) ^ a1 ^ a2 ^ gf_mul(a3, 2));
+        } else {
+            p[0] = (uint8_t)(gf_mul(a0, 14) ^ gf_mul(a1, 11) ^ gf_mul(a2, 13) ^ gf_mul(a3, 9));
+            p[1] = (uint8_t)(gf_mul(a0, 9) ^ gf_mul(a1, 14) ^ gf_mul(a2, 11) ^ gf_mul(a3, 13));
+            p[2] = (uint8_t)(gf_mul(a0, 13) ^ gf_mul(a1, 9) ^ gf_mul(a2, 14) ^ gf_mul(a3, 11));
+            p[3] = (uint8_t)(gf_mul(a0, 11) ^ gf_mul(a1, 13) ^ gf_mul(a2, 9) ^ gf_mul(a3, 14));
+        }
+    }
+}
+
+void orc_aes128(uint8_t s[16], uint8_t key[16], int dir, const orc_fault* f) {
+    pthread_once(&aes_once, aes_tables);
+    int has = f && f->active;
+    uint8_t mask = has ? (uint8_t)(1u << f->bit) : 0;
+    if (has && f->site < 16u) s[f->site] ^= mask;            /* the replica's private copy of the input */
+    if (dir) {
+        for (int r = 0; r < 10; ++r) aes_key_fwd(key, r);    /* :112-123 reach the last round key */
+        for (int i = 0; i < 16; ++i) s[i] ^= key[i];         /* :126-128 */
+    }
+    for (int r = 0; r < 10; ++r) {                           /* :132 main loop */
+        if (dir) {
+            aes_key_bwd(key, 9 - r);                         /* :133-141 */
+            if (r > 0) aes_mix_columns(s, 1);                /* :169-184 with dir */
+            aes_shift_rows(s, 1);                            /* :187-206 */
+            for (int i = 0; i < 16; ++i) s[i] = (uint8_t)(AES_IS[s[i]] ^ key[i]); /* :208-211 */
+        } else {
+            for (int i = 0; i < 16; ++i) s[i] = AES_S[s[i] ^ key[i]];             /* :143-146 */
+            aes_shift_rows(s, 0);                            /* :147-166 */
+            if (r < 9) aes_mix_columns(s, 0);                /* :169-184 */
+            aes_key_fwd(key, r);                             /* :214-221 */
+        }
+        if (has && f->site >= 16u && (f->site - 16u) / 16u == (uint32_t)r) s[(f->site - 16u) % 16u] ^= mask;
+    }
+    if (!dir) for (int i = 0; i < 16; ++i) s[i] ^= key[i];   /* :224-229 */
+}
+
+/* ------------------------------------------------------------------ */
+/* a7: matrix_multiply()  tests/mm_common/mm_common_tmr.c:3-20,          */
+/*     tests/matrixMultiply/matrixMultiply.c:95-112                      */
+/* `sum` is an unsigned long truncated to mm_t/unsigned on store (:16 /  */
+/* :108): only its low 32 bits are observable, so it is kept mod 2^32.   */
+/* ------------------------------------------------------------------ */
+uint32_t orc_mm_u32_elem(const uint32_t* A, const uint32_t* B, uint32_t K, uint32_t N, uint32_t i, uint32_t j,
+                         const orc_fault* f) {
+    uint32_t sum = 0;
+    for (uint32_t k = 0; k < K; ++k) {
+        sum += A[(size_t)i * K + k] * B[(size_t)k * N + j];
+        if (f && f->active && f->site == k) sum ^= (1u << f->bit);
+    }
+    return sum;
+}
+
+/* BASELINE config 4 (fp32 on tensor cores): tcgen05 kind::tf32 reads the top 19 bits
+ * of each fp32 operand; accumulation order inside the tensor core is unspecified, so
+ * this is a TOLERANCE oracle (exact products of the truncated operands, summed in
+ * double, rounded once). */
+static float tf32_trunc(float v) {
+    uint32_t b; memcpy(&b, &v, 4); b &= 0xFFFFE000u; memcpy(&v, &b, 4); return v;
+}
+float orc_gemm_tf32_elem(const float* A, const float* B, uint32_t K, uint32_t N, uint32_t i, uint32_t j,
+                         const orc_fault* f) {
+    double acc = 0.0;
+    for (uint32_t k = 0; k < K; ++k)
+        acc += (double)tf32_trunc(A[(size_t)i * K + k]) * (double)tf32_trunc(B[(size_t)k * N + j]);
+    float r = (float)acc;
+    if (f && f->active && f->site == 0) { uint32_t b; memcpy(&b, &r, 4); b ^= (1u << f->bit); memcpy(&r, &b, 4); }
+    return r;
+}
+
+/* ------------------------------------------------------------------ */
+/* a9-a13: the protected region                                          */
+/* ------------------------------------------------------------------ */
+/* TMR voter, identical shape at all four sites (synchronization.cpp:439-448,
+ * 512-522, 631-642, 934-938):  cmp = (orig == clone1); vote = select cmp, orig, clone2.
+ * NOT a bitwise majority.  Error counter (insertTMRCorrectionCount :1354-1465):
+ * cmp2 = (orig == clone2) :1391; if !(cmp & cmp2) TMR_ERROR_CNT++ :1400,1428-1431.
+ * DWC (splitBlocks :1117-1192): if (orig != clone1) -> FAULT_DETECTED_DWC (:1299-1302). */
+static int elem_eq(const uint8_t* a, const uint8_t* b, uint32_t es, int is_float) {
+    if (is_float) { float x, y; memcpy(&x, a, 4); memcpy(&y, b, 4); return x == y; } /* fcmp oeq :57-62 */
+    return memcmp(a, b, es) == 0;                                                     /* icmp eq */
+}
+
+static void run_replica(const orc_desc* d, uint64_t local, const orc_fault* f, uint8_t* out) {
+    switch (d->kernel) {
+    case ORC_K_CRC16: {
+        uint16_t c = orc_crc16((const uint8_t*)d->in + local * d->unit_bytes, d->unit_bytes, f);
+        memcpy(out, &c, 2);
+    } break;
+    case ORC_K_SHA256:
+        orc_sha256((const uint8_t*)d->in + local * d->unit_bytes, d->unit_bytes, out, f);
+        break;
+    case ORC_K_AES128: {
+        uint8_t key[16];                       /* each replica mutates ITS copy of key[] (cloneGlobals, cloning.cpp:2417-2462) */
+        if (d->mode & ORC_AES_KEY_PER_UNIT) memcpy(key, (const uint8_t*)d->aux + local * 16, 16);
+        else memcpy(key, d->key, 16);
+        memcpy(out, (const uint8_t*)d->in + local * 16, 16);
+        orc_aes128(out, key, (d->mode & ORC_AES_DECRYPT) ? 1 : 0, f);
+    } break;
+    case ORC_K_MM_U32: {
+        uint32_t v = orc_mm_u32_elem((const uint32_t*)d->in, (const uint32_t*)d->aux, d->K, d->N,
+                                     (uint32_t)(local / d->N), (uint32_t)(local % d->N), f);
+        memcpy(out, &v, 4);
+    } break;
+    case ORC_K_GEMM_TF32: {
+        float v = orc_gemm_tf32_elem((const float*)d->in, (const float*)d->aux, d->K, d->N,
+                                     (uint32_t)(local / d->N), (uint32_t)(local % d->N), f);
+        memcpy(out, &v, 4);
+    } break;
+    default: break;
+    }
+}
+
+int orc_run_range(const orc_desc* d, uint64_t u0, uint64_t u1, orc_stats* st) {
+    if (!d || d->num_clones < 1 || d->num_clones > 3 || d->kernel > ORC_K_GEMM_TF32) return -1;
+    const uint32_t ob = orc_out_bytes_per_unit(d->kernel);
+    const uint32_t nv = orc_votes_per_unit(d->kernel);
+    const uint32_t es = ob / nv;
+    const int is_float = d->kernel == ORC_K_GEMM_TF32;
+    const uint32_t nc = d->num_clones;
+    const orc_fault none = { 0, 0, 0, 0 };
+    for (uint64_t local = u0; local < u1; ++local) {
+        orc_fault f;
+        orc_fault_for_unit(d->plan, d->kernel, nc, d->unit_bytes, d->K, d->unit_base + local, local, &f);
+        if (f.active) st->injected++;
+        uint8_t rep[3][32];
+        for (uint32_t r = 0; r < nc; ++r) run_replica(d, local, (f.active && f.replica == r) ? &f : &none, rep[r]);
+        uint8_t* out = (uint8_t*)d->out + local * ob;
+        int disagree = 0;
+        if (nc == 1) {
+            memcpy(out, rep[0], ob);
+        } else if (nc == 2) {
+            for (uint32_t e = 0; e < nv; ++e)
+                if (!elem_eq(rep[0] + e * es, rep[1] + e * es, es, is_float)) disagree = 1;
+            memcpy(out, rep[0], ob);            /* compare passes -> the original's store proceeds */
+            if (disagree) st->dwc_detected++;
+        } else {
+            for (uint32_t e = 0; e < nv; ++e) {
+                const uint8_t *r0 = rep[0] + e * es, *r1 = rep[1] + e * es, *r2 = rep[2] + e * es;
+                int c01 = elem_eq(r0, r1, es, is_float), c02 = elem_eq(r0, r2, es, is_float);
+                if (d->flags & ORC_F_MAJORITY) {
+                    for (uint32_t b = 0; b < es; ++b)
+                        out[e * es + b] = (uint8_t)((r0[b] & r1[b]) | (r0[b] & r2[b]) | (r1[b] & r2[b]));
+                } else {
+                    memcpy(out + e * es, c01 ? r0 : r2, es);
+                }
+                if (!(c01 && c02)) {
+                    disagree = 1;
+                    if (d->flags & ORC_F_COUNT_ERRORS) st->errors_corrected++;
+                }
+            }
+            /* __SYNC_COUNT++ is emitted inside insertTMRCorrectionCount (:1415-1425), i.e. only
+             * for TMR with -countErrors. */
+            if ((d->flags & ORC_F_COUNT_SYNCS) && (d->flags & ORC_F_COUNT_ERRORS)) st->syncs += nv;
+        }
+        if (disagree && d->unit_base + local < st->first_fault_unit) st->first_fault_unit = d->unit_base + local;
+    }
+    return 0;
+}
+
+int orc_run(const orc_desc* d, orc_stats* st) { return orc_run_range(d, 0, d ? d->n_units : 0, st); }
+
+typedef struct { const orc_desc* d; uint64_t u0, u1; orc_stats st; int rc; } mt_arg;
+static void* mt_main(void* p) {
+    mt_arg* a = (mt_arg*)p;
+    a->rc = orc_run_range(a->d, a->u0, a->u1, &a->st);
+    return NULL;
+}
+int orc_run_mt(const orc_desc* d, int n_threads, orc_stats* st) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    pthread_once(&aes_once, aes_tables);
+    pthread_t th[256]; mt_arg args[256];
+    uint64_t per = (d->n_units + (uint64_t)n_threads - 1) / (uint64_t)n_threads;
+    for (int t = 0; t < n_threads; ++t) {
+        uint64_t u0 = per * (uint64_t)t, u1 = u0 + per;
+        if (u0 > d->n_units) u0 = d->n_units;
+        if (u1 > d->n_units) u1 = d->n_units;
+        args[t].d = d; args[t].u0 = u0; args[t].u1 = u1; args[t].rc = 0;
+        memset(&args[t].st, 0, sizeof(orc_stats)); args[t].st.first_fault_unit = ~(uint64_t)0;
+        pthread_create(&th[t], NULL, mt_main, &args[t]);
+    }
+    int rc = 0;
+    for (int t = 0; t < n_threads; ++t) {
+        pthread_join(th[t], NULL);
+        if (args[t].rc) rc = args[t].rc;
+        st->errors_corrected += args[t].st.errors_corrected;
+        st->dwc_detected += args[t].st.dwc_detected;
+        st->syncs += args[t].st.syncs;
+        st->injected += args[t].st.injected;
+        if (args[t].st.first_fault_unit < st->first_fault_unit) st->first_fault_unit = args[t].st.first_fault_unit;
+    }
+    return rc;
+}
