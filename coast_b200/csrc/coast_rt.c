@@ -1,0 +1,574 @@
+/*
+ * coast_rt.c -- host side of libcoast_rt.so (plain C over the CUDA DRIVER API).
+ *
+ * Replaces, at run time, what byuccl/coast does at compile time:
+ *   projects/dataflowProtection (run(M, numClones), dataflowProtection.cpp:63-164),
+ *   projects/TMR (TMR.cpp:29-36) and projects/DWC (DWC.cpp:29-36)
+ * by launching a hand-written sm_100a kernel in which every live value of the protected
+ * region is computed by num_clones replicas and voted at the SoR exit.
+ *
+ * libcuda.so.1 is bound lazily with dlopen() so that this library LOADS without a GPU
+ * (the CPU CI box) -- every compute entry point then returns COAST_ERR_NO_DRIVER.  There
+ * is deliberately NO CPU implementation of the workloads in this file.
+ */
+#define _GNU_SOURCE
+#include "../../include/coast_rt.h"
+#include "xmr_args.h"
+
+#include <cuda.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+extern const unsigned char coast_kernels_cubin[];   /* generated: bin2c of coast_kernels.cubin */
+
+/* ------------------------------------------------------------------ */
+/* the reference's run-time symbols                                     */
+/* ------------------------------------------------------------------ */
+__attribute__((weak)) uint32_t TMR_ERROR_CNT = 0;    /* synchronization.cpp:269-291 */
+__attribute__((weak)) uint64_t __SYNC_COUNT = 0;     /* synchronization.cpp:103-121 */
+__attribute__((weak)) void FAULT_DETECTED_DWC(void) { /* synchronization.cpp:1251-1266: default handler = abort() */
+    fprintf(stderr, "coast_rt: DWC mismatch detected -> FAULT_DETECTED_DWC -> abort()\n");
+    abort();
+}
+
+/* ------------------------------------------------------------------ */
+/* driver API binding                                                   */
+/* ------------------------------------------------------------------ */
+#define DRV_FUNCS(X)                                                                                         \
+    X(cuInit, (unsigned int))                                                                                \
+    X(cuDeviceGet, (CUdevice*, int))                                                                         \
+    X(cuDeviceGetAttribute, (int*, CUdevice_attribute, CUdevice))                                            \
+    X(cuDevicePrimaryCtxRetain, (CUcontext*, CUdevice))                                                      \
+    X(cuDevicePrimaryCtxRelease_v2, (CUdevice))                                                              \
+    X(cuCtxSetCurrent, (CUcontext))                                                                          \
+    X(cuCtxGetCurrent, (CUcontext*))                                                                         \
+    X(cuModuleLoadData, (CUmodule*, const void*))                                                            \
+    X(cuModuleUnload, (CUmodule))                                                                            \
+    X(cuModuleGetFunction, (CUfunction*, CUmodule, const char*))                                             \
+    X(cuFuncSetAttribute, (CUfunction, CUfunction_attribute, int))                                           \
+    X(cuOccupancyMaxActiveBlocksPerMultiprocessor, (int*, CUfunction, int, size_t))                          \
+    X(cuLaunchKernel, (CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,     \
+                       CUstream, void**, void**))                                                            \
+    X(cuMemAlloc_v2, (CUdeviceptr*, size_t))                                                                 \
+    X(cuMemFree_v2, (CUdeviceptr))                                                                           \
+    X(cuMemcpyHtoDAsync_v2, (CUdeviceptr, const void*, size_t, CUstream))                                    \
+    X(cuMemcpyDtoHAsync_v2, (void*, CUdeviceptr, size_t, CUstream))                                          \
+    X(cuMemcpyDtoDAsync_v2, (CUdeviceptr, CUdeviceptr, size_t, CUstream))                                    \
+    X(cuMemsetD8Async, (CUdeviceptr, unsigned char, size_t, CUstream))                                       \
+    X(cuMemHostAlloc, (void**, size_t, unsigned int))                                                        \
+    X(cuMemFreeHost, (void*))                                                                                \
+    X(cuStreamCreate, (CUstream*, unsigned int))                                                             \
+    X(cuStreamDestroy_v2, (CUstream))                                                                        \
+    X(cuStreamSynchronize, (CUstream))                                                                       \
+    X(cuGetErrorString, (CUresult, const char**))                                                            \
+    X(cuTensorMapEncodeTiled, (CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,      \
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, \
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill))
+
+#define X(name, args) static CUresult(CUDAAPI* p_##name) args;
+DRV_FUNCS(X)
+#undef X
+
+#define MAX_FN 128
+static struct {
+    int inited;
+    void* libcuda;
+    int device;
+    CUdevice dev;
+    CUcontext ctx;
+    CUmodule mod;
+    int sm_count;
+    CUdeviceptr counters;            /* XMR_CTR_COUNT x u64 */
+    uint64_t* h_counters;            /* pinned mirror */
+    struct { char name[64]; CUfunction fn; int ctas_per_sm; unsigned smem; } fns[MAX_FN];
+    int n_fns;
+    char err[512];
+    /* protection mode of the four reference entry points (coast_set_opt_passes / COAST_OPT_PASSES) */
+    uint32_t def_nc, def_flags; int def_set;
+    /* coast_run_host scratch: 3 slots */
+    CUstream hs[3]; CUdeviceptr h_in[3], h_out[3], h_aux[3]; size_t h_in_cap[3], h_out_cap[3], h_aux_cap[3];
+} G;
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(G.err, sizeof G.err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int drv_fail(CUresult r, const char* what) {
+    const char* s = NULL;
+    if (p_cuGetErrorString) p_cuGetErrorString(r, &s);
+    return fail(-(int)r, "%s: CUDA error %d (%s)", what, (int)r, s ? s : "?");
+}
+#define DRV(call) do { CUresult r_ = (call); if (r_ != CUDA_SUCCESS) return drv_fail(r_, #call); } while (0)
+
+const char* coast_last_error(void) { return G.err; }
+const char* coast_version(void) { return "coast_rt 0.1 (sm_100a)"; }
+
+static int bind_driver(void) {
+    if (G.libcuda) return COAST_OK;
+    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(COAST_ERR_NO_DRIVER, "libcuda.so.1 not found (%s): no GPU driver on this machine; "
+                                              "libcoast_rt has no CPU fallback", dlerror());
+#define X(name, args)                                                                 \
+    *(void**)(&p_##name) = dlsym(h, #name);                                           \
+    if (!p_##name) { dlclose(h); return fail(COAST_ERR_NO_DRIVER, "libcuda lacks %s", #name); }
+    DRV_FUNCS(X)
+#undef X
+    G.libcuda = h;
+    return COAST_OK;
+}
+
+static int ensure_ctx(void) {
+    if (!G.inited) return fail(COAST_ERR_NOT_INIT, "coast_init() has not been called");
+    CUcontext cur = NULL;
+    p_cuCtxGetCurrent(&cur);
+    if (cur != G.ctx) DRV(p_cuCtxSetCurrent(G.ctx));
+    return COAST_OK;
+}
+
+static int get_fn(const char* name, unsigned smem, CUfunction* fn, int* ctas_per_sm) {
+    for (int i = 0; i < G.n_fns; ++i)
+        if (!strcmp(G.fns[i].name, name) && G.fns[i].smem == smem) { *fn = G.fns[i].fn; if (ctas_per_sm) *ctas_per_sm = G.fns[i].ctas_per_sm; return COAST_OK; }
+    CUfunction f;
+    CUresult r = p_cuModuleGetFunction(&f, G.mod, name);
+    if (r != CUDA_SUCCESS) return drv_fail(r, name);
+    if (smem > 48 * 1024) DRV(p_cuFuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
+    int occ = 1;
+    DRV(p_cuOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f, XMR_CTA_THREADS, smem));
+    if (occ < 1) occ = 1;
+    if (G.n_fns < MAX_FN) {
+        snprintf(G.fns[G.n_fns].name, sizeof G.fns[0].name, "%s", name);
+        G.fns[G.n_fns].fn = f; G.fns[G.n_fns].ctas_per_sm = occ; G.fns[G.n_fns].smem = smem;
+        G.n_fns++;
+    }
+    *fn = f; if (ctas_per_sm) *ctas_per_sm = occ;
+    return COAST_OK;
+}
+
+static int launch_small(const char* name, unsigned grid, unsigned block, void** params, CUstream s) {
+    CUfunction f; int rc = get_fn(name, 0, &f, NULL);
+    if (rc) return rc;
+    DRV(p_cuLaunchKernel(f, grid, 1, 1, block, 1, 1, 0, s, params, NULL));
+    return COAST_OK;
+}
+
+int coast_stats_reset(void* stream) {
+    int rc = ensure_ctx(); if (rc) return rc;
+    void* params[] = { &G.counters };
+    return launch_small("xmr_counters_reset", 1, 32, params, (CUstream)stream);
+}
+
+int coast_init(int device) {
+    if (G.inited) {
+        if (device == G.device) return ensure_ctx();
+        return fail(COAST_ERR_BAD_ARG, "coast_rt already initialised on device %d", G.device);
+    }
+    int rc = bind_driver(); if (rc) return rc;
+    CUresult r = p_cuInit(0);
+    if (r != CUDA_SUCCESS) { drv_fail(r, "cuInit"); return COAST_ERR_NO_DRIVER; }
+    DRV(p_cuDeviceGet(&G.dev, device));
+    DRV(p_cuDevicePrimaryCtxRetain(&G.ctx, G.dev));      /* shared with the CUDA runtime / torch */
+    DRV(p_cuCtxSetCurrent(G.ctx));
+    int major = 0, minor = 0;
+    p_cuDeviceGetAttribute(&major, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MAJOR, G.dev);
+    p_cuDeviceGetAttribute(&minor, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR, G.dev);
+    if (major != 10) {
+        p_cuDevicePrimaryCtxRelease_v2(G.dev);
+        return fail(COAST_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library carries sm_100a code only", device, major, minor);
+    }
+    p_cuDeviceGetAttribute(&G.sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, G.dev);
+    r = p_cuModuleLoadData(&G.mod, coast_kernels_cubin);
+    if (r != CUDA_SUCCESS) { p_cuDevicePrimaryCtxRelease_v2(G.dev); return drv_fail(r, "cuModuleLoadData(sm_100a cubin)"); }
+    DRV(p_cuMemAlloc_v2(&G.counters, XMR_CTR_COUNT * sizeof(uint64_t)));
+    DRV(p_cuMemHostAlloc((void**)&G.h_counters, XMR_CTR_COUNT * sizeof(uint64_t), 0));
+    G.device = device;
+    G.inited = 1;
+    rc = coast_stats_reset(NULL); if (rc) return rc;
+    DRV(p_cuStreamSynchronize(NULL));
+    const char* env = getenv("COAST_OPT_PASSES");
+    if (env && !G.def_set) coast_set_opt_passes(env);
+    return COAST_OK;
+}
+
+int coast_shutdown(void) {
+    if (!G.inited) return COAST_OK;
+    ensure_ctx();
+    for (int i = 0; i < 3; ++i) {
+        if (G.h_in[i]) p_cuMemFree_v2(G.h_in[i]);
+        if (G.h_out[i]) p_cuMemFree_v2(G.h_out[i]);
+        if (G.h_aux[i]) p_cuMemFree_v2(G.h_aux[i]);
+        if (G.hs[i]) p_cuStreamDestroy_v2(G.hs[i]);
+        G.h_in[i] = G.h_out[i] = G.h_aux[i] = 0; G.h_in_cap[i] = G.h_out_cap[i] = G.h_aux_cap[i] = 0; G.hs[i] = NULL;
+    }
+    p_cuMemFree_v2(G.counters);
+    p_cuMemFreeHost(G.h_counters);
+    p_cuModuleUnload(G.mod);
+    p_cuDevicePrimaryCtxRelease_v2(G.dev);
+    G.inited = 0; G.n_fns = 0;
+    return COAST_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* OPT_PASSES front end (dataflowProtection.cpp:14-47 cl::opt names)     */
+/* ------------------------------------------------------------------ */
+int coast_parse_opt_passes(const char* s, uint32_t* num_clones, uint32_t* flags) {
+    uint32_t nc = COAST_UNPROTECTED, fl = 0; int tmr = 0, dwc = 0;
+    if (!s) s = "";
+    char buf[1024]; snprintf(buf, sizeof buf, "%s", s);
+    for (char* tok = strtok(buf, " \t\r\n"); tok; tok = strtok(NULL, " \t\r\n")) {
+        if (tok[0] == '#') break;                            /* rest of a Makefile line comment */
+        if (!strcmp(tok, "-TMR")) tmr = 1;
+        else if (!strcmp(tok, "-DWC")) dwc = 1;
+        else if (!strcmp(tok, "-countErrors")) fl |= COAST_F_COUNT_ERRORS;
+        else if (!strcmp(tok, "-countSyncs")) fl |= COAST_F_COUNT_SYNCS;
+        else if (!strcmp(tok, "-noMemReplication")) fl |= COAST_F_NO_MEM_REPLICATION;
+        else if (!strcmp(tok, "-i")) fl |= COAST_F_INTERLEAVE;
+        else if (!strcmp(tok, "-s")) fl |= COAST_F_SEGMENT;
+        else if (!strcmp(tok, "-verbose")) fl |= COAST_F_VERBOSE;
+        else if (!strcmp(tok, "-reportErrors")) {
+            fl |= COAST_F_REPORT_ERRORS_LEGACY;
+            fprintf(stderr, "coast_rt: -reportErrors is deprecated in the reference (counts AGREEING syncs, "
+                            "synchronization.cpp:1323-1350) and is not emulated; use -countErrors\n");
+        }
+        /* since v1.2 these are the default / no-ops on this path (passes.rst:337, synchronization.cpp:211-215) */
+        else if (!strcmp(tok, "-noLoadSync") || !strcmp(tok, "-noStoreDataSync") || !strcmp(tok, "-noStoreAddrSync")) { }
+        else fprintf(stderr, "coast_rt: OPT_PASSES token '%s' has no effect on the B200 runtime (ignored)\n", tok);
+    }
+    if (tmr && dwc) return fail(COAST_ERR_BAD_ARG, "-TMR and -DWC are mutually exclusive");
+    if (tmr) nc = COAST_TMR; else if (dwc) nc = COAST_DWC;
+    if (num_clones) *num_clones = nc;
+    if (flags) *flags = fl;
+    return COAST_OK;
+}
+
+int coast_set_opt_passes(const char* s) {
+    uint32_t nc, fl; int rc = coast_parse_opt_passes(s, &nc, &fl);
+    if (rc) return rc;
+    G.def_nc = nc; G.def_flags = fl; G.def_set = 1;
+    return COAST_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* geometry shared with oracle/ by specification            */
+/* ------------------------------------------------------------------ */
+static uint32_t sha_blocks(uint32_t len) { return (len + 8u) / 64u + 1u; }
+
+uint32_t coast_fault_sites(uint32_t kernel, uint32_t unit_bytes, uint32_t K) {
+    switch (kernel) {
+    case COAST_K_CRC16:     return 2u * unit_bytes;
+    case COAST_K_SHA256:    return 536u * sha_blocks(unit_bytes);
+    case COAST_K_AES128:    return 176u;
+    case COAST_K_MM_U32:    return K;
+    case COAST_K_GEMM_TF32: return 1u;
+    default:                return 0u;
+    }
+}
+uint32_t coast_fault_site_bits(uint32_t kernel, uint32_t unit_bytes, uint32_t K, uint32_t site) {
+    (void)K;
+    if (kernel == COAST_K_CRC16) return site < unit_bytes ? 16u : 8u;
+    if (kernel == COAST_K_AES128) return 8u;
+    return 32u;
+}
+uint32_t coast_out_bytes_per_unit(uint32_t kernel) {
+    static const uint32_t ob[COAST_K_COUNT_] = { 2, 32, 16, 4, 4 };
+    return kernel < COAST_K_COUNT_ ? ob[kernel] : 0;
+}
+uint32_t coast_votes_per_unit(uint32_t kernel) {
+    static const uint32_t nv[COAST_K_COUNT_] = { 1, 32, 16, 1, 1 };
+    return kernel < COAST_K_COUNT_ ? nv[kernel] : 0;
+}
+static uint64_t in_bytes_per_unit(const coast_launch_desc* d) {
+    switch (d->kernel) {
+    case COAST_K_CRC16: case COAST_K_SHA256: return d->unit_bytes;
+    case COAST_K_AES128: return 16;
+    default: return 0;
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* the launch                                                           */
+/* ------------------------------------------------------------------ */
+static unsigned ring_smem(unsigned tile_rows, unsigned row_bytes) {
+    unsigned tile = tile_rows * row_bytes;
+    unsigned stride = (tile + 1023u) & ~1023u;
+    return XMR_STAGES * stride + 64u;
+}
+
+static int encode_rows_map(CUtensorMap* map, const void* base, uint32_t row_bytes, uint64_t rows, uint32_t box_rows,
+                           CUtensorMapSwizzle swz) {
+    cuuint64_t gdim[2] = { row_bytes / 4u, rows };
+    cuuint64_t gstr[1] = { row_bytes };
+    cuuint32_t box[2] = { row_bytes / 4u, box_rows };
+    cuuint32_t estr[2] = { 1, 1 };
+    DRV(p_cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)base, gdim, gstr, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+    return COAST_OK;
+}
+
+int coast_launch(const coast_launch_desc* d, void* stream) {
+    int rc = ensure_ctx(); if (rc) return rc;
+    if (!d) return fail(COAST_ERR_BAD_ARG, "null descriptor");
+    if (d->kernel >= COAST_K_COUNT_) return fail(COAST_ERR_BAD_ARG, "unknown kernel id %u", d->kernel);
+    if (d->num_clones < 1 || d->num_clones > 3) return fail(COAST_ERR_BAD_ARG, "num_clones must be 1, 2 (DWC) or 3 (TMR)");
+    if (d->n_units == 0) return COAST_OK;
+    if (!d->d_in || !d->d_out) return fail(COAST_ERR_BAD_ARG, "null device buffer");
+    const uint32_t nc = d->num_clones;
+    const uint32_t upw = 32u / nc;
+    const int inj = d->plan && d->plan->mode != COAST_PLAN_NONE;
+
+    xmr_args a; memset(&a, 0, sizeof a);
+    a.in = d->d_in; a.out = d->d_out; a.aux = d->d_aux;
+    a.n_units = d->n_units; a.unit_base = d->unit_base;
+    a.counters = (unsigned long long*)G.counters;
+    a.unit_bytes = d->unit_bytes; a.flags = d->flags; a.mode = d->mode;
+    a.M = d->M; a.N = d->N; a.K = d->K;
+    memcpy(a.key, d->key, 16);
+    if (inj) {
+        a.plan_mode = d->plan->mode; a.seed_lo = d->plan->seed_lo; a.seed_hi = d->plan->seed_hi;
+        a.threshold = d->plan->threshold; a.plan_table = (const unsigned int*)d->plan->d_table;
+        if (a.plan_mode == COAST_PLAN_TABLE && !a.plan_table) return fail(COAST_ERR_BAD_ARG, "TABLE plan without d_table");
+        if (a.plan_mode > COAST_PLAN_TABLE) return fail(COAST_ERR_BAD_ARG, "unknown fault plan mode %u", a.plan_mode);
+    }
+    a.n_sites = coast_fault_sites(d->kernel, d->unit_bytes, d->K);
+
+    char name[64];
+    unsigned smem = 0; int tma = 0;
+    unsigned tile_rows = 0, row_bytes = 0; CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_NONE;
+    const int aligned16 = (((uintptr_t)d->d_in) & 15u) == 0;
+    switch (d->kernel) {
+    case COAST_K_SHA256:
+        if (d->unit_bytes == 64 && aligned16 && d->n_units < 0x7FFFFF00ull) {
+            tma = 1; tile_rows = XMR_WARPS * upw; row_bytes = 64; swz = CU_TENSOR_MAP_SWIZZLE_64B;
+            smem = ring_smem(tile_rows, row_bytes);
+            snprintf(name, sizeof name, "xmr_sha256_b64_nc%u_inj%d", nc, inj);
+        } else {
+            snprintf(name, sizeof name, "xmr_sha256_gen_nc%u_inj%d", nc, inj);
+        }
+        break;
+    case COAST_K_CRC16:
+        if (d->unit_bytes < 1 || d->unit_bytes > 255) return fail(COAST_ERR_BAD_ARG, "crc16 length is an unsigned char (1..255)");
+        if (d->unit_bytes == 64 && aligned16 && d->n_units < 0x7FFFFF00ull) {
+            tma = 1; tile_rows = XMR_WARPS * upw; row_bytes = 64; swz = CU_TENSOR_MAP_SWIZZLE_64B;
+            smem = ring_smem(tile_rows, row_bytes);
+            snprintf(name, sizeof name, "xmr_crc16_b64_nc%u_inj%d", nc, inj);
+        } else {
+            snprintf(name, sizeof name, "xmr_crc16_gen_nc%u_inj%d", nc, inj);
+        }
+        break;
+    case COAST_K_AES128:
+        if ((d->mode & COAST_AES_KEY_PER_UNIT) && !d->d_aux) return fail(COAST_ERR_BAD_ARG, "per-unit keys need d_aux");
+        if (!aligned16 || (((uintptr_t)d->d_out) & 15u)) return fail(COAST_ERR_BAD_ARG, "AES buffers must be 16-byte aligned");
+        if (!(d->mode & (COAST_AES_DECRYPT | COAST_AES_KEY_PER_UNIT)) && d->n_units < 0x7FFFFF00ull) {
+            tma = 1; tile_rows = XMR_WARPS * upw * 4u; row_bytes = 16;
+            unsigned ring = ring_smem(tile_rows, row_bytes);
+            smem = ((ring + 1023u) & ~1023u) + 256u * 32u * 4u;
+            snprintf(name, sizeof name, "xmr_aes128_enc_nc%u_inj%d", nc, inj);
+        } else {
+            snprintf(name, sizeof name, "xmr_aes128_gen_nc%u_inj%d", nc, inj);
+        }
+        break;
+    case COAST_K_MM_U32:
+        if (!d->d_aux || !d->M || !d->N || !d->K) return fail(COAST_ERR_BAD_ARG, "MM needs A (d_in), B (d_aux) and M,N,K");
+        if (d->n_units != (uint64_t)d->M * d->N) return fail(COAST_ERR_BAD_ARG, "MM: n_units must be M*N");
+        snprintf(name, sizeof name, "xmr_mm_u32_nc%u_inj%d", nc, inj);
+        break;
+    default:
+        return fail(COAST_ERR_UNSUPPORTED, "kernel %u is not built into this library yet", d->kernel);
+    }
+    if (d->kernel == COAST_K_SHA256 && (((uintptr_t)d->d_out) & 15u)) return fail(COAST_ERR_BAD_ARG, "SHA output must be 16-byte aligned");
+
+    CUfunction fn; int occ = 1;
+    rc = get_fn(name, smem, &fn, &occ); if (rc) return rc;
+    unsigned grid;
+    CUtensorMap map;
+    void* params[2] = { &a, &map };
+    if (tma) {
+        uint64_t n_tiles = (d->n_units + tile_rows - 1) / tile_rows;
+        a.n_tiles = (unsigned)n_tiles;
+        unsigned loads = (tile_rows + 255u) / 256u;
+        rc = encode_rows_map(&map, d->d_in, row_bytes, d->n_units, tile_rows / loads, swz); if (rc) return rc;
+        uint64_t cap = (uint64_t)G.sm_count * (unsigned)occ;
+        grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
+    } else {
+        uint64_t warps = (d->n_units + upw - 1) / upw;
+        uint64_t ctas = (warps + XMR_WARPS - 1) / XMR_WARPS;
+        uint64_t cap = (uint64_t)G.sm_count * (unsigned)occ * 4u;
+        grid = (unsigned)(ctas < cap ? ctas : cap);
+    }
+    if (d->flags & COAST_F_VERBOSE)
+        fprintf(stderr, "coast_rt: %s grid=%u block=%d smem=%u units=%llu\n", name, grid, XMR_CTA_THREADS, smem,
+                (unsigned long long)d->n_units);
+    DRV(p_cuLaunchKernel(fn, grid, 1, 1, XMR_CTA_THREADS, 1, 1, smem, (CUstream)stream, params, NULL));
+    return COAST_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* counters                                                             */
+/* ------------------------------------------------------------------ */
+static int sync_impl(void* stream, coast_stats* out, int call_handler) {
+    int rc = ensure_ctx(); if (rc) return rc;
+    DRV(p_cuMemcpyDtoHAsync_v2(G.h_counters, G.counters, XMR_CTR_COUNT * sizeof(uint64_t), (CUstream)stream));
+    rc = coast_stats_reset(stream); if (rc) return rc;
+    DRV(p_cuStreamSynchronize((CUstream)stream));
+    coast_stats st;
+    st.errors_corrected = G.h_counters[XMR_CTR_ERRORS];
+    st.dwc_detected = G.h_counters[XMR_CTR_DWC];
+    st.syncs = G.h_counters[XMR_CTR_SYNCS];
+    st.injected = G.h_counters[XMR_CTR_INJECTED];
+    st.first_fault_unit = G.h_counters[XMR_CTR_FIRST];
+    TMR_ERROR_CNT += (uint32_t)st.errors_corrected;          /* i32 wrap, synchronization.cpp:1428-1431 */
+    __SYNC_COUNT += st.syncs;
+    if (out) *out = st;
+    if (call_handler && st.dwc_detected) FAULT_DETECTED_DWC();   /* synchronization.cpp:1299-1302 */
+    return COAST_OK;
+}
+int coast_sync(void* stream, coast_stats* out) { return sync_impl(stream, out, 1); }
+int coast_sync_noabort(void* stream, coast_stats* out) { return sync_impl(stream, out, 0); }
+
+int coast_stats_snapshot(void* stream, void* d_stats_out) {
+    int rc = ensure_ctx(); if (rc) return rc;
+    if (!d_stats_out) return fail(COAST_ERR_BAD_ARG, "null d_stats_out");
+    DRV(p_cuMemcpyDtoDAsync_v2((CUdeviceptr)d_stats_out, G.counters, XMR_CTR_COUNT * sizeof(uint64_t), (CUstream)stream));
+    return COAST_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* memory / streams / synthetic data                                    */
+/* ------------------------------------------------------------------ */
+int coast_malloc(void** p, size_t bytes) { int rc = ensure_ctx(); if (rc) return rc; CUdeviceptr d; DRV(p_cuMemAlloc_v2(&d, bytes ? bytes : 1)); *p = (void*)d; return COAST_OK; }
+int coast_free(void* p) { int rc = ensure_ctx(); if (rc) return rc; if (p) DRV(p_cuMemFree_v2((CUdeviceptr)p)); return COAST_OK; }
+int coast_memcpy_h2d(void* d, const void* h, size_t n, void* s) { int rc = ensure_ctx(); if (rc) return rc; DRV(p_cuMemcpyHtoDAsync_v2((CUdeviceptr)d, h, n, (CUstream)s)); return COAST_OK; }
+int coast_memcpy_d2h(void* h, const void* d, size_t n, void* s) { int rc = ensure_ctx(); if (rc) return rc; DRV(p_cuMemcpyDtoHAsync_v2(h, (CUdeviceptr)d, n, (CUstream)s)); return COAST_OK; }
+int coast_memset(void* d, int byte, size_t n, void* s) { int rc = ensure_ctx(); if (rc) return rc; DRV(p_cuMemsetD8Async((CUdeviceptr)d, (unsigned char)byte, n, (CUstream)s)); return COAST_OK; }
+int coast_host_alloc(void** h, size_t n) { int rc = ensure_ctx(); if (rc) return rc; DRV(p_cuMemHostAlloc(h, n ? n : 1, 0)); return COAST_OK; }
+int coast_host_free(void* h) { int rc = ensure_ctx(); if (rc) return rc; if (h) DRV(p_cuMemFreeHost(h)); return COAST_OK; }
+int coast_stream_create(void** s) { int rc = ensure_ctx(); if (rc) return rc; CUstream st; DRV(p_cuStreamCreate(&st, CU_STREAM_NON_BLOCKING)); *s = st; return COAST_OK; }
+int coast_stream_destroy(void* s) { int rc = ensure_ctx(); if (rc) return rc; DRV(p_cuStreamDestroy_v2((CUstream)s)); return COAST_OK; }
+int coast_stream_sync(void* s) { int rc = ensure_ctx(); if (rc) return rc; DRV(p_cuStreamSynchronize((CUstream)s)); return COAST_OK; }
+
+int coast_fill_philox(void* d_dst, uint64_t n_words, uint64_t word_base, uint32_t seed, void* stream) {
+    int rc = ensure_ctx(); if (rc) return rc;
+    if (!n_words) return COAST_OK;
+    unsigned long long nw = n_words, wb = word_base;
+    void* params[] = { &d_dst, &nw, &wb, &seed };
+    uint64_t blks = (n_words + 3) / 4 + 1;
+    uint64_t ctas = (blks + 255) / 256, cap = (uint64_t)G.sm_count * 16;
+    return launch_small("xmr_fill_philox", (unsigned)(ctas < cap ? ctas : cap), 256, params, (CUstream)stream);
+}
+
+/* ------------------------------------------------------------------ */
+/* host-buffer call: H2D -> xMR kernel -> D2H, chunked over 3 streams    */
+/* ------------------------------------------------------------------ */
+static int slot_reserve(CUdeviceptr* p, size_t* cap, size_t need) {
+    if (*cap >= need) return COAST_OK;
+    if (*p) DRV(p_cuMemFree_v2(*p));
+    *p = 0; *cap = 0;
+    DRV(p_cuMemAlloc_v2(p, need));
+    *cap = need;
+    return COAST_OK;
+}
+
+static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int call_handler) {
+    int rc = ensure_ctx(); if (rc) return rc;
+    if (!d) return fail(COAST_ERR_BAD_ARG, "null descriptor");
+    if (d->plan && d->plan->mode == COAST_PLAN_TABLE) return fail(COAST_ERR_UNSUPPORTED, "coast_run_host: TABLE plans need device pointers; use coast_launch");
+    for (int i = 0; i < 3; ++i) if (!G.hs[i]) DRV(p_cuStreamCreate(&G.hs[i], CU_STREAM_NON_BLOCKING));
+    const uint64_t ob = coast_out_bytes_per_unit(d->kernel);
+    if (d->kernel == COAST_K_MM_U32) {                         /* one shot: A, B in; C out */
+        size_t ab = (size_t)d->M * d->K * 4, bb = (size_t)d->K * d->N * 4, cb = (size_t)d->M * d->N * 4;
+        rc = slot_reserve(&G.h_in[0], &G.h_in_cap[0], ab); if (rc) return rc;
+        rc = slot_reserve(&G.h_aux[0], &G.h_aux_cap[0], bb); if (rc) return rc;
+        rc = slot_reserve(&G.h_out[0], &G.h_out_cap[0], cb); if (rc) return rc;
+        DRV(p_cuMemcpyHtoDAsync_v2(G.h_in[0], d->d_in, ab, G.hs[0]));
+        DRV(p_cuMemcpyHtoDAsync_v2(G.h_aux[0], d->d_aux, bb, G.hs[0]));
+        coast_launch_desc c = *d; c.d_in = (void*)G.h_in[0]; c.d_aux = (void*)G.h_aux[0]; c.d_out = (void*)G.h_out[0];
+        rc = coast_launch(&c, G.hs[0]); if (rc) return rc;
+        DRV(p_cuMemcpyDtoHAsync_v2(d->d_out, G.h_out[0], cb, G.hs[0]));
+        return sync_impl(G.hs[0], out, call_handler);
+    }
+    const uint64_t ib = in_bytes_per_unit(d);
+    if (!ib || !ob) return fail(COAST_ERR_UNSUPPORTED, "coast_run_host: kernel %u", d->kernel);
+    const int per_unit_key = d->kernel == COAST_K_AES128 && (d->mode & COAST_AES_KEY_PER_UNIT);
+    /* chunk: about 8 MiB of input per launch; each chunk is its own launch (own tensor map), the fault
+     * plan is keyed by the global unit index so chunking never changes results */
+    uint64_t chunk = (8ull << 20) / ib;
+    if (chunk < 1024ull) chunk = 1024ull;
+    uint64_t done = 0; int slot = 0;
+    while (done < d->n_units) {
+        uint64_t n = d->n_units - done < chunk ? d->n_units - done : chunk;
+        rc = slot_reserve(&G.h_in[slot], &G.h_in_cap[slot], (size_t)(chunk * ib)); if (rc) return rc;
+        rc = slot_reserve(&G.h_out[slot], &G.h_out_cap[slot], (size_t)(chunk * ob)); if (rc) return rc;
+        DRV(p_cuMemcpyHtoDAsync_v2(G.h_in[slot], (const uint8_t*)d->d_in + done * ib, (size_t)(n * ib), G.hs[slot]));
+        coast_launch_desc c = *d;
+        c.d_in = (void*)G.h_in[slot]; c.d_out = (void*)G.h_out[slot];
+        c.n_units = n; c.unit_base = d->unit_base + done;
+        if (per_unit_key) {
+            rc = slot_reserve(&G.h_aux[slot], &G.h_aux_cap[slot], (size_t)(chunk * 16)); if (rc) return rc;
+            DRV(p_cuMemcpyHtoDAsync_v2(G.h_aux[slot], (const uint8_t*)d->d_aux + done * 16, (size_t)(n * 16), G.hs[slot]));
+            c.d_aux = (void*)G.h_aux[slot];
+        }
+        rc = coast_launch(&c, G.hs[slot]); if (rc) return rc;
+        DRV(p_cuMemcpyDtoHAsync_v2((uint8_t*)d->d_out + done * ob, G.h_out[slot], (size_t)(n * ob), G.hs[slot]));
+        done += n; slot = (slot + 1) % 3;
+    }
+    DRV(p_cuStreamSynchronize(G.hs[0])); DRV(p_cuStreamSynchronize(G.hs[1]));
+    return sync_impl(G.hs[2], out, call_handler);
+}
+int coast_run_host(const coast_launch_desc* d, coast_stats* out) { return run_host_impl(d, out, 1); }
+int coast_run_host_noabort(const coast_launch_desc* d, coast_stats* out) { return run_host_impl(d, out, 0); }
+
+/* ------------------------------------------------------------------ */
+/* the four reference entry points (what the unchanged tests call)      */
+/* ------------------------------------------------------------------ */
+static void entry_mode(uint32_t* nc, uint32_t* fl) {
+    if (!G.inited) {
+        const char* dv = getenv("COAST_DEVICE");
+        int rc = coast_init(dv ? atoi(dv) : 0);
+        if (rc) { fprintf(stderr, "coast_rt: cannot run the protected region on a GPU: %s\n", G.err); abort(); }
+    }
+    if (!G.def_set) { const char* env = getenv("COAST_OPT_PASSES"); coast_set_opt_passes(env ? env : ""); }
+    *nc = G.def_nc; *fl = G.def_flags;
+}
+static void entry_run(coast_launch_desc* d) {
+    int rc = coast_run_host(d, NULL);
+    if (rc) { fprintf(stderr, "coast_rt: protected launch failed: %s\n", G.err); abort(); }
+}
+
+unsigned short coast_xmr_crc16(const unsigned char* data_p, unsigned char length) {
+    coast_launch_desc d; memset(&d, 0, sizeof d);
+    entry_mode(&d.num_clones, &d.flags);
+    unsigned short out = 0xFFFF;                               /* crc of the empty message (crc16.c:23) */
+    if (!length) return out;
+    d.kernel = COAST_K_CRC16; d.n_units = 1; d.unit_bytes = length; d.d_in = data_p; d.d_out = &out;
+    entry_run(&d);
+    return out;
+}
+void coast_xmr_sha256_hash(unsigned char ctx_data[], uint32_t ctx_bitlen[], uint32_t ctx_state[], unsigned char data[],
+                           uint32_t len, unsigned char hash[]) {
+    (void)ctx_data; (void)ctx_bitlen; (void)ctx_state;         /* scratch of the CPU formulation; replicas keep it in registers */
+    coast_launch_desc d; memset(&d, 0, sizeof d);
+    entry_mode(&d.num_clones, &d.flags);
+    unsigned char dummy = 0;
+    d.kernel = COAST_K_SHA256; d.n_units = 1; d.unit_bytes = len; d.d_in = len ? data : &dummy; d.d_out = hash;
+    entry_run(&d);
+}
+void coast_xmr_aes_enc_dec(unsigned char* state, unsigned char* key, unsigned char dir) {
+    coast_launch_desc d; memset(&d, 0, sizeof d);
+    entry_mode(&d.num_clones, &d.flags);
+    d.kernel = COAST_K_AES128; d.n_units = 1; d.mode = dir ? COAST_AES_DECRYPT : 0; d.d_in = state; d.d_out = state;
+    memcpy(d.key, key, 16);
+    entry_run(&d);
+}
+void coast_xmr_matrix_multiply_u32(const uint32_t* f, const uint32_t* s, uint32_t* r, int side) {
+    coast_launch_desc d; memset(&d, 0, sizeof d);
+    entry_mode(&d.num_clones, &d.flags);
+    d.kernel = COAST_K_MM_U32; d.M = d.N = d.K = (uint32_t)side; d.n_units = (uint64_t)side * side;
+    d.d_in = f; d.d_aux = s; d.d_out = r;
+    entry_run(&d);
+}

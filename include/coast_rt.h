@@ -226,6 +226,8 @@ int  coast_fill_philox(void* d_dst, uint64_t n_words, uint64_t word_base, uint32
  * D2H -> host out, counters folded as coast_sync().  Chunked and double-buffered on two
  * internal streams.  `h_in`/`h_out`/`h_aux` are HOST pointers here (pinned or pageable). */
 int  coast_run_host(const coast_launch_desc* desc_with_host_ptrs, coast_stats* out);
+/* Same, but never calls FAULT_DETECTED_DWC (fault campaigns want the count, not SIGABRT). */
+int  coast_run_host_noabort(const coast_launch_desc* desc_with_host_ptrs, coast_stats* out);
 
 /* The four reference entry points, callable from the UNCHANGED tests (the BOARD=b200
  * make flow redirects their calls here).  Protection mode comes from

@@ -1,0 +1,212 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/coast_golden.json from the REFERENCE ITSELF, run here.
+
+Everything in the fixture is produced by executing byuccl/coast's own C sources, compiled
+where they lie under /root/reference/tests by oracle/Makefile into oracle/_ref (see
+oracle/ref/*.c).  /root/reference does not exist on the GPU box, so the outputs are
+committed as a small fixture next to this script:
+
+    python tests/golden/make_golden.py        # needs /root/reference
+
+Contents
+  crc16   : the shipped message (crc16.c:14) and crc16() of it, plus 64 random messages
+  sha256  : 10-byte KAT (sha256_common/sha_data.inc), 4000-byte KAT (hifive1/sha256.tmr/sha_data.inc),
+            reference digests of messages of every length 0..130 (padding edge cases 55/56/63/64/119/120)
+  aes     : the 568 NIST AESAVS records of tests/aes/ECB*.h (80 bytes each: key|key2|cipher|plain|input),
+            and what aes_enc_dec() leaves in state[] and key[] for each direction
+  mm      : mm_tmr.c 9x9 uint32 operands, results_matrix, xor_golden; matrixMultiply.c int operands/results
+  xmr     : TMR/DWC runs of the reference functions with a single-bit flip in ONE replica's private
+            copy of its input (the only fault sites reachable without editing reference sources)
+"""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as po  # noqa: E402
+
+
+def hexs(b):
+    return bytes(b).hex()
+
+
+def main():
+    assert os.path.exists("/root/reference/tests/crc16/crc16.c"), "needs the reference checkout"
+    po.build()
+    rng = np.random.default_rng(20260922)
+    g = {"generator": "tests/golden/make_golden.py", "reference_commit": "397a26e"}
+
+    # ---------------------------------------------------------------- crc16
+    rc = po.ref("crc16")
+    rc.ref_crc16.restype = C.c_ushort
+    rc.ref_crc16.argtypes = [C.c_char_p, C.c_ubyte]
+    msg = b"Automated TMR"
+    crc = {"shipped_msg": hexs(msg), "shipped_crc": rc.ref_crc16(msg, len(msg)), "random": []}
+    for i in range(64):
+        n = int(rng.integers(1, 256))
+        m = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        crc["random"].append([hexs(m), rc.ref_crc16(m, n)])
+    g["crc16"] = crc
+
+    # ---------------------------------------------------------------- sha256
+    rs = po.ref("sha256")
+    rs.ref_sha256_kat10_msg.restype = C.POINTER(C.c_uint8)
+    rs.ref_sha256_kat10_golden.restype = C.POINTER(C.c_uint8)
+    rs.ref_sha256.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p]
+    assert rs.ref_sha256_kat10() == 0
+    r4 = po.ref("sha4000")
+    r4.ref_sha4000_msg.restype = C.POINTER(C.c_uint8)
+    r4.ref_sha4000_golden.restype = C.POINTER(C.c_uint8)
+    r4.ref_sha4000_len.restype = C.c_uint32
+    assert r4.ref_sha4000_kat() == 0
+    n4 = r4.ref_sha4000_len()
+
+    def ref_sha(m):
+        out = C.create_string_buffer(32)
+        rs.ref_sha256(m if m else b"\0", len(m), out)
+        return out.raw
+
+    sha = {
+        "kat10_msg": hexs(rs.ref_sha256_kat10_msg()[:10]), "kat10_digest": hexs(rs.ref_sha256_kat10_golden()[:32]),
+        "kat4000_msg": hexs(r4.ref_sha4000_msg()[:n4]), "kat4000_digest": hexs(r4.ref_sha4000_golden()[:32]),
+        "by_length": [],
+    }
+    assert ref_sha(bytes.fromhex(sha["kat10_msg"])) == bytes.fromhex(sha["kat10_digest"])
+    assert ref_sha(bytes.fromhex(sha["kat4000_msg"])) == bytes.fromhex(sha["kat4000_digest"])
+    for n in range(0, 131):
+        m = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        sha["by_length"].append([hexs(m), hexs(ref_sha(m))])
+    g["sha256"] = sha
+
+    # ---------------------------------------------------------------- aes
+    ra = po.ref("aes")
+    assert ra.ref_aes_kat_errors() == 0
+    ra.ref_aes_kat_table.restype = C.POINTER(C.c_ubyte)
+    ra.ref_aes_kat_table.argtypes = [C.c_int, C.POINTER(C.c_uint)]
+    recs = []
+    for k in range(4):
+        cnt = C.c_uint()
+        p = ra.ref_aes_kat_table(k, C.byref(cnt))
+        recs.append(bytes(p[: cnt.value * 80]))
+    allrec = b"".join(recs)
+    assert len(allrec) == 568 * 80
+    key_after_enc, key_after_dec = [], []
+    for i in range(0, len(allrec), 80):
+        r = allrec[i:i + 80]
+        key, key2, cipher, plain, inp = r[0:16], r[16:32], r[32:48], r[48:64], r[64:80]
+        st = C.create_string_buffer(inp, 16)
+        kk = C.create_string_buffer(key, 16)
+        ra.ref_aes_enc_dec(st, kk, 0)
+        assert st.raw == cipher
+        key_after_enc.append(kk.raw)
+        kk2 = C.create_string_buffer(key2, 16)
+        ra.ref_aes_enc_dec(st, kk2, 1)
+        assert st.raw == plain
+        key_after_dec.append(kk2.raw)
+    g["aes"] = {"table_counts": [len(x) // 80 for x in recs], "records": hexs(allrec),
+                "key_after_enc": hexs(b"".join(key_after_enc)), "key_after_dec": hexs(b"".join(key_after_dec))}
+
+    # ---------------------------------------------------------------- mm
+    rm = po.ref("mm")
+    assert rm.ref_mm_error() == 0
+    for f in ("ref_mm_first", "ref_mm_second", "ref_mm_results"):
+        getattr(rm, f).restype = C.POINTER(C.c_uint32)
+    rm.ref_mm_xor_golden.restype = C.c_uint32
+    side = rm.ref_mm_side()
+    ri = po.ref("mmint")
+    assert ri.ref_mmint_run_main() == 0
+    for f in ("ref_mmint_first", "ref_mmint_second"):
+        getattr(ri, f).restype = C.POINTER(C.c_int32)
+    ri.ref_mmint_results.restype = C.POINTER(C.c_uint32)
+    g["mm"] = {
+        "side": side,
+        "u32_first": list(rm.ref_mm_first()[: side * side]), "u32_second": list(rm.ref_mm_second()[: side * side]),
+        "u32_results": list(rm.ref_mm_results()[: side * side]), "xor_golden": rm.ref_mm_xor_golden(),
+        "int_first": list(ri.ref_mmint_first()[: side * side]), "int_second": list(ri.ref_mmint_second()[: side * side]),
+        "int_results": list(ri.ref_mmint_results()[: side * side]),
+    }
+
+    # ---------------------------------------------------------------- xMR with input-copy faults
+    # SHA: 24 messages of 64 bytes; per unit one flip in replica r's private data[] copy.
+    n = 24
+    msgs = rng.integers(0, 256, (n, 64), dtype=np.uint8)
+    faults = (po.RefFault * n)()
+    plan = []
+    for u in range(n):
+        if u % 3 == 2:
+            faults[u] = po.RefFault(0, -1, 0)
+            plan.append(None)
+        else:
+            r_, by, bi = int(rng.integers(0, 3)), int(rng.integers(0, 64)), int(rng.integers(0, 8))
+            faults[u] = po.RefFault(r_, by, bi)
+            plan.append([r_, by, bi])
+    xmr = {"sha_msgs": hexs(msgs.tobytes()), "sha_faults": plan, "sha_runs": {}}
+    rs.ref_sha256_xmr.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                  C.c_void_p, C.POINTER(po.RefStats)]
+    for nc in (2, 3):
+        fl = (po.RefFault * n)()
+        for u in range(n):
+            fl[u] = faults[u] if (faults[u].byte < 0 or faults[u].replica < nc) else po.RefFault(0, -1, 0)
+        out = np.zeros(n * 32, dtype=np.uint8)
+        st = po.RefStats()
+        st.first_fault_unit = po.NO_FAULT_UNIT
+        rs.ref_sha256_xmr(msgs.ctypes.data, out.ctypes.data, n, 64, nc, 1, 1, fl, C.byref(st))
+        xmr["sha_runs"][str(nc)] = {"out": hexs(out.tobytes()), "stats": st.as_dict()}
+    # AES enc, one key: 32 blocks, flips in the replica's private state copy
+    n = 32
+    blocks = rng.integers(0, 256, (n, 16), dtype=np.uint8)
+    key = rng.integers(0, 256, 16, dtype=np.uint8)
+    faults = (po.RefFault * n)()
+    plan = []
+    for u in range(n):
+        if u % 4 == 3:
+            faults[u] = po.RefFault(0, -1, 0)
+            plan.append(None)
+        else:
+            r_, by, bi = int(rng.integers(0, 2)), int(rng.integers(0, 16)), int(rng.integers(0, 8))
+            faults[u] = po.RefFault(r_, by, bi)
+            plan.append([r_, by, bi])
+    ra.ref_aes_xmr.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int,
+                               C.c_int, C.c_void_p, C.POINTER(po.RefStats)]
+    xmr.update({"aes_blocks": hexs(blocks.tobytes()), "aes_key": hexs(key.tobytes()), "aes_faults": plan, "aes_runs": {}})
+    for nc in (2, 3):
+        out = np.zeros(n * 16, dtype=np.uint8)
+        st = po.RefStats()
+        st.first_fault_unit = po.NO_FAULT_UNIT
+        ra.ref_aes_xmr(blocks.ctypes.data, out.ctypes.data, n, key.ctypes.data, 0, 0, nc, 1, 1, faults, C.byref(st))
+        xmr["aes_runs"][str(nc)] = {"out": hexs(out.tobytes()), "stats": st.as_dict()}
+    # CRC16: 30 messages of 13 bytes
+    n = 30
+    msgs = rng.integers(0, 256, (n, 13), dtype=np.uint8)
+    faults = (po.RefFault * n)()
+    plan = []
+    for u in range(n):
+        if u % 5 == 4:
+            faults[u] = po.RefFault(0, -1, 0)
+            plan.append(None)
+        else:
+            r_, by, bi = int(rng.integers(0, 3)), int(rng.integers(0, 13)), int(rng.integers(0, 8))
+            faults[u] = po.RefFault(r_, by, bi)
+            plan.append([r_, by, bi])
+    rc.ref_crc16_xmr.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                 C.c_void_p, C.POINTER(po.RefStats)]
+    out = np.zeros(n, dtype=np.uint16)
+    st = po.RefStats()
+    st.first_fault_unit = po.NO_FAULT_UNIT
+    rc.ref_crc16_xmr(msgs.ctypes.data, out.ctypes.data, n, 13, 3, 1, 1, faults, C.byref(st))
+    xmr.update({"crc_msgs": hexs(msgs.tobytes()), "crc_faults": plan,
+                "crc_run_tmr": {"out": [int(x) for x in out], "stats": st.as_dict()}})
+    g["xmr"] = xmr
+
+    path = os.path.join(ROOT, "tests", "golden", "coast_golden.json")
+    with open(path, "w") as f:
+        json.dump(g, f, separators=(",", ":"))
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,357 @@
+"""GPU (B200): the CUDA path, called through the C ABI (libcoast_rt.so), against the CPU oracle on
+the same seeded inputs -- bit-exact outputs AND equal counters, with and without injected faults --
+and against the committed golden fixtures.  Integer/byte work: the bar is bit-exact."""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+STAT_KEYS = ("errors_corrected", "dwc_detected", "syncs", "injected", "first_fault_unit")
+
+
+def H(x):
+    return bytes.fromhex(x)
+
+
+def dev(rt, arr):
+    import torch
+    a = np.ascontiguousarray(arr)
+    if a.dtype == np.uint32:
+        a = a.view(np.int32)
+    elif a.dtype == np.uint16:
+        a = a.view(np.int16)
+    return torch.from_numpy(a.copy()).cuda()
+
+
+def host(t):
+    return t.cpu().numpy().view(np.uint8) if t.dtype.itemsize == 1 else t.cpu().numpy()
+
+
+def both(rt, oracle, kernel, nc, inp, n, *, flags=0, mode=0, unit_bytes=0, M=0, N=0, K=0, aux=None, key=None,
+         plan_kw=None, table=None, unit_base=0):
+    import coast_b200 as cb
+    oplan = gplan = None
+    if table is not None:
+        oplan = oracle.make_plan(oracle.PLAN_TABLE, table=table)
+        gplan = cb.FaultPlan(mode=cb.PLAN_TABLE, table=dev(rt, table))
+    elif plan_kw:
+        oplan = oracle.make_plan(oracle.PLAN_BERNOULLI, **plan_kw)
+        gplan = cb.FaultPlan(mode=cb.PLAN_BERNOULLI, **plan_kw)
+    o_out, o_st = oracle.run(kernel, nc, inp, n, flags=flags, mode=mode, unit_bytes=unit_bytes, M=M, N=N, K=K, aux=aux,
+                             key=key, plan=oplan, unit_base=unit_base)
+    g_out, g_st = rt.run(kernel, nc, dev(rt, inp), n, flags=flags, mode=mode, unit_bytes=unit_bytes, M=M, N=N, K=K,
+                         aux=dev(rt, aux) if aux is not None else None, key=key, plan=gplan, unit_base=unit_base)
+    g = host(g_out)
+    assert g.tobytes() == o_out.tobytes(), f"output mismatch kernel={kernel} nc={nc} n={n}"
+    gd = g_st.as_dict()
+    for k in STAT_KEYS:
+        assert gd[k] == o_st[k], (k, gd, o_st)
+    return g, gd
+
+
+def msgs(oracle, n, nbytes, seed):
+    return oracle.fill_philox((n * nbytes + 3) // 4, 0, seed).view(np.uint8)[: n * nbytes].copy()
+
+
+# ------------------------------------------------------------------------------------------ fill
+def test_fill_philox_matches_oracle(rt, oracle):
+    import torch
+    for n_words, base in ((1, 0), (4, 0), (1000, 0), (1003, 5), (4096, 2), (7, 3)):
+        t = torch.zeros(n_words, dtype=torch.int32, device="cuda")
+        rt.fill_philox(t, seed=11, word_base=base)
+        torch.cuda.synchronize()
+        assert (t.cpu().numpy().view(np.uint32) == oracle.fill_philox(n_words, base, 11)).all()
+
+
+# ------------------------------------------------------------------------------------------ sha256
+@pytest.mark.parametrize("nc", [1, 2, 3])
+@pytest.mark.parametrize("n", [1, 9, 10, 11, 79, 80, 81, 257, 5000])
+def test_sha256_b64_zero_fault(rt, oracle, nc, n):
+    m = msgs(oracle, n, 64, 2)
+    g, st = both(rt, oracle, oracle.K_SHA256, nc, m, n, unit_bytes=64, flags=3)
+    for u in (0, n // 2, n - 1):
+        assert g[32 * u: 32 * u + 32].tobytes() == hashlib.sha256(m[64 * u: 64 * u + 64].tobytes()).digest()
+    assert st["errors_corrected"] == 0 and st["dwc_detected"] == 0
+
+
+@pytest.mark.parametrize("nc", [1, 2, 3])
+def test_sha256_b64_bernoulli_faults(rt, oracle, nc):
+    n = 4000
+    m = msgs(oracle, n, 64, 2)
+    g, st = both(rt, oracle, oracle.K_SHA256, nc, m, n, unit_bytes=64, flags=3, plan_kw=dict(seed=77, p=0.2))
+    assert st["injected"] > 500
+    if nc == 3:
+        clean, _ = oracle.run(oracle.K_SHA256, 1, m, n, unit_bytes=64)
+        assert g.tobytes() == clean.tobytes()          # every single fault is out-voted
+        assert st["errors_corrected"] >= st["injected"]
+
+
+def test_sha256_every_site_class_table_plan(rt, oracle):
+    """one unit per enumerated site class and replica: m[] words, working vars at several rounds, ctx_state, both blocks"""
+    sites = [0, 7, 15, 16, 16 + 8 * 5 + 3, 16 + 8 * 63 + 7, 528, 535, 536, 536 + 15, 536 + 16 + 8 * 31 + 4, 536 + 535]
+    ent = [(r, s, b) for s in sites for r in range(3) for b in (0, 31)]
+    n = len(ent) + 5
+    m = msgs(oracle, n, 64, 4)
+    for nc in (2, 3):
+        tab = np.zeros(n, dtype=np.uint32)
+        for u, (r, s, b) in enumerate(ent):
+            tab[u] = oracle.fault_entry(r, s, b)       # replica 2 entries are ignored under DWC
+        tab[-1] = oracle.fault_entry(0, 2000, 0)        # out-of-range site -> ignored
+        tab[-2] = oracle.fault_entry(0, 3, 31) & ~0x80000000 & 0xFFFFFFFF   # valid bit clear -> ignored
+        both(rt, oracle, oracle.K_SHA256, nc, m, n, unit_bytes=64, flags=3, table=tab)
+
+
+@pytest.mark.parametrize("length", [1, 3, 10, 55, 56, 63, 65, 119, 120, 200])
+def test_sha256_general_lengths(rt, oracle, length):
+    n = 37
+    m = msgs(oracle, n, length, 6)
+    g, _ = both(rt, oracle, oracle.K_SHA256, 3, m, n, unit_bytes=length, flags=3, plan_kw=dict(seed=length, p=0.3))
+    g1, _ = both(rt, oracle, oracle.K_SHA256, 1, m, n, unit_bytes=length)
+    for u in range(n):
+        assert g1[32 * u: 32 * u + 32].tobytes() == hashlib.sha256(m[length * u: length * u + length].tobytes()).digest()
+
+
+def test_sha256_reference_kats(rt, oracle, golden):
+    g = golden["sha256"]
+    for key_m, key_d in (("kat10_msg", "kat10_digest"), ("kat4000_msg", "kat4000_digest")):
+        m = np.frombuffer(H(g[key_m]), dtype=np.uint8)
+        for nc in (1, 2, 3):
+            out, st = rt.run(oracle.K_SHA256, nc, dev(rt, m), 1, unit_bytes=len(m), flags=3)
+            assert host(out).tobytes() == H(g[key_d])
+            assert st.errors_corrected == 0 and st.dwc_detected == 0     # "C:0 E:0 F:0" (sha256_tmr.c:30)
+
+
+def test_sha256_unaligned_input_takes_general_path(rt, oracle):
+    import torch
+    n = 100
+    m = msgs(oracle, n, 64, 9)
+    buf = torch.zeros(n * 64 + 4, dtype=torch.uint8, device="cuda")
+    buf[4:] = torch.from_numpy(m.copy()).cuda()
+    out, _ = rt.run(oracle.K_SHA256, 3, buf[4:], n, unit_bytes=64)
+    ref, _ = oracle.run(oracle.K_SHA256, 3, m, n, unit_bytes=64)
+    assert host(out).tobytes() == ref.tobytes()
+
+
+def test_sha256_full_size_properties(rt, oracle):
+    """BASELINE config 2: 2^20 x 64-byte messages.  Size-independent properties: digests equal hashlib on a
+    sample; TMR under a p=2^-6 fault plan gives bit-identical output to the fault-free run; counters equal the
+    oracle's on the first 2^15 units' worth of the same plan (prefix run with the same unit_base)."""
+    import torch
+    import coast_b200 as cb
+    n = 1 << 20
+    d_in = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    rt.fill_philox(d_in, seed=2)
+    clean, st0 = rt.run(cb.K_SHA256, 3, d_in, n, unit_bytes=64, flags=3)
+    assert st0.errors_corrected == 0 and st0.syncs == 32 * n
+    plan = cb.FaultPlan(mode=cb.PLAN_BERNOULLI, seed=22, p=2 ** -6)
+    faulty, st1 = rt.run(cb.K_SHA256, 3, d_in, n, unit_bytes=64, flags=3, plan=plan)
+    assert torch.equal(clean, faulty)
+    assert abs(st1.injected - n / 64) < 6 * (n / 64) ** 0.5
+    unp, _ = rt.run(cb.K_SHA256, 1, d_in, n, unit_bytes=64)
+    assert torch.equal(clean, unp)
+    h_in = d_in.cpu().numpy()
+    h_out = clean.cpu().numpy()
+    for u in list(range(0, n, 65537)) + [n - 1]:
+        assert h_out[32 * u: 32 * u + 32].tobytes() == hashlib.sha256(h_in[64 * u: 64 * u + 64].tobytes()).digest()
+    k = 1 << 15
+    _, so = oracle.run(oracle.K_SHA256, 3, h_in[: 64 * k], k, unit_bytes=64, flags=3,
+                       plan=oracle.make_plan(oracle.PLAN_BERNOULLI, seed=22, p=2 ** -6), threads=8)
+    _, sg = rt.run(cb.K_SHA256, 3, d_in[: 64 * k], k, unit_bytes=64, flags=3, plan=plan)
+    assert sg.as_dict() == so
+
+
+# ------------------------------------------------------------------------------------------ aes
+@pytest.mark.parametrize("nc", [1, 2, 3])
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 319, 320, 321, 512, 1025, 6000])
+def test_aes_enc_zero_fault(rt, oracle, nc, n):
+    blocks = msgs(oracle, n, 16, 3)
+    both(rt, oracle, oracle.K_AES128, nc, blocks, n, key=bytes(range(16)), flags=3)
+
+
+@pytest.mark.parametrize("nc", [1, 2, 3])
+def test_aes_enc_bernoulli_faults_detect_rate(rt, oracle, nc):
+    n = 20000
+    blocks = msgs(oracle, n, 16, 3)
+    g, st = both(rt, oracle, oracle.K_AES128, nc, blocks, n, key=bytes(16), flags=3, plan_kw=dict(seed=33, p=0.05))
+    if nc == 2:
+        assert st["dwc_detected"] == st["injected"] > 500    # every state flip propagates (bijective rounds)
+
+
+def test_aes_every_site_table_plan(rt, oracle):
+    ent = [(r, s, b) for s in range(176) for r in (0, 1, 2) for b in (0, 7)]
+    n = len(ent)
+    blocks = msgs(oracle, n, 16, 5)
+    tab = np.array([oracle.fault_entry(r, s, b) for (r, s, b) in ent], dtype=np.uint32)
+    for nc in (2, 3):
+        both(rt, oracle, oracle.K_AES128, nc, blocks, n, key=bytes(range(1, 17)), flags=3, table=tab)        # T-table kernel
+        both(rt, oracle, oracle.K_AES128, nc, blocks, n, key=bytes(range(1, 17)), flags=3, table=tab, mode=1)  # decrypt, byte-wise kernel
+
+
+def test_aes_568_nist_kats_on_device(rt, oracle, golden):
+    """aes_test() (tests/aes/aes.c:29-103) on the GPU: encrypt with key, compare to cipher; decrypt with key2, compare to plain."""
+    rec = np.frombuffer(H(golden["aes"]["records"]), dtype=np.uint8).reshape(568, 80)
+    keys, keys2, cipher, plain, inp = (np.ascontiguousarray(rec[:, 16 * i: 16 * i + 16]) for i in range(5))
+    for nc in (1, 2, 3):
+        enc, st = rt.run(oracle.K_AES128, nc, dev(rt, inp), 568, mode=oracle.AES_KEY_PER_UNIT, aux=dev(rt, keys), flags=3)
+        assert host(enc).tobytes() == cipher.tobytes()
+        dec, st2 = rt.run(oracle.K_AES128, nc, enc, 568, mode=oracle.AES_KEY_PER_UNIT | oracle.AES_DECRYPT, aux=dev(rt, keys2), flags=3)
+        assert host(dec).tobytes() == plain.tobytes()
+        assert st.errors_corrected == st.dwc_detected == st2.errors_corrected == st2.dwc_detected == 0   # "Number of errors: 0"
+    # single-key T-table kernel on the VarTxt table (all-zero key, aes/ECBVarTxt128.h)
+    vt = rec[14 + 42 + 256:]
+    assert not vt[:, :16].any()
+    enc, _ = rt.run(oracle.K_AES128, 2, dev(rt, np.ascontiguousarray(vt[:, 64:80])), 256, key=bytes(16))
+    assert host(enc).tobytes() == np.ascontiguousarray(vt[:, 32:48]).tobytes()
+
+
+def test_aes_decrypt_and_per_unit_keys_with_faults(rt, oracle):
+    n = 3000
+    blocks = msgs(oracle, n, 16, 3)
+    keys = msgs(oracle, n, 16, 8)
+    for mode in (oracle.AES_DECRYPT, oracle.AES_KEY_PER_UNIT, oracle.AES_KEY_PER_UNIT | oracle.AES_DECRYPT):
+        both(rt, oracle, oracle.K_AES128, 2, blocks, n, key=bytes(range(16)), mode=mode, flags=3,
+             aux=keys if mode & oracle.AES_KEY_PER_UNIT else None, plan_kw=dict(seed=5, p=0.1))
+        both(rt, oracle, oracle.K_AES128, 3, blocks, n, key=bytes(range(16)), mode=mode, flags=3,
+             aux=keys if mode & oracle.AES_KEY_PER_UNIT else None, plan_kw=dict(seed=6, p=0.1))
+
+
+def test_aes_full_size_roundtrip_and_detect_rate(rt, oracle):
+    """BASELINE config 3: 2^24 blocks, DWC, Bernoulli(2^-10) flips.  Properties: decrypt(encrypt(x)) == x over the
+    full buffer; dwc_detected == injected (detect-rate parity: 100% of state flips); prefix counters == oracle."""
+    import torch
+    import coast_b200 as cb
+    n = 1 << 24
+    d_in = torch.empty(n * 16, dtype=torch.uint8, device="cuda")
+    rt.fill_philox(d_in, seed=3)
+    key = bytes(16)
+    enc, st = rt.run(cb.K_AES128, 2, d_in, n, key=key)
+    assert st.dwc_detected == 0
+    dec, _ = rt.run(cb.K_AES128, 1, enc, n, key=key, mode=cb.AES_DECRYPT)
+    assert torch.equal(dec, d_in)
+    plan = cb.FaultPlan(mode=cb.PLAN_BERNOULLI, seed=33, p=2 ** -10)
+    enc_f, st_f = rt.run(cb.K_AES128, 2, d_in, n, key=key, plan=plan)
+    assert st_f.dwc_detected == st_f.injected
+    assert abs(st_f.injected - n / 1024) < 6 * (n / 1024) ** 0.5
+    k = 1 << 16
+    o_out, so = oracle.run(oracle.K_AES128, 2, d_in[: 16 * k].cpu().numpy(), k, key=key,
+                           plan=oracle.make_plan(oracle.PLAN_BERNOULLI, seed=33, p=2 ** -10), threads=8)
+    g_out, sg = rt.run(cb.K_AES128, 2, d_in[: 16 * k], k, key=key, plan=plan)
+    assert sg.as_dict() == so and host(g_out).tobytes() == o_out.tobytes()
+
+
+# ------------------------------------------------------------------------------------------ crc16
+def test_crc16_shipped_message(rt, oracle, golden):
+    m = np.frombuffer(H(golden["crc16"]["shipped_msg"]), dtype=np.uint8)
+    for nc in (1, 2, 3):
+        out, st = rt.run(oracle.K_CRC16, nc, dev(rt, m), 1, unit_bytes=13, flags=3)
+        assert int(host(out).view(np.uint16)[0]) == 0x5BA3           # "result: 5ba3"
+    for mh, c in golden["crc16"]["random"]:
+        mm = np.frombuffer(H(mh), dtype=np.uint8)
+        out, _ = rt.run(oracle.K_CRC16, 3, dev(rt, mm), 1, unit_bytes=len(mm))
+        assert int(host(out).view(np.uint16)[0]) == c
+
+
+@pytest.mark.parametrize("nc", [1, 2, 3])
+@pytest.mark.parametrize("length,n", [(64, 1), (64, 81), (64, 3000), (13, 500), (1, 40), (255, 100), (48, 77)])
+def test_crc16_faults(rt, oracle, nc, length, n):
+    m = msgs(oracle, n, length, 1)
+    both(rt, oracle, oracle.K_CRC16, nc, m, n, unit_bytes=length, flags=3)
+    both(rt, oracle, oracle.K_CRC16, nc, m, n, unit_bytes=length, flags=3, plan_kw=dict(seed=length, p=0.3))
+
+
+def test_crc16_full_size(rt, oracle):
+    import torch
+    import coast_b200 as cb
+    n = 1 << 20
+    d_in = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    rt.fill_philox(d_in, seed=1)
+    a, _ = rt.run(cb.K_CRC16, 1, d_in, n, unit_bytes=64)
+    b, st = rt.run(cb.K_CRC16, 3, d_in, n, unit_bytes=64, flags=3, plan=cb.FaultPlan(mode=cb.PLAN_BERNOULLI, seed=4, p=0.01))
+    assert torch.equal(a, b) and st.errors_corrected == st.injected      # one u16 vote per unit; every crc/data flip shows
+    k = 1 << 14
+    o, _ = oracle.run(oracle.K_CRC16, 1, d_in[: 64 * k].cpu().numpy(), k, unit_bytes=64)
+    assert host(a[: 2 * k]).tobytes() == o.tobytes()
+
+
+# ------------------------------------------------------------------------------------------ matmul (exact)
+def test_mm_reference_9x9(rt, oracle, golden):
+    g = golden["mm"]
+    A, B = np.array(g["u32_first"], dtype=np.uint32), np.array(g["u32_second"], dtype=np.uint32)
+    for nc in (1, 2, 3):
+        out, st = rt.run(oracle.K_MM_U32, nc, dev(rt, A), 81, M=9, N=9, K=9, aux=dev(rt, B), flags=3)
+        C = host(out).view(np.uint32)
+        assert list(C) == g["u32_results"] and int(np.bitwise_xor.reduce(C)) == g["xor_golden"]   # "Error?: 0"
+    Ai = np.array(g["int_first"], dtype=np.int32).view(np.uint32)
+    Bi = np.array(g["int_second"], dtype=np.int32).view(np.uint32)
+    out, _ = rt.run(oracle.K_MM_U32, 2, dev(rt, Ai), 81, M=9, N=9, K=9, aux=dev(rt, Bi))
+    assert list(host(out).view(np.uint32)) == g["int_results"]                                    # "Number of errors: 0"
+
+
+@pytest.mark.parametrize("nc", [1, 2, 3])
+@pytest.mark.parametrize("M,N,K", [(9, 9, 9), (17, 33, 5), (64, 64, 64), (100, 130, 70)])
+def test_mm_faults(rt, oracle, nc, M, N, K):
+    A = oracle.fill_philox(M * K, 0, 4)
+    B = oracle.fill_philox(K * N, 0, 44)
+    both(rt, oracle, oracle.K_MM_U32, nc, A, M * N, M=M, N=N, K=K, aux=B, flags=3)
+    both(rt, oracle, oracle.K_MM_U32, nc, A, M * N, M=M, N=N, K=K, aux=B, flags=3, plan_kw=dict(seed=M, p=0.2))
+
+
+# ------------------------------------------------------------------------------------------ ABI behaviour on the GPU
+def test_counters_fold_into_reference_globals(rt, oracle):
+    before_e, before_s = rt.tmr_error_cnt, rt.sync_count
+    n = 300
+    m = msgs(oracle, n, 64, 2)
+    _, st = both(rt, oracle, oracle.K_SHA256, 3, m, n, unit_bytes=64, flags=3, plan_kw=dict(seed=1, p=0.5))
+    assert rt.tmr_error_cnt == (before_e + st["errors_corrected"]) & 0xFFFFFFFF       # i32 TMR_ERROR_CNT
+    assert rt.sync_count == before_s + st["syncs"]                                     # i64 __SYNC_COUNT
+
+
+def test_majority_voter_extension(rt, oracle):
+    n = 500
+    m = msgs(oracle, n, 64, 2)
+    both(rt, oracle, oracle.K_SHA256, 3, m, n, unit_bytes=64, flags=3 | 0x100, plan_kw=dict(seed=3, p=0.4))
+
+
+def test_run_host_matches_device_path(rt, oracle):
+    import torch
+    import coast_b200 as cb
+    n = 300000
+    h_in = torch.from_numpy(msgs(oracle, n, 64, 2)).pin_memory()
+    h_out = torch.empty(n * 32, dtype=torch.uint8).pin_memory()
+    plan = cb.FaultPlan(mode=cb.PLAN_BERNOULLI, seed=9, p=0.01)
+    st = rt.run_host(cb.K_SHA256, 3, h_in, h_out, n, unit_bytes=64, flags=3, plan=plan)
+    d_out, st2 = rt.run(cb.K_SHA256, 3, h_in.cuda(), n, unit_bytes=64, flags=3, plan=plan)
+    assert torch.equal(d_out.cpu(), h_out) and st.as_dict() == st2.as_dict()
+    # AES through the host path, DWC with faults: never aborts in the noabort flavour
+    hb = torch.from_numpy(msgs(oracle, n, 16, 3)).pin_memory()
+    ho = torch.empty(n * 16, dtype=torch.uint8).pin_memory()
+    st = rt.run_host(cb.K_AES128, 2, hb, ho, n, key=bytes(16), plan=plan)
+    o, so = oracle.run(oracle.K_AES128, 2, hb.numpy(), n, key=bytes(16), plan=oracle.make_plan(oracle.PLAN_BERNOULLI, seed=9, p=0.01), threads=8)
+    assert ho.numpy().tobytes() == o.tobytes() and st.as_dict() == so
+
+
+def test_reference_entry_points(rt, oracle, golden):
+    """the four functions the unchanged reference tests call (BOARD=b200 flow), under -TMR -countErrors"""
+    import ctypes as C
+    L = rt.L
+    assert L.coast_set_opt_passes(b"-TMR -countErrors") == 0
+    assert L.coast_xmr_crc16(b"Automated TMR", 13) == 0x5BA3
+    g = golden["sha256"]
+    msg = C.create_string_buffer(H(g["kat10_msg"]), 10)
+    digest = C.create_string_buffer(32)
+    cd, bl, stt = C.create_string_buffer(64), (C.c_uint32 * 2)(), (C.c_uint32 * 8)()
+    L.coast_xmr_sha256_hash(cd, bl, stt, msg, 10, digest)
+    assert digest.raw == H(g["kat10_digest"])
+    rec = H(golden["aes"]["records"])[:80]
+    state, key = C.create_string_buffer(rec[64:80], 16), C.create_string_buffer(rec[0:16], 16)
+    L.coast_xmr_aes_enc_dec(state, key, 0)
+    assert state.raw == rec[32:48]
+    key2 = C.create_string_buffer(rec[16:32], 16)
+    L.coast_xmr_aes_enc_dec(state, key2, 1)
+    assert state.raw == rec[48:64]
+    mm = golden["mm"]
+    A = (C.c_uint32 * 81)(*mm["u32_first"]); B = (C.c_uint32 * 81)(*mm["u32_second"]); R = (C.c_uint32 * 81)()
+    L.coast_xmr_matrix_multiply_u32(A, B, R, 9)
+    assert list(R) == mm["u32_results"]
