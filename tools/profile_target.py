@@ -1,0 +1,67 @@
+#!/usr/bin/env python3
+"""Small launch driver for ncu captures (never a bench number): runs one workload/protection combo
+`--iters` times on device-resident Philox inputs.
+
+  ncu --set full --clock-control none --import-source on -k regex:xmr_sha256 -o gpurun_out/prof \
+      python tools/profile_target.py --kernel sha256 --nc 3 --iters 3
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--kernel", choices=["sha256", "aes", "crc16", "mm"], default="sha256")
+    ap.add_argument("--nc", type=int, default=3)
+    ap.add_argument("--log2n", type=int, default=20)
+    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--inject", type=float, default=0.0)
+    ap.add_argument("--side", type=int, default=1024)
+    ap.add_argument("--time", action="store_true", help="print CUDA-event ms per launch (outside any profiler)")
+    a = ap.parse_args()
+    import torch
+    import coast_b200 as cb
+    rt = cb.Runtime(0)
+    n = 1 << a.log2n
+    plan = cb.FaultPlan(mode=cb.PLAN_BERNOULLI, seed=7, p=a.inject) if a.inject > 0 else None
+    flags = cb.F_COUNT_ERRORS | cb.F_COUNT_SYNCS
+    if a.kernel == "sha256":
+        d_in = torch.empty(n * 64, dtype=torch.uint8, device="cuda"); rt.fill_philox(d_in, 2)
+        out = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+        d = rt.make_desc(cb.K_SHA256, a.nc, d_in, out, n, flags=flags, unit_bytes=64, plan=plan)
+        alg = n * 96
+    elif a.kernel == "crc16":
+        d_in = torch.empty(n * 64, dtype=torch.uint8, device="cuda"); rt.fill_philox(d_in, 1)
+        out = torch.empty(n * 2, dtype=torch.uint8, device="cuda")
+        d = rt.make_desc(cb.K_CRC16, a.nc, d_in, out, n, flags=flags, unit_bytes=64, plan=plan)
+        alg = n * 66
+    elif a.kernel == "aes":
+        d_in = torch.empty(n * 16, dtype=torch.uint8, device="cuda"); rt.fill_philox(d_in, 3)
+        out = torch.empty(n * 16, dtype=torch.uint8, device="cuda")
+        d = rt.make_desc(cb.K_AES128, a.nc, d_in, out, n, flags=flags, key=bytes(16), plan=plan)
+        alg = n * 32
+    else:
+        s = a.side
+        A = torch.empty(s * s, dtype=torch.int32, device="cuda"); rt.fill_philox(A, 4)
+        B = torch.empty(s * s, dtype=torch.int32, device="cuda"); rt.fill_philox(B, 44)
+        out = torch.empty(s * s, dtype=torch.int32, device="cuda")
+        d = rt.make_desc(cb.K_MM_U32, a.nc, A, out, s * s, flags=flags, M=s, N=s, K=s, d_aux=B, plan=plan)
+        alg = 3 * s * s * 4
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(a.iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); rt.launch(d); e1.record(); e1.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    st = rt.sync()
+    if a.time:
+        best = min(ms)
+        print(f"{a.kernel} nc={a.nc} n={n} inject={a.inject}: best {best:.4f} ms, median {sorted(ms)[len(ms)//2]:.4f} ms, "
+              f"{alg / best / 1e6:.1f} GB/s algorithmic; stats={st.as_dict()}")
+
+
+if __name__ == "__main__":
+    main()
