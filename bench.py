@@ -252,6 +252,15 @@ def run_ours(args):
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     sampler.stop()
     assert torch.equal(h_out, outs[0].cpu())
+    # context for the e2e number: what a bare pinned copy of the same buffers achieves on this box
+    def copy_gbs(dst, src, reps=5):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        return src.numel() * reps / (time.perf_counter() - t) / 1e9
+    pcie_h2d, pcie_d2h = copy_gbs(ins[1], h_in), copy_gbs(h_out, outs[0])
 
     t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -283,7 +292,8 @@ def run_ours(args):
                          "note": "integer-issue bound, not HBM bound: see DESIGN.md section 5 (ALU ceiling)"},
             "e2e": {"value": round(world * n * OUT_BYTES / e2e_s / 1e6, 1), "unit": "MB/s",
                     "h2d_bytes_per_step": n * UNIT_BYTES, "d2h_bytes_per_step": n * OUT_BYTES + 40,
-                    "ms_per_step": round(e2e_s * 1e3, 4), "timer": "host clock around the blocking C-ABI call coast_run_host"},
+                    "ms_per_step": round(e2e_s * 1e3, 4), "timer": "host clock around the blocking C-ABI call coast_run_host",
+                    "pcie_pinned_copy_gbs": {"h2d": round(pcie_h2d, 1), "d2h": round(pcie_d2h, 1)}},
             "gpu_launches": timed_launches,
             "clocks": sampler.summary(),
         }
