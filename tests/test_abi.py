@@ -1,0 +1,107 @@
+"""CPU: the C-ABI library builds, loads without a GPU, exports every symbol include/coast_rt.h declares,
+parses OPT_PASSES like the reference's Makefiles write them, and fails LOUDLY (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "coast_rt.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    fns = re.findall(r"^\s*(?:int|void|unsigned short|uint32_t|const char\*)\s+(\w+)\s*\(", src, flags=re.M)
+    vars_ = re.findall(r"^\s*extern\s+\w+\s+(\w+);", src, flags=re.M)
+    return sorted(set(fns)), sorted(set(vars_))
+
+
+def test_library_exports_everything_the_header_declares(built_lib):
+    fns, vars_ = declared_symbols()
+    assert "coast_launch" in fns and "FAULT_DETECTED_DWC" in fns and len(fns) >= 30
+    assert vars_ == ["TMR_ERROR_CNT", "__SYNC_COUNT"]
+    L = C.CDLL(built_lib)
+    for name in fns + vars_:
+        assert hasattr(L, name), f"libcoast_rt.so does not export {name}"
+    import coast_b200.runtime as r
+    assert set(fns + vars_) == set(r.EXPORTS)
+    assert C.c_uint32.in_dll(L, "TMR_ERROR_CNT").value == 0       # zero-initialised (synchronization.cpp:278-290)
+    assert C.c_uint64.in_dll(L, "__SYNC_COUNT").value == 0
+
+
+def test_sm100a_cubin_is_embedded(built_lib):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "coast_b200", "csrc", "coast_kernels.cubin")],
+                         capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    blob = open(built_lib, "rb").read()
+    cubin = open(os.path.join(ROOT, "coast_b200", "csrc", "coast_kernels.cubin"), "rb").read()
+    assert cubin[:4] == b"\x7fELF" and cubin in blob
+
+
+@pytest.mark.parametrize("s,nc,fl", [
+    ("-TMR -reportErrors", 3, 0x40),                       # tests/crc16/Makefile:3
+    ("-TMR -verbose -countErrors", 3, 0x21),               # tests/sha256_common/Makefile:3
+    ("-DWC #-DebugStatements", 2, 0),                      # tests/matrixMultiply/Makefile:3
+    ("", 1, 0),                                            # tests/aes/Makefile:3
+    ("-TMR -countErrors -countSyncs -noMemReplication -i", 3, 0x1 | 0x2 | 0x4 | 0x8),
+    ("-DWC -noLoadSync -noStoreDataSync -noStoreAddrSync -s", 2, 0x10),   # unittest/cfg/full.yml sweep
+    ("-TMR -CFCSS -someUnknownPass", 3, 0),                # unknown tokens: warn and ignore
+])
+def test_parse_opt_passes(built_lib, s, nc, fl):
+    import coast_b200 as cb
+    assert cb.parse_opt_passes(s) == (nc, fl)
+
+
+def test_tmr_and_dwc_are_exclusive(built_lib):
+    import coast_b200 as cb
+    with pytest.raises(cb.CoastError):
+        cb.parse_opt_passes("-TMR -DWC")
+
+
+def test_geometry_matches_oracle_spec(built_lib, oracle):
+    import coast_b200 as cb
+    L = cb.load_library()
+    for k in range(5):
+        assert L.coast_out_bytes_per_unit(k) == oracle.out_bytes_per_unit(k)
+        assert L.coast_votes_per_unit(k) == oracle.votes_per_unit(k)
+        for ub in (0, 1, 10, 13, 55, 56, 64, 119, 120, 255, 4000):
+            for K in (0, 9, 4096):
+                n = L.coast_fault_sites(k, ub, K)
+                assert n == oracle.fault_sites(k, ub, K)
+                for site in {0, n // 2, max(n, 1) - 1}:
+                    assert L.coast_fault_site_bits(k, ub, K, site) == oracle.fault_site_bits(k, ub, K, site)
+
+
+def _has_gpu():
+    return os.path.exists("/dev/nvidiactl")
+
+
+@pytest.mark.skipif(_has_gpu(), reason="this test documents the no-GPU behaviour")
+def test_no_gpu_fails_loudly_never_falls_back(built_lib):
+    import coast_b200 as cb
+    L = cb.load_library()
+    d = cb.LaunchDesc()
+    d.kernel, d.num_clones, d.n_units = cb.K_SHA256, 3, 1
+    assert L.coast_launch(C.byref(d), None) == cb.runtime.ERR_NOT_INIT
+    assert b"coast_init" in L.coast_last_error()
+    assert L.coast_init(0) == cb.runtime.ERR_NO_DRIVER
+    assert b"no CPU fallback" in L.coast_last_error()
+    with pytest.raises(cb.CoastError) as e:
+        cb.Runtime(0)
+    assert e.value.code == cb.runtime.ERR_NO_DRIVER
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under coast_b200/ or include/ may import, include or load it
+    (comments that say the fault-site spec is shared with oracle/ are fine)."""
+    pat = re.compile(r"pyoracle|liboracle|coast_oracle|(?:import|from)\s+oracle|#\s*include\s+\"[^\"]*oracle|_ref/libref")
+    bad = []
+    for base in ("coast_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".c", ".cu", ".cuh", ".h", ".S")) or f == "Makefile":
+                    if pat.search(open(os.path.join(dp, f), errors="ignore").read()):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad
