@@ -8,3 +8,4 @@
 #include "xmr_aes128.cuh"
 #include "xmr_crc16.cuh"
 #include "xmr_mm.cuh"
+#include "xmr_gemm_tf32.cuh"

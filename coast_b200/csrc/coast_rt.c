@@ -311,6 +311,41 @@ static int encode_rows_map(CUtensorMap* map, const void* base, uint32_t row_byte
     return COAST_OK;
 }
 
+/* tcgen05 TF32 GEMM: A through a 2-D map (box 32 k x 128 m), B (row-major K x N, N contiguous) through a 3-D view
+ * {32 n, K, N/32} (box 32 x 32 x 4) so one TMA lands the [n-chunk][k][128 B] layout the MN-major UMMA descriptor reads. */
+#define GEMM_SMEM (6u * (16384u + 16384u) + 1024u + 256u)
+static int launch_gemm_tf32(const coast_launch_desc* d, xmr_args* a, int inj, CUstream stream) {
+    char name[64];
+    snprintf(name, sizeof name, "xmr_gemm_tf32_nc%u_inj%d", d->num_clones, inj);
+    CUfunction fn; int occ = 1;
+    int rc = get_fn(name, GEMM_SMEM, &fn, &occ); if (rc) return rc;
+    CUtensorMap ma, mb;
+    {
+        cuuint64_t gdim[2] = { d->K, d->M };
+        cuuint64_t gstr[1] = { (cuuint64_t)d->K * 4u };
+        cuuint32_t box[2] = { 32, 128 };
+        cuuint32_t estr[2] = { 1, 1 };
+        DRV(p_cuTensorMapEncodeTiled(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)d->d_in, gdim, gstr, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+    }
+    {
+        cuuint64_t gdim[3] = { 32, d->K, d->N / 32u };
+        cuuint64_t gstr[2] = { (cuuint64_t)d->N * 4u, 128u };
+        cuuint32_t box[3] = { 32, 32, 4 };
+        cuuint32_t estr[3] = { 1, 1, 1 };
+        DRV(p_cuTensorMapEncodeTiled(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)d->d_aux, gdim, gstr, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+    }
+    unsigned tiles = (d->M / 128u) * (d->N / 128u);
+    unsigned grid = tiles < (unsigned)G.sm_count ? tiles : (unsigned)G.sm_count;
+    void* params[3] = { a, &ma, &mb };
+    if (d->flags & COAST_F_VERBOSE) fprintf(stderr, "coast_rt: %s grid=%u smem=%u tiles=%u\n", name, grid, GEMM_SMEM, tiles);
+    DRV(p_cuLaunchKernel(fn, grid, 1, 1, 256, 1, 1, GEMM_SMEM, stream, params, NULL));
+    return COAST_OK;
+}
+
 int coast_launch(const coast_launch_desc* d, void* stream) {
     int rc = ensure_ctx(); if (rc) return rc;
     if (!d) return fail(COAST_ERR_BAD_ARG, "null descriptor");
@@ -378,6 +413,13 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
         if (d->n_units != (uint64_t)d->M * d->N) return fail(COAST_ERR_BAD_ARG, "MM: n_units must be M*N");
         snprintf(name, sizeof name, "xmr_mm_u32_nc%u_inj%d", nc, inj);
         break;
+    case COAST_K_GEMM_TF32:
+        if (!d->d_aux || !d->M || !d->N || !d->K) return fail(COAST_ERR_BAD_ARG, "GEMM needs A (d_in), B (d_aux) and M,N,K");
+        if (d->n_units != (uint64_t)d->M * d->N) return fail(COAST_ERR_BAD_ARG, "GEMM: n_units must be M*N");
+        if (d->M % 128u || d->N % 128u || d->K % 32u)
+            return fail(COAST_ERR_UNSUPPORTED, "GEMM_TF32 tiles are 128x128x32: M,N must be multiples of 128 and K of 32 (got %u,%u,%u)", d->M, d->N, d->K);
+        if (!aligned16 || (((uintptr_t)d->d_aux) & 15u) || (((uintptr_t)d->d_out) & 15u)) return fail(COAST_ERR_BAD_ARG, "GEMM buffers must be 16-byte aligned");
+        return launch_gemm_tf32(d, &a, inj, (CUstream)stream);
     default:
         return fail(COAST_ERR_UNSUPPORTED, "kernel %u is not built into this library yet", d->kernel);
     }
@@ -480,7 +522,7 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int call_
     if (d->plan && d->plan->mode == COAST_PLAN_TABLE) return fail(COAST_ERR_UNSUPPORTED, "coast_run_host: TABLE plans need device pointers; use coast_launch");
     for (int i = 0; i < 3; ++i) if (!G.hs[i]) DRV(p_cuStreamCreate(&G.hs[i], CU_STREAM_NON_BLOCKING));
     const uint64_t ob = coast_out_bytes_per_unit(d->kernel);
-    if (d->kernel == COAST_K_MM_U32) {                         /* one shot: A, B in; C out */
+    if (d->kernel == COAST_K_MM_U32 || d->kernel == COAST_K_GEMM_TF32) {   /* one shot: A, B in; C out */
         size_t ab = (size_t)d->M * d->K * 4, bb = (size_t)d->K * d->N * 4, cb = (size_t)d->M * d->N * 4;
         rc = slot_reserve(&G.h_in[0], &G.h_in_cap[0], ab); if (rc) return rc;
         rc = slot_reserve(&G.h_aux[0], &G.h_aux_cap[0], bb); if (rc) return rc;

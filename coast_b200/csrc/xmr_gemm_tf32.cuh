@@ -1,0 +1,226 @@
+// xmr_gemm_tf32.cuh -- protected dense matmul on the 5th-gen tensor cores (BASELINE config 4).
+//
+// C[M,N] = A[M,K] . B[K,N], fp32 in / fp32 out, row-major, tcgen05.mma kind::tf32 (operands are read
+// as TF32 = top 19 bits of each fp32; fp32 accumulate in TMEM).  It is the tensor-core realisation of
+// matrix_multiply() (tests/matrixMultiply/matrixMultiply.c:95-112, tests/mm_common/mm_common_tmr.c:3-20);
+// the bit-exact integer flavour of those loops is xmr_mm.cuh.
+//
+// Redundancy costs FLOPs, not bandwidth:
+//   * ONE copy of each A/B tile is staged in shared memory by TMA (128B swizzle; 32-byte atoms for the
+//     N-contiguous B operand), 6-stage mbarrier ring;
+//   * the single MMA-issuing thread issues every tcgen05.mma NC times, once per replica, against NC
+//     DIFFERENT TMEM accumulators (columns [r*128, r*128+128)) -- the replicas of cloneInsns
+//     (cloning.cpp:2189-2204) are NC independent accumulator tiles fed from the same operand bytes;
+//   * the epilogue warps read the NC accumulators back (tcgen05.ld), vote element-wise with the reference's
+//     select voter and `fcmp oeq` (synchronization.cpp:57-62,512-522), count disagreements
+//     (:1391-1431), and write ONE voted C tile.
+// Unit = one C element (the `mm_t` store, mm_common_tmr.c:16); local unit index = i*N + j.
+// Fault site 0 = the replica's final accumulator value (32 bits) as read back for the vote.
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4..7 = epilogue (TMEM lane quarter = warp % 4).  Persistent CTAs, one per SM, tile = 128 x 128.
+#pragma once
+#include "xmr_common.cuh"
+
+namespace xmr {
+namespace gemm {
+
+constexpr int BM = 128, BN = 128, BK = 32;          // BK fp32 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;                            // 32 bytes of tf32
+constexpr int STAGES = 6;
+constexpr uint32_t A_STAGE = BM * BK * 4;            // 16 KiB
+constexpr uint32_t B_STAGE = BK * BN * 4;            // 16 KiB, laid out [BN/32 chunks][BK rows][128 B]
+constexpr uint32_t SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t TMEM_COLS = 512;                  // 3 replicas x 128 fp32 columns (power of two >= 384)
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {      // arrives on `bar` when all previously issued MMAs retire
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread = TMEM lane (row), registers = columns
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), fixed 0b001 [46,49),
+// swizzle mode [61,64): 2 = SWIZZLE_128B (16-byte atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms).
+// Bring-up on the B200 (tools/probe/tc_probe.cu): an MN-major TF32 operand is only read correctly with the
+// 32-byte-atom swizzle (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); with plain SWIZZLE_128B the MMA returns zeros.
+constexpr uint32_t SWZ_128B = 2, SWZ_128B_BASE32B = 1;
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t swizzle) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)swizzle << 61);
+}
+// Instruction descriptor (InstrDescriptor): c_format F32 (1) [4,6), a/b_format TF32 (2) [7,10)/[10,13),
+// a_major K (0) [15], b_major MN (1) [16] (B is row-major K x N: N contiguous), N>>3 [17,23), M>>4 [24,29)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+template <int NC, bool INJECT>
+__device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* map_a, const CUtensorMap* map_b) {
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023u) & ~(uintptr_t)1023u);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE + B_STAGE));
+    uint64_t* full = bars;                 // [STAGES]  TMA -> MMA
+    uint64_t* empty = bars + STAGES;       // [STAGES]  MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * STAGES;       // MMA -> epilogue
+    uint64_t* tmem_empty = bars + 2 * STAGES + 1;  // epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tiles_n = a.N / BN, tiles_m = a.M / BM, n_tiles = tiles_m * tiles_n, kblocks = a.K / BK;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(map_a); tma_prefetch_desc(map_b);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 128);
+        fence_barrier_init();
+    }
+    if (warp == 2) {                                            // one warp allocates TMEM and later frees it
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int m0 = (int)(tile / tiles_n) * BM, n0 = (int)(tile % tiles_n) * BN;
+            for (uint32_t kb = 0; kb < kblocks; ++kb, ++it) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&full[s], A_STAGE + B_STAGE);
+                tma_load_2d(sA + s * A_STAGE, map_a, &full[s], (int)(kb * BK), m0);              // box {32 k, 128 m}
+                tma_load_3d(sB + s * B_STAGE, map_b, &full[s], 0, (int)(kb * BK), n0 / 32);      // box {32 n, 32 k, 4 chunks}
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer: every MMA is issued NC times into NC accumulators =====
+        uint32_t it = 0, tcount = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            mbar_wait(tmem_empty, (tcount & 1u) ^ 1u);         // epilogue drained the accumulators of the previous tile
+            tc_fence_after();
+            for (uint32_t kb = 0; kb < kblocks; ++kb, ++it) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + s * A_STAGE), b_addr = smem_u32(sB + s * B_STAGE);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    // A: K-major SW128, rows 128 B apart, 8-row groups 1024 B apart; advance 32 B per UMMA_K inside the swizzle row
+                    const uint64_t da = smem_desc(a_addr + k * UMMA_K * 4, 16, 1024, SWZ_128B);
+                    // B: MN-major, 32B-atom swizzle: atom = 4 k-rows x 128 B (512 B, SBO); N chunks BK*128 B apart (LBO);
+                    // one UMMA_K = 8 k-rows = 1024 B further down the chunk
+                    const uint64_t db = smem_desc(b_addr + k * 1024, BK * 128, 512, SWZ_128B_BASE32B);
+#pragma unroll
+                    for (int r = 0; r < NC; ++r)
+                        tc_mma_tf32(tmem_base + r * BN, da, db, IDESC, (kb | (uint32_t)k) ? 1u : 0u);
+                }
+                tc_commit(&empty[s]);                           // smem slot free once these MMAs retire
+            }
+            tc_commit(tmem_full);                               // accumulators complete
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers, vote, count, ONE store =====
+        const int q = warp & 3;                                 // TMEM lane quarter this warp may touch
+        const uint32_t flags = a.flags;
+        const bool majority = flags & COAST_F_MAJORITY_D;
+        float* C = static_cast<float*>(a.out);
+        Tally tally;
+        uint32_t tcount = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            const uint32_t m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            mbar_wait(tmem_full, tcount & 1u);
+            tc_fence_after();
+            const uint32_t row = m0 + q * 32 + lane;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[3][32];
+#pragma unroll
+                for (int r = 0; r < NC; ++r) tc_ld_32x32(lane_addr + r * BN + c0, v[r]);
+                tc_wait_ld();
+                float* dst = C + (size_t)row * a.N + n0 + c0;
+                const unsigned long long local0 = (unsigned long long)row * a.N + n0 + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        uint32_t r0 = v[0][j + e], r1 = NC > 1 ? v[1][j + e] : r0, r2 = NC > 2 ? v[2][j + e] : r0;
+                        if (INJECT) {
+                            Fault f = fault_for_unit(a, NC, local0 + j + e, [](uint32_t) { return 32u; });
+                            if (f.active) {
+                                tally.injected++;
+                                uint32_t mk = 1u << f.bit;
+                                if (f.replica == 0) r0 ^= mk; else if (f.replica == 1) r1 ^= mk; else r2 ^= mk;
+                            }
+                        }
+                        const float f0 = __uint_as_float(r0), f1 = __uint_as_float(r1), f2 = __uint_as_float(r2);
+                        uint32_t vote = r0, bad = 0;
+                        if (NC == 2) bad = (f0 == f1) ? 0u : 1u;
+                        if (NC == 3) {
+                            const bool c01 = (f0 == f1), c02 = (f0 == f2);       // fcmp oeq
+                            vote = majority ? ((r0 & r1) | (r0 & r2) | (r1 & r2)) : (c01 ? r0 : r2);
+                            bad = (c01 && c02) ? 0u : 1u;
+                        }
+                        o[e] = vote;
+                        tally.unit_exit<NC>(bad, 1u, flags, a.unit_base + local0 + j + e);
+                    }
+                    *reinterpret_cast<uint4*>(dst + j) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tmem_empty);                            // 128 arrivals release the accumulators
+        }
+        tally.flush(a.counters);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace gemm
+}  // namespace xmr
+
+#define XMR_GEMM_KERNEL(NC, INJ)                                                                         \
+    extern "C" __global__ void __launch_bounds__(256, 1)                                                 \
+    xmr_gemm_tf32_nc##NC##_inj##INJ(const __grid_constant__ xmr_args a, const __grid_constant__ CUtensorMap map_a, \
+                                    const __grid_constant__ CUtensorMap map_b) {                         \
+        xmr::gemm::gemm_body<NC, INJ != 0>(a, &map_a, &map_b);                                           \
+    }
+XMR_GEMM_KERNEL(1, 0) XMR_GEMM_KERNEL(2, 0) XMR_GEMM_KERNEL(3, 0)
+XMR_GEMM_KERNEL(1, 1) XMR_GEMM_KERNEL(2, 1) XMR_GEMM_KERNEL(3, 1)

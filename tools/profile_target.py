@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--kernel", choices=["sha256", "aes", "crc16", "mm"], default="sha256")
+    ap.add_argument("--kernel", choices=["sha256", "aes", "crc16", "mm", "gemm"], default="sha256")
     ap.add_argument("--nc", type=int, default=3)
     ap.add_argument("--log2n", type=int, default=20)
     ap.add_argument("--iters", type=int, default=3)
@@ -43,6 +43,14 @@ def main():
         out = torch.empty(n * 16, dtype=torch.uint8, device="cuda")
         d = rt.make_desc(cb.K_AES128, a.nc, d_in, out, n, flags=flags, key=bytes(16), plan=plan)
         alg = n * 32
+    elif a.kernel == "gemm":
+        s = a.side
+        A = torch.rand(s * s, dtype=torch.float32, device="cuda") * 2 - 1
+        B = torch.rand(s * s, dtype=torch.float32, device="cuda") * 2 - 1
+        out = torch.empty(s * s, dtype=torch.float32, device="cuda")
+        d = rt.make_desc(cb.K_GEMM_TF32, a.nc, A, out, s * s, flags=flags, M=s, N=s, K=s, d_aux=B, plan=plan)
+        alg = 3 * s * s * 4
+        flops = 2.0 * s * s * s
     else:
         s = a.side
         A = torch.empty(s * s, dtype=torch.int32, device="cuda"); rt.fill_philox(A, 4)
@@ -61,6 +69,8 @@ def main():
         best = min(ms)
         print(f"{a.kernel} nc={a.nc} n={n} inject={a.inject}: best {best:.4f} ms, median {sorted(ms)[len(ms)//2]:.4f} ms, "
               f"{alg / best / 1e6:.1f} GB/s algorithmic; stats={st.as_dict()}")
+        if a.kernel == "gemm":
+            print(f"   useful {flops / best / 1e9:.1f} TFLOP/s, issued {a.nc * flops / best / 1e9:.1f} TFLOP/s (tf32)")
 
 
 if __name__ == "__main__":
