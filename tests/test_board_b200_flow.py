@@ -1,0 +1,75 @@
+"""The BOARD=b200 make flow (include/makefiles/Makefile.common): the reference's UNCHANGED test directories
+build against libcoast_rt.so -- `make -C <coast>/tests/<t> LEVEL=<repo>/include BOARD=b200 exe`.
+
+CPU part (needs the reference checkout): the flow builds, the coast pass redirected the protected-region calls,
+the binary links the runtime.  GPU part: the binaries built here travel with the snapshot (oracle/_ref/b200/, where
+every output of compiling reference sources goes) and must print what the reference harness greps for."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/tests"
+OUT = os.path.join(ROOT, "oracle", "_ref", "b200")
+
+# test dir, TARGET, extra make vars, runtime entry the pass must have wired in, expected stdout regex, expected exit code
+CASES = [
+    ("crc16", "crc16", [], "coast_xmr_crc16", r"result: 5ba3", 0),                                  # crc16.c:42
+    ("aes", "aes", [], "coast_xmr_aes_enc_dec", r"Number of errors: 0", 0),                         # aes.c:114 (568 NIST KATs)
+    ("matrixMultiply", "matrixMultiply", [], "coast_xmr_matrix_multiply", r"Number of errors: 0", 0),   # unittest/cfg/full.yml:2-3
+    ("sha256_common", "sha256_tmr", ["SRCFILES={ref}/sha256_common/sha256_tmr.c"], "coast_xmr_sha256_hash",
+     r"C:0 E:0 F:0 T:0us", 0),                                                                      # sha256_tmr.c:30
+    ("mm_common", "mm_tmr", ["SRCFILES={ref}/mm_common/mm_tmr.c", "TARGET=mm_tmr", "OPT_PASSES=-TMR -countErrors"],
+     "coast_xmr_matrix_multiply", r"Error\?: 0", 0),                                                # mm_tmr.c:38
+]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout absent (GPU box)")
+@pytest.mark.parametrize("tdir,target,extra,entry,_re,_rc", CASES)
+def test_unchanged_reference_tests_build_against_the_runtime(built_lib, tdir, target, extra, entry, _re, _rc):
+    cmd = ["make", "-s", "-C", os.path.join(REF, tdir), f"LEVEL={ROOT}/include", "BOARD=b200", "-B"] + \
+          [e.format(ref=REF) for e in extra] + ["exe"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    exe = os.path.join(OUT, target, target + ".out")
+    assert os.path.exists(exe)
+    asm = "".join(open(os.path.join(OUT, target, f)).read() for f in os.listdir(os.path.join(OUT, target)) if f.endswith(".xmr.s"))
+    assert re.search(r"call\s+" + entry + r"@PLT", asm), "the pass did not redirect the protected-region call"
+    needed = subprocess.run(["readelf", "-d", exe], capture_output=True, text=True).stdout
+    assert "libcoast_rt.so" in needed
+    glue = open(os.path.join(OUT, target, "coast_glue.c")).read()
+    assert "coast_set_opt_passes" in glue
+
+
+def test_coast_h_has_the_full_macro_surface():
+    """every macro of the reference's tests/COAST.h:11-67 exists, and the header is gcc-clean in all positions the tests use"""
+    src = r'''
+    #include <stddef.h>
+    #include "COAST.h"
+    __DEFAULT_NO_xMR
+    unsigned __xMR g1[4]; unsigned __NO_xMR g2[4]; int __COAST_VOLATILE keep;
+    int checkGolden() __NO_xMR { int __xMR n = 0; return n; }
+    void __xMR f1(void) {}  __attribute__((noinline)) int __xMR f2(int a) { return a; }
+    void isr(void) __ISR_FUNC; int rv(void) __xMR_RET_VAL; int pl(void) __xMR_PROT_LIB; int ac(int*) __xMR_ALL_AFTER_CALL;
+    int __xMR_AFTER_CALL(scanf, 1_2)(const char*, ...);
+    MALLOC_WRAPPER_REGISTER(my_malloc); PRINTF_WRAPPER_REGISTER(my_printf); void* GENERIC_COAST_WRAPPER(thing)(void);
+    void ig(void) __COAST_IGNORE_GLOBAL(g1); void na(int a, int b) __NO_xMR_ARG(1); void ni(void) __COAST_NO_INLINE;
+    void fc(void) __xMR_FN_CALL; void sk(void) __SKIP_FN_CALL;
+    int main(void) { void* p = MALLOC_WRAPPER_CALL(my_malloc, 4); (void)p; return __xMR_DEFAULT_BEHAVIOR__; }
+    '''
+    res = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"), "-x", "c", "-"],
+                         input=src, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tdir,target,extra,entry,regex,rc", CASES)
+def test_unchanged_reference_tests_run_on_the_gpu(tdir, target, extra, entry, regex, rc):
+    exe = os.path.join(OUT, target, target + ".out")
+    if not os.path.exists(exe):
+        pytest.skip("binary was not built on the CPU box (needs the reference checkout)")
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == rc, res.stdout + res.stderr          # unittest.py:76-78: non-zero exit = fail
+    assert re.search(regex, res.stdout), res.stdout + res.stderr   # unittest.py:80-86 regex on stdout
