@@ -355,3 +355,40 @@ def test_reference_entry_points(rt, oracle, golden):
     A = (C.c_uint32 * 81)(*mm["u32_first"]); B = (C.c_uint32 * 81)(*mm["u32_second"]); R = (C.c_uint32 * 81)()
     L.coast_xmr_matrix_multiply_u32(A, B, R, 9)
     assert list(R) == mm["u32_results"]
+
+
+# ------------------------------------------------------------------------------------------ edge cases
+def test_empty_and_degenerate_inputs(rt, oracle):
+    import torch
+    import coast_b200 as cb
+    dummy = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    # n_units == 0 is a no-op, not an error
+    d = rt.make_desc(cb.K_SHA256, 3, dummy, out, 0, unit_bytes=64)
+    rt.launch(d)
+    st = rt.sync()
+    assert st.as_dict() == cb.Stats().as_dict()
+    # the empty message (unit_bytes == 0)
+    o, _ = rt.run(cb.K_SHA256, 3, dummy, 5, unit_bytes=0, flags=3)
+    assert host(o)[:32].tobytes() == hashlib.sha256(b"").digest() and host(o)[128:160].tobytes() == hashlib.sha256(b"").digest()
+    # crc16's length is an `unsigned char` (crc16.c:21): 0 and >255 are rejected loudly
+    for bad in (0, 256):
+        with pytest.raises(cb.CoastError):
+            rt.run(cb.K_CRC16, 3, dummy, 1, unit_bytes=bad)
+    with pytest.raises(cb.CoastError):
+        rt.run(cb.K_SHA256, 4, dummy, 1, unit_bytes=64)            # num_clones must be 1, 2 or 3
+    with pytest.raises(cb.CoastError):
+        rt.run(cb.K_GEMM_TF32, 3, dummy, 100 * 100, M=100, N=100, K=100, aux=dummy)   # tile constraint stated, not silently padded
+
+
+def test_sha256_long_message_multi_block_faults_in_late_blocks(rt, oracle):
+    """4000-byte messages = 63 compressions: fault sites in every block index are reachable and agree with the oracle"""
+    n, L = 12, 4000
+    m = msgs(oracle, n, L, 12)
+    ns = oracle.fault_sites(oracle.K_SHA256, L)
+    assert ns == 63 * 536
+    tab = np.zeros(n, dtype=np.uint32)
+    for u in range(n):
+        tab[u] = oracle.fault_entry(u % 3, (u * 2999 + 17) % ns, (u * 7) % 32)
+    both(rt, oracle, oracle.K_SHA256, 3, m, n, unit_bytes=L, flags=3, table=tab)
+    both(rt, oracle, oracle.K_SHA256, 2, m, n, unit_bytes=L, flags=3, table=tab)
