@@ -282,12 +282,13 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": "sha256 TMR, 2^20 x 64-byte messages per GPU (BASELINE configs[1])",
                        "units_per_gpu": n, "unit_bytes": UNIT_BYTES, "protection": "-TMR -countErrors -countSyncs",
-                       "voter": "select (r0==r1?r0:r2), warp shuffle, 32 u8 votes/unit",
+                       "voter": "select (r0==r1?r0:r2), 32 u8 votes/unit",
+                       "layout": "-s: replicas on adjacent warps, SoR-exit exchange through shared memory (default; -i = adjacent lanes + warp shuffle)",
                        "l2": f"{NSETS} rotating in/out buffer sets = {NSETS * n * ALG_BYTES_PER_UNIT >> 20} MiB > 126 MB L2",
                        "parallelism": f"shard{world}" if world > 1 else "1gpu"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "xmr_sha256_b64_nc3_inj0", "kernel_ms": round(k_ms, 5),
+                         "kernel": "xmr_sha256_b64_seg_nc3_inj0", "kernel_ms": round(k_ms, 5),
                          "algorithmic_bytes_per_launch": n * ALG_BYTES_PER_UNIT,
                          "note": "integer-issue bound, not HBM bound: see DESIGN.md section 5 (ALU ceiling)"},
             "e2e": {"value": round(world * n * OUT_BYTES / e2e_s / 1e6, 1), "unit": "MB/s",

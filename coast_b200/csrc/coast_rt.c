@@ -131,7 +131,7 @@ static int ensure_ctx(void) {
     return COAST_OK;
 }
 
-static int get_fn(const char* name, unsigned smem, CUfunction* fn, int* ctas_per_sm) {
+static int get_fn_b(const char* name, unsigned smem, int block, CUfunction* fn, int* ctas_per_sm) {
     for (int i = 0; i < G.n_fns; ++i)
         if (!strcmp(G.fns[i].name, name) && G.fns[i].smem == smem) { *fn = G.fns[i].fn; if (ctas_per_sm) *ctas_per_sm = G.fns[i].ctas_per_sm; return COAST_OK; }
     CUfunction f;
@@ -139,7 +139,7 @@ static int get_fn(const char* name, unsigned smem, CUfunction* fn, int* ctas_per
     if (r != CUDA_SUCCESS) return drv_fail(r, name);
     if (smem > 48 * 1024) DRV(p_cuFuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
     int occ = 1;
-    DRV(p_cuOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f, XMR_CTA_THREADS, smem));
+    DRV(p_cuOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f, block, smem));
     if (occ < 1) occ = 1;
     if (G.n_fns < MAX_FN) {
         snprintf(G.fns[G.n_fns].name, sizeof G.fns[0].name, "%s", name);
@@ -148,6 +148,10 @@ static int get_fn(const char* name, unsigned smem, CUfunction* fn, int* ctas_per
     }
     *fn = f; if (ctas_per_sm) *ctas_per_sm = occ;
     return COAST_OK;
+}
+
+static int get_fn(const char* name, unsigned smem, CUfunction* fn, int* ctas_per_sm) {
+    return get_fn_b(name, smem, XMR_CTA_THREADS, fn, ctas_per_sm);
 }
 
 static int launch_small(const char* name, unsigned grid, unsigned block, void** params, CUstream s) {
@@ -373,7 +377,7 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
     a.n_sites = coast_fault_sites(d->kernel, d->unit_bytes, d->K);
 
     char name[64];
-    unsigned smem = 0; int tma = 0;
+    unsigned smem = 0; int tma = 0; int block = XMR_CTA_THREADS;
     unsigned tile_rows = 0, row_bytes = 0; CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_NONE;
     const int aligned16 = (((uintptr_t)d->d_in) & 15u) == 0;
     switch (d->kernel) {
@@ -382,6 +386,13 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
             tma = 1; tile_rows = XMR_WARPS * upw; row_bytes = 64; swz = CU_TENSOR_MAP_SWIZZLE_64B;
             smem = ring_smem(tile_rows, row_bytes);
             snprintf(name, sizeof name, "xmr_sha256_b64_nc%u_inj%d", nc, inj);
+            /* TMR replica scheduling: -s (segmented, the reference default, interface.cpp:245-247) = replicas on
+             * adjacent warps; -i (interleaved) = replicas on adjacent lanes.  Results are identical. */
+            if (nc == 3 && !(d->flags & COAST_F_INTERLEAVE)) {
+                block = 384; tile_rows = 128;
+                smem = ((ring_smem(tile_rows, row_bytes) + 127u) & ~127u) + 2u * 4u * 2u * 8u * 32u * 4u;
+                snprintf(name, sizeof name, "xmr_sha256_b64_seg_nc3_inj%d", inj);
+            }
         } else {
             snprintf(name, sizeof name, "xmr_sha256_gen_nc%u_inj%d", nc, inj);
         }
@@ -426,7 +437,7 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
     if (d->kernel == COAST_K_SHA256 && (((uintptr_t)d->d_out) & 15u)) return fail(COAST_ERR_BAD_ARG, "SHA output must be 16-byte aligned");
 
     CUfunction fn; int occ = 1;
-    rc = get_fn(name, smem, &fn, &occ); if (rc) return rc;
+    rc = get_fn_b(name, smem, block, &fn, &occ); if (rc) return rc;
     unsigned grid;
     CUtensorMap map;
     void* params[2] = { &a, &map };
@@ -444,9 +455,9 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
         grid = (unsigned)(ctas < cap ? ctas : cap);
     }
     if (d->flags & COAST_F_VERBOSE)
-        fprintf(stderr, "coast_rt: %s grid=%u block=%d smem=%u units=%llu\n", name, grid, XMR_CTA_THREADS, smem,
+        fprintf(stderr, "coast_rt: %s grid=%u block=%d smem=%u units=%llu\n", name, grid, block, smem,
                 (unsigned long long)d->n_units);
-    DRV(p_cuLaunchKernel(fn, grid, 1, 1, XMR_CTA_THREADS, 1, 1, smem, (CUstream)stream, params, NULL));
+    DRV(p_cuLaunchKernel(fn, grid, 1, 1, (unsigned)block, 1, 1, smem, (CUstream)stream, params, NULL));
     return COAST_OK;
 }
 

@@ -221,6 +221,99 @@ __device__ __forceinline__ void sha256_gen_body(const xmr_args& a) {
     tally.flush(a.counters);
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMR, segmented layout (-s, the reference's default replica scheduling, interface.cpp:245-247):
+// the three replicas of a unit sit on the SAME lane of three ADJACENT WARPS, so all 32 lanes of every
+// warp carry a unit (the interleaved layout idles 2 of 32 lanes).  CTA = 12 warps = 4 groups x 3 replica
+// warps; tile = 128 messages through the same TMA ring.  SoR exit: replica warps 1 and 2 publish their
+// state through shared memory, a 96-thread named barrier per group orders it, warp 0 of the group votes
+// (same select voter / counters) and stores 32 lanes x 32 B = 1 KiB contiguous.
+// ---------------------------------------------------------------------------------------------
+constexpr int SEG_THREADS = 384, SEG_GROUPS = 4, SEG_TU = SEG_GROUPS * 32;
+
+template <bool INJECT>
+__device__ __forceinline__ void sha256_b64_seg_body(const xmr_args& a, const CUtensorMap* tmap) {
+    using Ring = TileRing<SEG_TU, 64>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    Ring ring;
+    ring.init(smem_raw, tmap);
+    // exchange buffer [parity][group][replica 1..2][word][lane]
+    uint32_t* exch = reinterpret_cast<uint32_t*>(smem_raw + ((Ring::SMEM_BYTES + 127u) & ~127u));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = warp / 3, r = warp - 3 * g;
+    const int ul = g * 32 + lane;
+    const uint32_t n_tiles = a.n_tiles;
+    const bool majority = a.flags & COAST_F_MAJORITY_D;
+    uint32_t tile = blockIdx.x;
+    if (tile < n_tiles) ring.issue(0, tile);
+    Tally tally;
+    uint32_t it = 0;
+    for (; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t next = tile + gridDim.x;
+        if (next < n_tiles) ring.issue((it + 1u) & 1u, next);
+        const uint8_t* base = ring.wait(it);
+        uint32_t m[16];
+        const uint8_t* row = base + ul * 64;
+        const int sw = (ul >> 1) & 3;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint4 q = *reinterpret_cast<const uint4*>(row + ((c ^ sw) << 4));
+            m[4 * c + 0] = bswap(q.x); m[4 * c + 1] = bswap(q.y); m[4 * c + 2] = bswap(q.z); m[4 * c + 3] = bswap(q.w);
+        }
+        __syncthreads();
+        const unsigned long long local = (unsigned long long)tile * SEG_TU + ul;
+        const bool valid = local < a.n_units;
+        uint32_t fs0 = 0xFFFFFFFFu, fs1 = 0xFFFFFFFFu, fmask = 0u;
+        if (INJECT) {
+            Fault f = fault_for_unit(a, 3, valid ? local : 0ull, [](uint32_t) { return 32u; });
+            if (f.active && valid) {
+                if (r == 0) tally.injected++;
+                if ((int)f.replica == r) {
+                    fmask = 1u << f.bit;
+                    if (f.site < SHA_SITES_PER_BLOCK) fs0 = f.site; else fs1 = f.site - SHA_SITES_PER_BLOCK;
+                }
+            }
+        }
+        uint32_t st[8];
+        sha_init(st);
+        sha_compress<INJECT>(st, m, fs0, fmask);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) m[i] = 0u;
+        m[0] = 0x80000000u; m[15] = 512u;
+        sha_compress<INJECT>(st, m, fs1, fmask);
+
+        uint32_t* ex = exch + ((it & 1u) * SEG_GROUPS + g) * (2 * 8 * 32);
+        if (r > 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ex[((r - 1) * 8 + i) * 32 + lane] = st[i];
+        }
+        // the group's 3 warps (96 threads); ids are immediates so only 5 hardware barriers are reserved (0 = __syncthreads)
+        if (g == 0) asm volatile("bar.sync 1, 96;" ::: "memory");
+        else if (g == 1) asm volatile("bar.sync 2, 96;" ::: "memory");
+        else if (g == 2) asm volatile("bar.sync 3, 96;" ::: "memory");
+        else asm volatile("bar.sync 4, 96;" ::: "memory");
+        if (r == 0) {
+            uint32_t o[8], bad = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t x = st[i], r1 = ex[i * 32 + lane], r2 = ex[(8 + i) * 32 + lane];
+                const uint32_t e01 = __vcmpeq4(x, r1), e02 = __vcmpeq4(x, r2);
+                const uint32_t v = majority ? ((x & r1) | (x & r2) | (r1 & r2)) : ((x & e01) | (r2 & ~e01));
+                bad += __popc(~(e01 & e02)) >> 3;
+                o[i] = bswap(v);
+            }
+            if (valid) {
+                uint4* dst = reinterpret_cast<uint4*>(static_cast<uint8_t*>(a.out) + local * 32ull);
+                dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                tally.unit_exit<3>(bad, 32u, a.flags, a.unit_base + local);
+            }
+        }
+        // exch is double-buffered by tile parity; the __syncthreads of the next iteration orders its reuse
+    }
+    tally.flush(a.counters);
+}
+
 }  // namespace xmr
 
 #define XMR_SHA_B64_KERNEL(NC, INJ)                                                                      \
@@ -237,3 +330,10 @@ XMR_SHA_B64_KERNEL(1, 0) XMR_SHA_B64_KERNEL(2, 0) XMR_SHA_B64_KERNEL(3, 0)
 XMR_SHA_B64_KERNEL(1, 1) XMR_SHA_B64_KERNEL(2, 1) XMR_SHA_B64_KERNEL(3, 1)
 XMR_SHA_GEN_KERNEL(1, 0) XMR_SHA_GEN_KERNEL(2, 0) XMR_SHA_GEN_KERNEL(3, 0)
 XMR_SHA_GEN_KERNEL(1, 1) XMR_SHA_GEN_KERNEL(2, 1) XMR_SHA_GEN_KERNEL(3, 1)
+
+#define XMR_SHA_B64_SEG_KERNEL(INJ)                                                                      \
+    extern "C" __global__ void __launch_bounds__(xmr::SEG_THREADS)                                       \
+    xmr_sha256_b64_seg_nc3_inj##INJ(const __grid_constant__ xmr_args a, const __grid_constant__ CUtensorMap tmap) { \
+        xmr::sha256_b64_seg_body<INJ != 0>(a, &tmap);                                                    \
+    }
+XMR_SHA_B64_SEG_KERNEL(0) XMR_SHA_B64_SEG_KERNEL(1)

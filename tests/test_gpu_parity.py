@@ -392,3 +392,11 @@ def test_sha256_long_message_multi_block_faults_in_late_blocks(rt, oracle):
         tab[u] = oracle.fault_entry(u % 3, (u * 2999 + 17) % ns, (u * 7) % 32)
     both(rt, oracle, oracle.K_SHA256, 3, m, n, unit_bytes=L, flags=3, table=tab)
     both(rt, oracle, oracle.K_SHA256, 2, m, n, unit_bytes=L, flags=3, table=tab)
+
+
+@pytest.mark.parametrize("layout_flag", [0x8, 0x10])      # -i (adjacent lanes) / -s (adjacent warps, the default)
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 127, 128, 129, 1000, 4099])
+def test_sha256_tmr_layouts_give_identical_results(rt, oracle, layout_flag, n):
+    m = msgs(oracle, n, 64, 21)
+    both(rt, oracle, oracle.K_SHA256, 3, m, n, unit_bytes=64, flags=3 | layout_flag)
+    both(rt, oracle, oracle.K_SHA256, 3, m, n, unit_bytes=64, flags=3 | layout_flag, plan_kw=dict(seed=n, p=0.25))

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--inject", type=float, default=0.0)
     ap.add_argument("--side", type=int, default=1024)
+    ap.add_argument("--flags", type=lambda x: int(x, 0), default=0, help="extra COAST_F_* bits, e.g. 0x8 = -i, 0x10 = -s")
     ap.add_argument("--time", action="store_true", help="print CUDA-event ms per launch (outside any profiler)")
     a = ap.parse_args()
     import torch
@@ -27,7 +28,7 @@ def main():
     rt = cb.Runtime(0)
     n = 1 << a.log2n
     plan = cb.FaultPlan(mode=cb.PLAN_BERNOULLI, seed=7, p=a.inject) if a.inject > 0 else None
-    flags = cb.F_COUNT_ERRORS | cb.F_COUNT_SYNCS
+    flags = cb.F_COUNT_ERRORS | cb.F_COUNT_SYNCS | a.flags
     if a.kernel == "sha256":
         d_in = torch.empty(n * 64, dtype=torch.uint8, device="cuda"); rt.fill_philox(d_in, 2)
         out = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
