@@ -411,9 +411,9 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
         if ((d->mode & COAST_AES_KEY_PER_UNIT) && !d->d_aux) return fail(COAST_ERR_BAD_ARG, "per-unit keys need d_aux");
         if (!aligned16 || (((uintptr_t)d->d_out) & 15u)) return fail(COAST_ERR_BAD_ARG, "AES buffers must be 16-byte aligned");
         if (!(d->mode & (COAST_AES_DECRYPT | COAST_AES_KEY_PER_UNIT)) && d->n_units < 0x7FFFFF00ull) {
-            tma = 1; tile_rows = XMR_WARPS * upw * 4u; row_bytes = 16;
-            unsigned ring = ring_smem(tile_rows, row_bytes);
-            smem = ((ring + 1023u) & ~1023u) + 256u * 32u * 4u;
+            /* 512-thread CTAs; the shared window [0, 0x30000) holds the ring and the two 64 KiB-aligned T-tables */
+            tma = 1; block = 512; tile_rows = 16u * upw * (nc == 1 ? 2u : 4u); row_bytes = 16;
+            smem = 0x30000u;
             snprintf(name, sizeof name, "xmr_aes128_enc_nc%u_inj%d", nc, inj);
         } else {
             snprintf(name, sizeof name, "xmr_aes128_gen_nc%u_inj%d", nc, inj);
@@ -445,6 +445,7 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
         uint64_t n_tiles = (d->n_units + tile_rows - 1) / tile_rows;
         a.n_tiles = (unsigned)n_tiles;
         unsigned loads = (tile_rows + 255u) / 256u;
+        while (tile_rows % loads) ++loads;                        /* mirrors TileRing::pick_loads() */
         rc = encode_rows_map(&map, d->d_in, row_bytes, d->n_units, tile_rows / loads, swz); if (rc) return rc;
         uint64_t cap = (uint64_t)G.sm_count * (unsigned)occ;
         grid = (unsigned)(n_tiles < cap ? n_tiles : cap);

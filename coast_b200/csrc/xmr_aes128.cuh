@@ -5,8 +5,9 @@
 //   xmr_aes128_enc  : encrypt, one ECB key (BASELINE config 3).  Column/T-table formulation of the
 //                     same rounds: AddRoundKey-then-SubBytes (:143-146), ShiftRows (:147-166),
 //                     MixColumns (:169-184), forward key schedule (:214-221), last AddRoundKey (:224-229).
-//                     TE0 is replicated 32x in shared memory as te[x][lane] so every lookup is
-//                     bank-conflict free whatever the data; blocks arrive through the TMA tile ring.
+//                     TE0..TE3 are replicated 32x in shared memory (row x = 32 lanes of TE_k[x]) so every lookup
+//                     is bank-conflict free whatever the data and its address is ONE byte-permute; blocks
+//                     arrive through the TMA tile ring.
 //   xmr_aes128_gen  : byte-wise restatement that follows the TI control flow literally; handles
 //                     decrypt (dir=1, :112-129,133-141,187-212) and per-unit keys (the 568 KATs).
 // Fault sites (identical in oracle/): 0..15 = state byte as loaded; 16+16r+i = state[i] at the
@@ -18,19 +19,26 @@
 
 namespace xmr {
 
-constexpr int AES_J = 4;   // blocks per lane group per tile (ILP across independent blocks)
+// ---- T-table kernel geometry --------------------------------------------------------------------
+// 512-thread CTAs, one per SM.  Shared-memory WINDOW layout (absolute shared::cta addresses):
+//   [dyn base .. 0x10000)  TMA tile ring (2 stages)
+//   [0x10000 .. 0x20000)   row x (256 B): TE0[x] replicated over 32 lanes | TE1[x] = rotl8  replicated over 32 lanes
+//   [0x20000 .. 0x30000)   row x (256 B): TE2[x] = rotl16 x 32 lanes     | TE3[x] = rotl24 x 32 lanes
+// Row stride 256 B + 64 KiB alignment make the lookup address ONE byte-permute:
+//   addr = PRMT(t, lanebase) = lanebase.b3 : lanebase.b2 : byte_k(t) : lanebase.b0,  lanebase = table | half | lane*4
+// and bank = lane for every lane whatever the data -> no shared-memory bank conflicts, no rotates, no LEA.
+// (r01 first version: one TE0 copy + PRMT rotates + SHF/LOP3/LEA per lookup = 975 instructions per block; ncu showed
+//  the ALU pipe at 95 %.)
+constexpr int AES_THREADS = 512, AES_WARPS = 16;
+constexpr uint32_t AES_TAB01 = 0x10000u, AES_TAB23 = 0x20000u, AES_WINDOW_END = 0x30000u;
+template <int NC> struct AesGeom { static constexpr int J = NC == 1 ? 2 : 4; static constexpr int TROWS = AES_WARPS * Lanes<NC>::kUnitsPerWarp * J; };
 
-__device__ __forceinline__ uint32_t rotl8(uint32_t v) { return __byte_perm(v, 0u, 0x2103u); }
-__device__ __forceinline__ uint32_t rotl16(uint32_t v) { return __byte_perm(v, 0u, 0x1032u); }
-__device__ __forceinline__ uint32_t rotl24(uint32_t v) { return __byte_perm(v, 0u, 0x0321u); }
-
-// te points at this lane's column of the replicated table: te[x * 32]
-__device__ __forceinline__ uint32_t te_b0(const uint32_t* te, uint32_t t) { return te[(t & 0xFFu) << 5]; }
-__device__ __forceinline__ uint32_t te_b1(const uint32_t* te, uint32_t t) { return te[((t >> 8) & 0xFFu) << 5]; }
-__device__ __forceinline__ uint32_t te_b2(const uint32_t* te, uint32_t t) { return te[((t >> 16) & 0xFFu) << 5]; }
-__device__ __forceinline__ uint32_t te_b3(const uint32_t* te, uint32_t t) { return te[(t >> 24) << 5]; }
-// S-box byte = byte 1 of TE0[x]
-__device__ __forceinline__ uint32_t sb(const uint32_t* te, uint32_t x) { return (te[x << 5] >> 8) & 0xFFu; }
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
+// table row of byte k of t: splice that byte into byte 1 of the lane's base address
+__device__ __forceinline__ uint32_t tab_b0(uint32_t lb, uint32_t t) { return lds32(__byte_perm(t, lb, 0x7604u)); }
+__device__ __forceinline__ uint32_t tab_b1(uint32_t lb, uint32_t t) { return lds32(__byte_perm(t, lb, 0x7614u)); }
+__device__ __forceinline__ uint32_t tab_b2(uint32_t lb, uint32_t t) { return lds32(__byte_perm(t, lb, 0x7624u)); }
+__device__ __forceinline__ uint32_t tab_b3(uint32_t lb, uint32_t t) { return lds32(__byte_perm(t, lb, 0x7634u)); }
 
 template <int NC>
 __device__ __forceinline__ void aes_vote_store(const uint32_t (&c)[4], uint8_t* out, unsigned long long local,
@@ -48,16 +56,28 @@ __device__ __forceinline__ void aes_vote_store(const uint32_t (&c)[4], uint8_t* 
 template <int NC, bool INJECT>
 __device__ __forceinline__ void aes128_enc_body(const xmr_args& a, const CUtensorMap* tmap) {
     constexpr int UPW = Lanes<NC>::kUnitsPerWarp;
-    constexpr int TROWS = XMR_WARPS * UPW * AES_J;
+    constexpr int J = AesGeom<NC>::J;
+    constexpr int TROWS = AesGeom<NC>::TROWS;
     using Ring = TileRing<TROWS, 16>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint32_t* te_all = reinterpret_cast<uint32_t*>(smem_raw + Ring::SMEM_BYTES + ((1024 - (Ring::SMEM_BYTES & 1023)) & 1023));
+    const uint32_t win = smem_u32(smem_raw);                    // shared-window address of the dynamic region
+    uint8_t* ring_mem = smem_raw + ((1024u - (win & 1023u)) & 1023u);
     Ring ring;
-    ring.init(smem_raw, tmap);
+    ring.init(ring_mem, tmap);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 256 * 32; i += XMR_CTA_THREADS) te_all[i] = XMR_AES_TE0[i >> 5];
+    {   // build the two 64 KiB tables
+        uint32_t* t01 = reinterpret_cast<uint32_t*>(smem_raw + (AES_TAB01 - win));
+        uint32_t* t23 = reinterpret_cast<uint32_t*>(smem_raw + (AES_TAB23 - win));
+        for (int i = tid; i < 256 * 64; i += AES_THREADS) {
+            const uint32_t v = XMR_AES_TE0[i >> 6];
+            const bool hi = (i & 32) != 0;
+            t01[i] = hi ? __byte_perm(v, 0u, 0x2103u) : v;                               // TE1 = rotl8
+            t23[i] = hi ? __byte_perm(v, 0u, 0x0321u) : __byte_perm(v, 0u, 0x1032u);     // TE3 = rotl24 : TE2 = rotl16
+        }
+    }
     __syncthreads();
-    const uint32_t* te = te_all + lane;
+    const uint32_t lb0 = AES_TAB01 + 4u * lane, lb1 = AES_TAB01 + 128u + 4u * lane;
+    const uint32_t lb2 = AES_TAB23 + 4u * lane, lb3 = AES_TAB23 + 128u + 4u * lane;
     const int r = Lanes<NC>::replica(lane);
     const int u = Lanes<NC>::unit(lane);
 
@@ -67,10 +87,11 @@ __device__ __forceinline__ void aes128_enc_body(const xmr_args& a, const CUtenso
     for (int i = 0; i < 4; ++i)
         rk[i] = (uint32_t)a.key[4 * i] | ((uint32_t)a.key[4 * i + 1] << 8) | ((uint32_t)a.key[4 * i + 2] << 16) | ((uint32_t)a.key[4 * i + 3] << 24);
 #pragma unroll
-    for (int rd = 0; rd < 10; ++rd) {                          // :214-221
-        uint32_t w = rk[4 * rd + 3];
-        uint32_t rw = __funnelshift_r(w, w, 8);                 // bytes (k13,k14,k15,k12)
-        uint32_t sw = sb(te, rw & 0xFFu) | (sb(te, (rw >> 8) & 0xFFu) << 8) | (sb(te, (rw >> 16) & 0xFFu) << 16) | (sb(te, rw >> 24) << 24);
+    for (int rd = 0; rd < 10; ++rd) {                          // :214-221; S-box byte = byte 1 of TE0 = byte 2 of TE1 ...
+        const uint32_t w = rk[4 * rd + 3];
+        // SubWord(RotWord(w)): bytes (S[w.b1], S[w.b2], S[w.b3], S[w.b0])
+        const uint32_t sw = (tab_b1(lb2, w) & 0x000000FFu) | (tab_b2(lb0, w) & 0x0000FF00u) |
+                            (tab_b3(lb0, w) & 0x00FF0000u) | (tab_b0(lb1, w) & 0xFF000000u);
         rk[4 * rd + 4] = rk[4 * rd] ^ sw ^ (uint32_t)XMR_AES_RCON[rd];
         rk[4 * rd + 5] = rk[4 * rd + 1] ^ rk[4 * rd + 4];
         rk[4 * rd + 6] = rk[4 * rd + 2] ^ rk[4 * rd + 5];
@@ -86,29 +107,38 @@ __device__ __forceinline__ void aes128_enc_body(const xmr_args& a, const CUtenso
         const uint32_t next = tile + gridDim.x;
         if (next < n_tiles) ring.issue((it + 1u) & 1u, next);
         const uint8_t* base = ring.wait(it);
-        uint32_t s[AES_J][4];
+        uint32_t s[J][4];
 #pragma unroll
-        for (int j = 0; j < AES_J; ++j) {
-            uint4 q = *reinterpret_cast<const uint4*>(base + ((warp * AES_J + j) * UPW + u) * 16);
+        for (int j = 0; j < J; ++j) {
+            uint4 q = *reinterpret_cast<const uint4*>(base + ((warp * J + j) * UPW + u) * 16);
             s[j][0] = q.x; s[j][1] = q.y; s[j][2] = q.z; s[j][3] = q.w;
         }
         __syncthreads();
 
-        unsigned long long local[AES_J];
-        bool valid[AES_J];
-        uint32_t fsite[AES_J], fmask[AES_J];
+        unsigned long long local[J];
+        bool valid[J];
+        // fault of block j as branch-free masks: column word fcol[j], shifted bit fbit[j], applied when frd[j] == round
+        // (frd = -1: the replica's input copy, before round 0)
+        uint32_t fbit[J]; int frd[J], fcol[J];
 #pragma unroll
-        for (int j = 0; j < AES_J; ++j) {
-            local[j] = (unsigned long long)tile * TROWS + (unsigned)((warp * AES_J + j) * UPW + u);
+        for (int j = 0; j < J; ++j) {
+            local[j] = (unsigned long long)tile * TROWS + (unsigned)((warp * J + j) * UPW + u);
             valid[j] = local[j] < a.n_units;
-            fsite[j] = 0xFFFFFFFFu; fmask[j] = 0u;
+            fbit[j] = 0u; frd[j] = -2; fcol[j] = 0;
             if (INJECT) {
                 Fault f = fault_for_unit(a, NC, valid[j] ? local[j] : 0ull, [](uint32_t) { return 8u; });
                 if (f.active && valid[j]) {
                     if (Lanes<NC>::voter(lane)) tally.injected++;
-                    if ((int)f.replica == r) { fsite[j] = f.site; fmask[j] = 1u << f.bit; }
+                    if ((int)f.replica == r) {
+                        const uint32_t i = f.site < 16u ? f.site : ((f.site - 16u) & 15u);
+                        frd[j] = f.site < 16u ? -1 : (int)((f.site - 16u) >> 4);
+                        fcol[j] = (int)(i >> 2);
+                        fbit[j] = (1u << f.bit) << (8u * (i & 3u));
+                    }
                 }
-                if (fsite[j] < 16u) s[j][fsite[j] >> 2] ^= fmask[j] << (8u * (fsite[j] & 3u));
+                const uint32_t hit = frd[j] == -1 ? fbit[j] : 0u;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) s[j][c] ^= fcol[j] == c ? hit : 0u;
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) s[j][c] ^= rk[c];       // first half of :143-146 (state ^ key)
@@ -116,30 +146,31 @@ __device__ __forceinline__ void aes128_enc_body(const xmr_args& a, const CUtenso
 #pragma unroll
         for (int rd = 0; rd < 10; ++rd) {
 #pragma unroll
-            for (int j = 0; j < AES_J; ++j) {
-                uint32_t t0 = s[j][0], t1 = s[j][1], t2 = s[j][2], t3 = s[j][3], n[4];
-                if (rd < 9) {                                   // SubBytes+ShiftRows+MixColumns via TE0
-                    n[0] = te_b0(te, t0) ^ rotl8(te_b1(te, t1)) ^ rotl16(te_b2(te, t2)) ^ rotl24(te_b3(te, t3));
-                    n[1] = te_b0(te, t1) ^ rotl8(te_b1(te, t2)) ^ rotl16(te_b2(te, t3)) ^ rotl24(te_b3(te, t0));
-                    n[2] = te_b0(te, t2) ^ rotl8(te_b1(te, t3)) ^ rotl16(te_b2(te, t0)) ^ rotl24(te_b3(te, t1));
-                    n[3] = te_b0(te, t3) ^ rotl8(te_b1(te, t0)) ^ rotl16(te_b2(te, t1)) ^ rotl24(te_b3(te, t2));
-                } else {                                        // round 9: no MixColumns (:168)
-                    n[0] = sb(te, t0 & 0xFFu) | (sb(te, (t1 >> 8) & 0xFFu) << 8) | (sb(te, (t2 >> 16) & 0xFFu) << 16) | (sb(te, t3 >> 24) << 24);
-                    n[1] = sb(te, t1 & 0xFFu) | (sb(te, (t2 >> 8) & 0xFFu) << 8) | (sb(te, (t3 >> 16) & 0xFFu) << 16) | (sb(te, t0 >> 24) << 24);
-                    n[2] = sb(te, t2 & 0xFFu) | (sb(te, (t3 >> 8) & 0xFFu) << 8) | (sb(te, (t0 >> 16) & 0xFFu) << 16) | (sb(te, t1 >> 24) << 24);
-                    n[3] = sb(te, t3 & 0xFFu) | (sb(te, (t0 >> 8) & 0xFFu) << 8) | (sb(te, (t1 >> 16) & 0xFFu) << 16) | (sb(te, t2 >> 24) << 24);
+            for (int j = 0; j < J; ++j) {
+                const uint32_t t0 = s[j][0], t1 = s[j][1], t2 = s[j][2], t3 = s[j][3];
+                uint32_t n[4];
+                if (rd < 9) {                                   // SubBytes + ShiftRows + MixColumns = 4 table rows XORed
+                    n[0] = tab_b0(lb0, t0) ^ tab_b1(lb1, t1) ^ tab_b2(lb2, t2) ^ tab_b3(lb3, t3);
+                    n[1] = tab_b0(lb0, t1) ^ tab_b1(lb1, t2) ^ tab_b2(lb2, t3) ^ tab_b3(lb3, t0);
+                    n[2] = tab_b0(lb0, t2) ^ tab_b1(lb1, t3) ^ tab_b2(lb2, t0) ^ tab_b3(lb3, t1);
+                    n[3] = tab_b0(lb0, t3) ^ tab_b1(lb1, t0) ^ tab_b2(lb2, t1) ^ tab_b3(lb3, t2);
+                } else {                                        // round 9: no MixColumns (:168); S[x] sits in byte p of the table picked per position
+                    n[0] = (tab_b0(lb2, t0) & 0x000000FFu) | (tab_b1(lb0, t1) & 0x0000FF00u) | (tab_b2(lb0, t2) & 0x00FF0000u) | (tab_b3(lb1, t3) & 0xFF000000u);
+                    n[1] = (tab_b0(lb2, t1) & 0x000000FFu) | (tab_b1(lb0, t2) & 0x0000FF00u) | (tab_b2(lb0, t3) & 0x00FF0000u) | (tab_b3(lb1, t0) & 0xFF000000u);
+                    n[2] = (tab_b0(lb2, t2) & 0x000000FFu) | (tab_b1(lb0, t3) & 0x0000FF00u) | (tab_b2(lb0, t0) & 0x00FF0000u) | (tab_b3(lb1, t1) & 0xFF000000u);
+                    n[3] = (tab_b0(lb2, t3) & 0x000000FFu) | (tab_b1(lb0, t0) & 0x0000FF00u) | (tab_b2(lb0, t1) & 0x00FF0000u) | (tab_b3(lb1, t2) & 0xFF000000u);
                 }
-                if (INJECT && fsite[j] >= 16u && (fsite[j] - 16u) >> 4 == (uint32_t)rd) {
-                    uint32_t i = (fsite[j] - 16u) & 15u;
+                if (INJECT) {
+                    const uint32_t hit = frd[j] == rd ? fbit[j] : 0u;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) if ((i >> 2) == (uint32_t)c) n[c] ^= fmask[j] << (8u * (i & 3u));
+                    for (int c = 0; c < 4; ++c) n[c] ^= fcol[j] == c ? hit : 0u;
                 }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) s[j][c] = n[c] ^ rk[4 * (rd + 1) + c];   // next round's / last AddRoundKey
             }
         }
 #pragma unroll
-        for (int j = 0; j < AES_J; ++j)
+        for (int j = 0; j < J; ++j)
             aes_vote_store<NC>(s[j], static_cast<uint8_t*>(a.out), local[j], a.unit_base + local[j], valid[j], lane, a.flags, tally);
     }
     tally.flush(a.counters);
@@ -266,7 +297,7 @@ __device__ __forceinline__ void aes128_gen_body(const xmr_args& a) {
 }  // namespace xmr
 
 #define XMR_AES_ENC_KERNEL(NC, INJ)                                                                      \
-    extern "C" __global__ void __launch_bounds__(XMR_CTA_THREADS)                                        \
+    extern "C" __global__ void __launch_bounds__(xmr::AES_THREADS, 1)                                    \
     xmr_aes128_enc_nc##NC##_inj##INJ(const __grid_constant__ xmr_args a, const __grid_constant__ CUtensorMap tmap) { \
         xmr::aes128_enc_body<NC, INJ != 0>(a, &tmap);                                                    \
     }

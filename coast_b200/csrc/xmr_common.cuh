@@ -187,16 +187,18 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 
 // ---------------------------------------------------------------- TMA tile ring
 // A CTA-wide 2-stage ring of input tiles: TILE_ROWS rows of ROW_BYTES bytes, filled by thread 0 with
-// LOADS = ceil(TILE_ROWS/256) tiled TMA loads (box = {ROW_BYTES, TILE_ROWS/LOADS}; rows past the end of
+// LOADS equal tiled TMA loads of <= 256 rows (box = {ROW_BYTES, TILE_ROWS/LOADS}; rows past the end of
 // the tensor are zero-filled by the hardware, which is what makes ragged tails free).
 //   prologue : ring.init(smem, tmap); ring.issue(0, first_tile)
 //   loop it  : ring.issue((it+1)&1, next_tile)  [if any];  ring.wait(it);  <copy rows to registers>;
 //              __syncthreads();   // everyone drained stage it&1 -> it may be refilled at it+1
 template <int TILE_ROWS, int ROW_BYTES>
 struct TileRing {
-    static constexpr int LOADS = (TILE_ROWS + 255) / 256;
+    // smallest number of equal TMA boxes of at most 256 rows
+    static constexpr int pick_loads() { int l = (TILE_ROWS + 255) / 256; while (TILE_ROWS % l) ++l; return l; }
+    static constexpr int LOADS = pick_loads();
     static constexpr int BOX_ROWS = TILE_ROWS / LOADS;
-    static_assert(TILE_ROWS % LOADS == 0, "tile must split into equal TMA boxes");
+    static_assert(TILE_ROWS % LOADS == 0 && BOX_ROWS <= 256, "tile must split into equal TMA boxes");
     static constexpr uint32_t TILE_BYTES = (uint32_t)TILE_ROWS * ROW_BYTES;
     static constexpr uint32_t STAGE_STRIDE = (TILE_BYTES + 1023u) & ~1023u;
     static constexpr uint32_t SMEM_BYTES = XMR_STAGES * STAGE_STRIDE + 64;

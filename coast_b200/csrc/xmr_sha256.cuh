@@ -42,7 +42,7 @@ template <bool INJECT>
 __device__ __forceinline__ void sha_compress(uint32_t (&st)[8], uint32_t (&m)[16], uint32_t fs, uint32_t fmask) {
     if (INJECT && fs < 16u) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) if (fs == (uint32_t)i) m[i] ^= fmask;
+        for (int i = 0; i < 16; ++i) m[i] ^= fs == (uint32_t)i ? fmask : 0u;
     }
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
     const uint32_t ft = INJECT ? ((fs - 16u) >> 3) : 0u;      // round of the fault (valid when 16 <= fs < 528)
@@ -71,7 +71,7 @@ __device__ __forceinline__ void sha_compress(uint32_t (&st)[8], uint32_t (&m)[16
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;   // :90-97
     if (INJECT && fs >= 528u && fs < 536u) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) if (fs - 528u == (uint32_t)i) st[i] ^= fmask;
+        for (int i = 0; i < 8; ++i) st[i] ^= fs - 528u == (uint32_t)i ? fmask : 0u;
     }
 }
 
