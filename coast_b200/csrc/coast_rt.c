@@ -365,6 +365,7 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
     a.in = d->d_in; a.out = d->d_out; a.aux = d->d_aux;
     a.n_units = d->n_units; a.unit_base = d->unit_base;
     a.counters = (unsigned long long*)G.counters;
+    a.status = (unsigned char*)d->d_status;
     a.unit_bytes = d->unit_bytes; a.flags = d->flags; a.mode = d->mode;
     a.M = d->M; a.N = d->N; a.K = d->K;
     memcpy(a.key, d->key, 16);

@@ -101,7 +101,7 @@ __device__ __forceinline__ void aes128_enc_body(const xmr_args& a, const CUtenso
     const uint32_t n_tiles = a.n_tiles;
     uint32_t tile = blockIdx.x;
     if (tile < n_tiles) ring.issue(0, tile);
-    Tally tally;
+    Tally tally(a);
     uint32_t it = 0;
     for (; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t next = tile + gridDim.x;
@@ -194,7 +194,7 @@ __device__ __forceinline__ void aes128_gen_body(const xmr_args& a) {
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     const unsigned long long n_wtiles = (a.n_units + UPW - 1) / UPW;
     const bool dir = a.mode & 1u, per_unit = a.mode & 2u;
-    Tally tally;
+    Tally tally(a);
     for (unsigned long long wt = gwarp; wt < n_wtiles; wt += nwarps) {
         const unsigned long long local = wt * UPW + Lanes<NC>::unit(lane);
         const bool valid = local < a.n_units;

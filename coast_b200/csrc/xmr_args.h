@@ -13,6 +13,7 @@ typedef struct xmr_args {
     unsigned long long unit_base;
     unsigned long long* counters;     /* XMR_CTR_* slots, device memory            */
     const unsigned int* plan_table;   /* COAST_PLAN_TABLE: one u32 per local unit  */
+    unsigned char* status;            /* optional: per-unit count of disagreeing votes (saturating u8) */
     unsigned int unit_bytes;
     unsigned int flags;               /* COAST_F_*                                  */
     unsigned int mode;                /* COAST_AES_*                                */

@@ -124,6 +124,10 @@ __device__ __forceinline__ Voted vote_f32(float x, bool majority) {
 struct Tally {
     uint32_t errors = 0, dwc = 0, syncs = 0, injected = 0;
     unsigned long long first = ~0ull;
+    unsigned char* status = nullptr;          // optional per-unit disagreement count (campaign tooling)
+    unsigned long long base = 0;
+    __device__ __forceinline__ Tally() {}
+    __device__ __forceinline__ explicit Tally(const xmr_args& a) : status(a.status), base(a.unit_base) {}
     // one unit's SoR exit: `bad` disagreeing elements out of `nvotes`
     template <int NC> __device__ __forceinline__ void unit_exit(uint32_t bad, uint32_t nvotes, uint32_t flags, unsigned long long gunit) {
         if (NC == 3) {
@@ -135,6 +139,7 @@ struct Tally {
             dwc += bad ? 1u : 0u;
         }
         if (NC > 1 && bad && gunit < first) first = gunit;
+        if (status) status[gunit - base] = (unsigned char)(NC > 1 ? (bad > 255u ? 255u : bad) : 0u);
     }
     // all 32 lanes must call
     __device__ __forceinline__ void flush(unsigned long long* ctr) {

@@ -156,7 +156,7 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
         const uint32_t flags = a.flags;
         const bool majority = flags & COAST_F_MAJORITY_D;
         float* C = static_cast<float*>(a.out);
-        Tally tally;
+        Tally tally(a);
         uint32_t tcount = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
             const uint32_t m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;

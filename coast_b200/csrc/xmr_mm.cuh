@@ -26,7 +26,7 @@ __device__ __forceinline__ void mm_u32_body(const xmr_args& a) {
     const uint32_t* __restrict__ B = static_cast<const uint32_t*>(a.aux);
     uint32_t* C = static_cast<uint32_t*>(a.out);
     const uint32_t K = a.K, N = a.N;
-    Tally tally;
+    Tally tally(a);
     for (unsigned long long wt = gwarp; wt < n_wtiles; wt += nwarps) {
         const unsigned long long local = wt * UPW + Lanes<NC>::unit(lane);
         const bool valid = local < a.n_units;

@@ -119,7 +119,7 @@ __device__ __forceinline__ void sha256_b64_body(const xmr_args& a, const CUtenso
     const uint32_t n_tiles = a.n_tiles;
     uint32_t tile = blockIdx.x;
     if (tile < n_tiles) ring.issue(0, tile);
-    Tally tally;
+    Tally tally(a);
     uint32_t it = 0;
     for (; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t next = tile + gridDim.x;
@@ -185,7 +185,7 @@ __device__ __forceinline__ void sha256_gen_body(const xmr_args& a) {
     const uint32_t len = a.unit_bytes;
     const uint32_t nblk = (len + 8u) / 64u + 1u;
     const unsigned long long n_wtiles = (a.n_units + UPW - 1) / UPW;
-    Tally tally;
+    Tally tally(a);
     for (unsigned long long wt = gwarp; wt < n_wtiles; wt += nwarps) {
         const unsigned long long local = wt * UPW + Lanes<NC>::unit(lane);
         const bool valid = local < a.n_units;
@@ -246,7 +246,7 @@ __device__ __forceinline__ void sha256_b64_seg_body(const xmr_args& a, const CUt
     const bool majority = a.flags & COAST_F_MAJORITY_D;
     uint32_t tile = blockIdx.x;
     if (tile < n_tiles) ring.issue(0, tile);
-    Tally tally;
+    Tally tally(a);
     uint32_t it = 0;
     for (; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t next = tile + gridDim.x;

@@ -39,7 +39,7 @@ class LaunchDesc(C.Structure):
                 ("n_units", C.c_uint64), ("unit_base", C.c_uint64),
                 ("unit_bytes", C.c_uint32), ("M", C.c_uint32), ("N", C.c_uint32), ("K", C.c_uint32),
                 ("d_in", C.c_void_p), ("d_out", C.c_void_p), ("d_aux", C.c_void_p),
-                ("key", C.c_uint8 * 16), ("plan", C.POINTER(_Plan))]
+                ("key", C.c_uint8 * 16), ("plan", C.POINTER(_Plan)), ("d_status", C.c_void_p)]
 
 
 class _Stats(C.Structure):
@@ -169,7 +169,7 @@ class Runtime:
         return s.cuda_stream
 
     def make_desc(self, kernel, num_clones, d_in, d_out, n_units, *, flags=0, mode=0, unit_bytes=0, M=0, N=0, K=0,
-                  d_aux=None, key: bytes | None = None, plan: FaultPlan | None = None, unit_base=0):
+                  d_aux=None, key: bytes | None = None, plan: FaultPlan | None = None, unit_base=0, d_status=None):
         d = LaunchDesc()
         d.kernel, d.num_clones, d.flags, d.mode = kernel, num_clones, flags, mode
         d.n_units, d.unit_base, d.unit_bytes = n_units, unit_base, unit_bytes
@@ -180,6 +180,8 @@ class Runtime:
             d.d_aux = d_aux.data_ptr() if hasattr(d_aux, "data_ptr") else d_aux
         if key is not None:
             d.key = (C.c_uint8 * 16)(*key)
+        if d_status is not None:
+            d.d_status = d_status.data_ptr() if hasattr(d_status, "data_ptr") else d_status
         keep = None
         if plan is not None and plan.mode != PLAN_NONE:
             keep = plan.to_c()
@@ -224,12 +226,12 @@ class Runtime:
 
     # -- convenience: device tensors in, device tensor + Stats out ----------------------------
     def run(self, kernel, num_clones, inp, n_units, *, flags=0, mode=0, unit_bytes=0, M=0, N=0, K=0, aux=None,
-            key: bytes | None = None, plan: FaultPlan | None = None, unit_base=0, out=None, stream=None):
+            key: bytes | None = None, plan: FaultPlan | None = None, unit_base=0, out=None, stream=None, status=None):
         torch = self.torch
         if out is None:
             out = torch.empty(n_units * OUT_BYTES[kernel], dtype=torch.uint8, device=f"cuda:{self.device}")
         d = self.make_desc(kernel, num_clones, inp, out, n_units, flags=flags, mode=mode, unit_bytes=unit_bytes,
-                           M=M, N=N, K=K, d_aux=aux, key=key, plan=plan, unit_base=unit_base)
+                           M=M, N=N, K=K, d_aux=aux, key=key, plan=plan, unit_base=unit_base, d_status=status)
         self.launch(d, stream)
         return out, self.sync(stream)
 

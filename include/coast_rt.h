@@ -153,6 +153,9 @@ typedef struct coast_launch_desc {
     const void* d_aux;
     uint8_t     key[16];   /* AES single-key mode                                 */
     const coast_fault_plan* plan; /* NULL = no injection                          */
+    void*       d_status;  /* optional, n_units x uint8_t: per unit, the number of SoR-exit votes at which the
+                              replicas disagreed (saturating at 255; 0 = all agreed).  This is the per-run "F:"
+                              field of the board report line (decoder.py:66) for campaign tooling.              */
 } coast_launch_desc;
 
 /* Counters of everything launched since the last coast_sync(). */
