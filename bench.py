@@ -166,9 +166,31 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def workload_table(cb):
+    """BASELINE.json configs as bench workloads.  `sha256` (configs[1]) is the default and the headline line; the others
+    are extra lines for the remaining single-GPU configurations (python bench.py --workload aes|gemm|crc16)."""
+    F = cb.F_COUNT_ERRORS | cb.F_COUNT_SYNCS
+    return {
+        "sha256": dict(kernel=cb.K_SHA256, nc=3, flags=F, n=1 << 20, unit_bytes=64, in_b=64, out_b=32, alg_b=96, plan=None,
+                       name="sha256 TMR, 2^20 x 64-byte messages per GPU (BASELINE configs[1])", kname="xmr_sha256_b64_seg_nc3_inj0",
+                       protection="-TMR -countErrors -countSyncs", bound="hbm", sets=4),
+        "aes": dict(kernel=cb.K_AES128, nc=2, flags=0, n=1 << 24, unit_bytes=0, in_b=16, out_b=16, alg_b=32,
+                    plan=dict(seed=33, p=2.0 ** -10), key=bytes(16),
+                    name="aes-128 ECB encrypt DWC, 2^24 x 16-byte blocks, Bernoulli(2^-10) single-bit flips (BASELINE configs[2])",
+                    kname="xmr_aes128_enc_nc2_inj1", protection="-DWC + on-device injector", bound="hbm", sets=2),
+        "crc16": dict(kernel=cb.K_CRC16, nc=3, flags=F, n=1 << 20, unit_bytes=64, in_b=64, out_b=2, alg_b=66, plan=None,
+                      name="crc16 TMR, 2^20 x 64-byte messages (SURVEY.md 8d config 1 timing shape)", kname="xmr_crc16_b64_nc3_inj0",
+                      protection="-TMR -countErrors -countSyncs", bound="hbm", sets=4),
+        "gemm": dict(kernel=cb.K_GEMM_TF32, nc=3, flags=F, side=4096, plan=None,
+                     name="matmul TMR 4096x4096x4096 fp32 on tcgen05 kind::tf32, three TMEM accumulator replicas + voter (BASELINE configs[3])",
+                     kname="xmr_gemm_tf32_nc3_inj0", protection="-TMR -countErrors -countSyncs", bound="tensor", sets=2),
+    }
+
+
 def run_ours(args):
     import torch
     import coast_b200 as cb
+    from coast_b200.shard import shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -180,23 +202,56 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     rt = cb.Runtime(local)
     dev = f"cuda:{local}"
-    flags = cb.F_COUNT_ERRORS | cb.F_COUNT_SYNCS
-    n = N_UNITS
-    unit_base = rank * n                                   # shard = contiguous global unit range
+    W = workload_table(cb)[args.workload]
+    is_gemm = W["kernel"] == cb.K_GEMM_TF32
+    plan = cb.FaultPlan(mode=cb.PLAN_BERNOULLI, **W["plan"]) if W.get("plan") else None
+    nsets = W["sets"]
 
-    ins = [torch.empty(n * UNIT_BYTES, dtype=torch.uint8, device=dev) for _ in range(NSETS)]
-    outs = [torch.empty(n * OUT_BYTES, dtype=torch.uint8, device=dev) for _ in range(NSETS)]
-    for i, t in enumerate(ins):
-        rt.fill_philox(t, seed=2, word_base=(unit_base * UNIT_BYTES // 4) + i * 0x10000000)
-    descs = [rt.make_desc(cb.K_SHA256, 3, ins[i], outs[i], n, flags=flags, unit_bytes=UNIT_BYTES, unit_base=unit_base)
-             for i in range(NSETS)]
+    if is_gemm:
+        # strong scaling: C row-blocks of side/world rows per GPU, A row-block local, B replicated
+        side = W["side"]
+        r0, r1 = shard_range(side // 128, rank, world)
+        rows = (r1 - r0) * 128
+        n = rows * side
+        unit_base = r0 * 128 * side
+        scaling = "strong"
+        out_b, in_b = 4, 0
+        alg_bytes = (rows * side + side * side + rows * side) * 4
+        flops_issued = 3 * 2.0 * rows * side * side
+        ins, outs, auxs = [], [], []
+        for i in range(nsets):
+            A = torch.empty(max(rows, 1) * side, dtype=torch.float32, device=dev)
+            B = torch.empty(side * side, dtype=torch.float32, device=dev)
+            rt.fill_philox(A, seed=4, word_base=unit_base + i * 0x20000000)
+            rt.fill_philox(B, seed=44, word_base=i * 0x20000000)
+            # Philox words -> uniform(-1,1) fp32
+            A = (A.view(torch.int32).to(torch.float64) / 2 ** 31).to(torch.float32).contiguous()
+            B = (B.view(torch.int32).to(torch.float64) / 2 ** 31).to(torch.float32).contiguous()
+            ins.append(A); auxs.append(B); outs.append(torch.empty(max(n, 1), dtype=torch.float32, device=dev))
+        descs = [rt.make_desc(W["kernel"], W["nc"], ins[i], outs[i], n, flags=W["flags"], M=rows, N=side, K=side, d_aux=auxs[i],
+                              unit_base=unit_base, plan=plan) for i in range(nsets)] if n else []
+        total_out_bytes = side * side * 4
+    else:
+        n = W["n"]                                           # weak scaling: the same shard size on every GPU
+        unit_base = rank * n
+        scaling = "weak"
+        in_b, out_b = W["in_b"], W["out_b"]
+        alg_bytes = n * W["alg_b"]
+        ins = [torch.empty(n * in_b, dtype=torch.uint8, device=dev) for _ in range(nsets)]
+        outs = [torch.empty(n * out_b, dtype=torch.uint8, device=dev) for _ in range(nsets)]
+        for i, t in enumerate(ins):
+            rt.fill_philox(t, seed=2, word_base=(unit_base * in_b // 4) + i * 0x10000000)
+        descs = [rt.make_desc(W["kernel"], W["nc"], ins[i], outs[i], n, flags=W["flags"], unit_bytes=W["unit_bytes"], key=W.get("key"),
+                              unit_base=unit_base, plan=plan) for i in range(nsets)]
+        total_out_bytes = world * n * out_b
     d_stats = torch.zeros(5, dtype=torch.int64, device=dev)
     launches = 0
 
     def step(i):
         nonlocal launches
-        rt.launch(descs[i % NSETS])                        # ONE kernel: 3 replicas + voter + counters
-        launches += 1
+        if descs:
+            rt.launch(descs[i % nsets])                    # ONE kernel: replicas + voter + counters (+ injector)
+            launches += 1
         if dist is not None:
             rt.stats_snapshot(d_stats)                     # D2D copy of the counters
             dist.all_reduce(d_stats[:4])                   # the only exchange step: 32 bytes over NVLink
@@ -222,14 +277,18 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     timed_launches = launches
     st = rt.sync()                                         # fold counters once (outside the timed region)
-    assert st.errors_corrected == 0 and st.syncs == 32 * n * (args.steps + args.warmup), st
+    if args.workload == "sha256":
+        assert st.errors_corrected == 0 and st.syncs == 32 * n * (args.steps + args.warmup), st
+    if args.workload == "aes":
+        assert st.dwc_detected == st.injected > 0, st      # detect-rate parity: every state flip is detected
 
-    # kernel-only duration for the roofline: the same launches, bracketed per launch by events on the launching stream
+    # kernel-only duration for the roofline: per-launch events on the launching stream
     kms = []
     for i in range(max(3, min(args.steps, 20))):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        rt.launch(descs[i % NSETS])
+        if descs:
+            rt.launch(descs[i % nsets])
         b.record()
         b.synchronize()
         kms.append(a.elapsed_time(b))
@@ -237,21 +296,32 @@ def run_ours(args):
     k_ms = statistics.median(kms)
 
     # end to end through the reference-facing host call: pinned HOST buffers, H2D + kernel + D2H every step
-    h_in = torch.empty(n * UNIT_BYTES, dtype=torch.uint8).pin_memory()
-    h_in.copy_(ins[0].cpu())
-    h_out = torch.empty(n * OUT_BYTES, dtype=torch.uint8).pin_memory()
-    for _ in range(min(3, args.warmup)):
-        rt.run_host(cb.K_SHA256, 3, h_in, h_out, n, unit_bytes=UNIT_BYTES, flags=flags, unit_base=unit_base)
-    fence()
     e2e_steps = max(3, min(args.steps, 20))
+    if is_gemm:
+        h_in = ins[0].cpu().pin_memory(); h_aux = auxs[0].cpu().pin_memory()
+        h_out = torch.empty(max(n, 1), dtype=torch.float32).pin_memory()
+        call = lambda: rt.run_host(W["kernel"], W["nc"], h_in, h_out, n, flags=W["flags"], M=rows, N=side, K=side, h_aux=h_aux,
+                                   unit_base=unit_base, plan=plan)
+        h2d, d2h = (rows * side + side * side) * 4, rows * side * 4 + 40
+    else:
+        h_in = torch.empty(n * in_b, dtype=torch.uint8).pin_memory()
+        h_in.copy_(ins[0].cpu())
+        h_out = torch.empty(n * out_b, dtype=torch.uint8).pin_memory()
+        call = lambda: rt.run_host(W["kernel"], W["nc"], h_in, h_out, n, unit_bytes=W["unit_bytes"], flags=W["flags"],
+                                   key=W.get("key"), unit_base=unit_base, plan=plan)
+        h2d, d2h = n * in_b, n * out_b + 40
+    for _ in range(min(3, args.warmup)):
+        call()
+    fence()
     sampler.start()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        rt.run_host(cb.K_SHA256, 3, h_in, h_out, n, unit_bytes=UNIT_BYTES, flags=flags, unit_base=unit_base)
+        call()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     sampler.stop()
-    assert torch.equal(h_out, outs[0].cpu())
+    assert torch.equal(h_out.view(torch.uint8), outs[0].cpu().view(torch.uint8))
+
     # context for the e2e number: what a bare pinned copy of the same buffers achieves on this box
     def copy_gbs(dst, src, reps=5):
         torch.cuda.synchronize()
@@ -259,46 +329,57 @@ def run_ours(args):
         for _ in range(reps):
             dst.copy_(src, non_blocking=True)
         torch.cuda.synchronize()
-        return src.numel() * reps / (time.perf_counter() - t) / 1e9
-    pcie_h2d, pcie_d2h = copy_gbs(ins[1], h_in), copy_gbs(h_out, outs[0])
+        return src.numel() * src.element_size() * reps / (time.perf_counter() - t) / 1e9
+    pcie_h2d, pcie_d2h = copy_gbs(ins[1 % nsets], h_in), copy_gbs(h_out, outs[0])
 
     t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)           # max over ranks
     ms, e2e_s = float(t[0]), float(t[1])
     if rank == 0:
-        peak, peak_src = peaks()
         ms_per_step = ms / args.steps
-        value = world * n * OUT_BYTES / (ms_per_step * 1e-3) / 1e6
-        achieved = n * ALG_BYTES_PER_UNIT / (k_ms * 1e-3) / 1e9
+        value = total_out_bytes / (ms_per_step * 1e-3) / 1e6
+        if W["bound"] == "hbm":
+            peak, peak_src = peaks()
+            achieved, unit = alg_bytes / (k_ms * 1e-3) / 1e9, "GB/s"
+            rl_extra = {"algorithmic_bytes_per_launch": alg_bytes,
+                        "note": "integer-issue / shared-memory bound, not HBM bound: see DESIGN.md section 5"}
+        else:
+            pj = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            peak = float(pj.get("bf16_tflops", 1590.0)) / 2.0
+            peak_src = "measured bf16 cuBLAS burst / 2 (TF32 runs at half the bf16 rate)" if pj else "fallback 1590/2"
+            achieved, unit = flops_issued / (k_ms * 1e-3) / 1e12, "TFLOP/s"
+            rl_extra = {"issued_flops_per_launch": flops_issued, "useful_flops_per_launch": flops_issued / 3,
+                        "note": "issued = 3 replicas x 2MNK; useful = one replica"}
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_sha256_tmr_traffic.json")
+        tp = os.path.join(ROOT, "profiles", f"r01_{args.workload}_traffic.json")
+        if args.workload == "sha256":
+            tp = os.path.join(ROOT, "profiles", "r01_sha256_tmr_traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
         line = {
-            "metric": METRIC, "value": round(value, 1), "unit": "MB/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "sha256 TMR, 2^20 x 64-byte messages per GPU (BASELINE configs[1])",
-                       "units_per_gpu": n, "unit_bytes": UNIT_BYTES, "protection": "-TMR -countErrors -countSyncs",
-                       "voter": "select (r0==r1?r0:r2), 32 u8 votes/unit",
-                       "layout": "-s: replicas on adjacent warps, SoR-exit exchange through shared memory (default; -i = adjacent lanes + warp shuffle)",
-                       "l2": f"{NSETS} rotating in/out buffer sets = {NSETS * n * ALG_BYTES_PER_UNIT >> 20} MiB > 126 MB L2",
+            "metric": METRIC if args.workload == "sha256" else f"protected-kernel throughput (MB/s voted output), {args.workload}",
+            "value": round(value, 1), "unit": "MB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f32(tf32 mma)" if is_gemm else ("u8" if args.workload == "aes" else "u32"), "data": "synthetic",
+            "config": {"workload": W["name"], "units_per_gpu": n, "protection": W["protection"],
+                       "voter": "select (r0==r1?r0:r2), one vote per stored element",
+                       "layout": "-s: replicas on adjacent warps (sha256 TMR default); adjacent lanes otherwise; GEMM: 3 TMEM accumulators",
+                       "l2": f"{nsets} rotating in/out buffer sets = {nsets * alg_bytes >> 20} MiB > 126 MB L2",
                        "parallelism": f"shard{world}" if world > 1 else "1gpu"},
-            "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "xmr_sha256_b64_seg_nc3_inj0", "kernel_ms": round(k_ms, 5),
-                         "algorithmic_bytes_per_launch": n * ALG_BYTES_PER_UNIT,
-                         "note": "integer-issue bound, not HBM bound: see DESIGN.md section 5 (ALU ceiling)"},
-            "e2e": {"value": round(world * n * OUT_BYTES / e2e_s / 1e6, 1), "unit": "MB/s",
-                    "h2d_bytes_per_step": n * UNIT_BYTES, "d2h_bytes_per_step": n * OUT_BYTES + 40,
+            "roofline": dict({"bound": W["bound"], "achieved": round(achieved, 2), "peak": peak, "unit": unit,
+                              "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
+                              "kernel": W["kname"], "kernel_ms": round(k_ms, 5)}, **rl_extra),
+            "e2e": {"value": round(total_out_bytes / e2e_s / 1e6, 1), "unit": "MB/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_s * 1e3, 4), "timer": "host clock around the blocking C-ABI call coast_run_host",
                     "pcie_pinned_copy_gbs": {"h2d": round(pcie_h2d, 1), "d2h": round(pcie_d2h, 1)}},
             "gpu_launches": timed_launches,
             "clocks": sampler.summary(),
+            "stats_last_sync": st.as_dict(),
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "sha256":
             line["cpu_baseline"] = cpu_baseline_block()
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -313,6 +394,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", choices=["sha256", "aes", "crc16", "gemm"], default="sha256",
+                    help="default sha256 = BASELINE configs[1], the headline line; the others are extra lines")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
