@@ -8,4 +8,5 @@
 #include "xmr_aes128.cuh"
 #include "xmr_crc16.cuh"
 #include "xmr_mm.cuh"
+#include "xmr_mm_tiled.cuh"
 #include "xmr_gemm_tf32.cuh"

@@ -378,7 +378,7 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
     a.n_sites = coast_fault_sites(d->kernel, d->unit_bytes, d->K);
 
     char name[64];
-    unsigned smem = 0; int tma = 0; int block = XMR_CTA_THREADS;
+    unsigned smem = 0; int tma = 0; int block = XMR_CTA_THREADS; int mm_tiled = 0;
     unsigned tile_rows = 0, row_bytes = 0; CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_NONE;
     const int aligned16 = (((uintptr_t)d->d_in) & 15u) == 0;
     switch (d->kernel) {
@@ -424,6 +424,12 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
         if (!d->d_aux || !d->M || !d->N || !d->K) return fail(COAST_ERR_BAD_ARG, "MM needs A (d_in), B (d_aux) and M,N,K");
         if (d->n_units != (uint64_t)d->M * d->N) return fail(COAST_ERR_BAD_ARG, "MM: n_units must be M*N");
         snprintf(name, sizeof name, "xmr_mm_u32_nc%u_inj%d", nc, inj);
+        /* register-tiled fast path: 64 x 128 x 16 tiles, NC x 128 threads (replicas on adjacent warps) */
+        if (d->M % 64u == 0 && d->N % 128u == 0 && d->K % 16u == 0 && aligned16 && !(((uintptr_t)d->d_aux) & 15u) &&
+            !(((uintptr_t)d->d_out) & 15u)) {
+            mm_tiled = 1; block = (int)nc * 128; smem = 64u * 1024u;
+            snprintf(name, sizeof name, "xmr_mm_u32_tiled_nc%u_inj%d", nc, inj);
+        }
         break;
     case COAST_K_GEMM_TF32:
         if (!d->d_aux || !d->M || !d->N || !d->K) return fail(COAST_ERR_BAD_ARG, "GEMM needs A (d_in), B (d_aux) and M,N,K");
@@ -450,6 +456,8 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
         rc = encode_rows_map(&map, d->d_in, row_bytes, d->n_units, tile_rows / loads, swz); if (rc) return rc;
         uint64_t cap = (uint64_t)G.sm_count * (unsigned)occ;
         grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
+    } else if (mm_tiled) {
+        grid = (d->M / 64u) * (d->N / 128u);
     } else {
         uint64_t warps = (d->n_units + upw - 1) / upw;
         uint64_t ctas = (warps + XMR_WARPS - 1) / XMR_WARPS;
@@ -550,9 +558,13 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int call_
     const uint64_t ib = in_bytes_per_unit(d);
     if (!ib || !ob) return fail(COAST_ERR_UNSUPPORTED, "coast_run_host: kernel %u", d->kernel);
     const int per_unit_key = d->kernel == COAST_K_AES128 && (d->mode & COAST_AES_KEY_PER_UNIT);
-    /* chunk: about 8 MiB of input per launch; each chunk is its own launch (own tensor map), the fault
-     * plan is keyed by the global unit index so chunking never changes results */
-    uint64_t chunk = (8ull << 20) / ib;
+    /* each chunk is its own launch (own tensor map); the fault plan is keyed by the global unit index so
+     * chunking never changes results */
+    /* ~1/16 of the input per chunk, between 1 and 8 MiB: short pipeline fill/drain, few driver calls */
+    uint64_t chunk_bytes = d->n_units * ib / 16ull;
+    if (chunk_bytes < (1ull << 20)) chunk_bytes = 1ull << 20;
+    if (chunk_bytes > (8ull << 20)) chunk_bytes = 8ull << 20;
+    uint64_t chunk = chunk_bytes / ib;
     if (chunk < 1024ull) chunk = 1024ull;
     uint64_t done = 0; int slot = 0;
     while (done < d->n_units) {

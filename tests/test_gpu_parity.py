@@ -400,3 +400,44 @@ def test_sha256_tmr_layouts_give_identical_results(rt, oracle, layout_flag, n):
     m = msgs(oracle, n, 64, 21)
     both(rt, oracle, oracle.K_SHA256, 3, m, n, unit_bytes=64, flags=3 | layout_flag)
     both(rt, oracle, oracle.K_SHA256, 3, m, n, unit_bytes=64, flags=3 | layout_flag, plan_kw=dict(seed=n, p=0.25))
+
+
+@pytest.mark.parametrize("nc", [1, 2, 3])
+@pytest.mark.parametrize("M,N,K", [(64, 128, 16), (128, 256, 64), (192, 384, 160)])
+def test_mm_tiled_kernel_exact_and_faults(rt, oracle, nc, M, N, K):
+    """sizes that take the register-tiled kernel (64 x 128 x 16 tiles): bit-exact with the oracle, with and without faults"""
+    A = oracle.fill_philox(M * K, 0, 4)
+    B = oracle.fill_philox(K * N, 0, 44)
+    both(rt, oracle, oracle.K_MM_U32, nc, A, M * N, M=M, N=N, K=K, aux=B, flags=3)
+    both(rt, oracle, oracle.K_MM_U32, nc, A, M * N, M=M, N=N, K=K, aux=B, flags=3, plan_kw=dict(seed=K, p=0.1))
+    tab = np.zeros(M * N, dtype=np.uint32)
+    for u, (r, s, b) in enumerate([(0, 0, 0), (1, K - 1, 31), (2, K // 2, 7), (0, 3, 30), (1, 0, 16)]):
+        tab[u * 97 % (M * N)] = oracle.fault_entry(r, s, b)
+    both(rt, oracle, oracle.K_MM_U32, nc, A, M * N, M=M, N=N, K=K, aux=B, flags=3, table=tab)
+
+
+def test_mm_full_size_properties(rt, oracle):
+    """4096^3 exact integer TMR (the reference's own arithmetic at BASELINE config-4 size): voted output == unprotected output
+    bit for bit under a fault plan; spot elements equal the oracle's dot products; XOR-fold check as mm_common_tmr.c:23-32."""
+    import torch
+    import coast_b200 as cb
+    n = 4096
+    A = torch.empty(n * n, dtype=torch.int32, device="cuda")
+    B = torch.empty(n * n, dtype=torch.int32, device="cuda")
+    rt.fill_philox(A, seed=4)
+    rt.fill_philox(B, seed=44)
+    o1 = torch.empty(n * n, dtype=torch.int32, device="cuda")
+    o3 = torch.empty(n * n, dtype=torch.int32, device="cuda")
+    rt.run(cb.K_MM_U32, 1, A, n * n, M=n, N=n, K=n, aux=B, out=o1)
+    _, st = rt.run(cb.K_MM_U32, 3, A, n * n, M=n, N=n, K=n, aux=B, flags=3, out=o3, plan=cb.FaultPlan(mode=cb.PLAN_BERNOULLI, seed=8, p=2 ** -12))
+    assert torch.equal(o1, o3) and st.errors_corrected == st.injected > 3000
+    hA = oracle.fill_philox(n * n, 0, 4)
+    hB = oracle.fill_philox(n * n, 0, 44)
+    C = o3.cpu().numpy().view(np.uint32).reshape(n, n)
+    for (i, j) in [(0, 0), (1, 4095), (2047, 1234), (4095, 4095), (63, 64), (64, 127)]:
+        ref = int(np.sum(hA[i * n:(i + 1) * n].astype(np.uint64) * hB[j::n].astype(np.uint64)) & np.uint64(0xFFFFFFFF)) & 0xFFFFFFFF
+        exact = 0
+        for k in range(n):
+            exact = (exact + int(hA[i * n + k]) * int(hB[k * n + j])) & 0xFFFFFFFF
+        assert int(C[i, j]) == exact
+    assert int(np.bitwise_xor.reduce(C.ravel())) == int(np.bitwise_xor.reduce(o1.cpu().numpy().view(np.uint32)))
