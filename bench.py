@@ -133,30 +133,67 @@ def cpu_baseline_block(budget_s: float = 12.0):
             "sample": f"{n} x 64-byte messages, Philox(seed=2), TMR + countErrors, {threads} pthreads, {t:.2f} s"}
 
 
+def cpu_xmr(workload: str, n_units: int, threads: int, repeats: int = 1):
+    """CPU arm of any workload: (seconds per pass, kind, out_bytes_per_unit).  sha256 runs the reference's own
+    sha256_hash() (oracle/_ref); the others run the oracle port (oracle/coast_oracle.c) with pthreads."""
+    import numpy as np
+    from oracle import pyoracle as po
+    if workload.startswith("sha256"):
+        t, kind = cpu_tmr_sha(n_units, threads, repeats)
+        return t, kind, OUT_BYTES
+    po.build()
+    if workload == "crc16":
+        inp = po.fill_philox(n_units * 16, 0, 2).view(np.uint8)
+        kw = dict(kernel=po.K_CRC16, nc=3, flags=3, unit_bytes=64)
+        ob = 2
+    elif workload == "aes":
+        inp = po.fill_philox(n_units * 4, 0, 2).view(np.uint8)
+        kw = dict(kernel=po.K_AES128, nc=2, flags=0, key=bytes(16), plan=po.make_plan(po.PLAN_BERNOULLI, seed=33, p=2.0 ** -10))
+        ob = 16
+    else:  # gemm: a row-block sample of the 4096^3 problem (n_units = rows * 4096)
+        side = 4096
+        rows = max(1, n_units // side)
+        A = (po.fill_philox(rows * side, 0, 4).astype(np.float64) / 2 ** 31 - 1.0).astype(np.float32)
+        B = (po.fill_philox(side * side, 0, 44).astype(np.float64) / 2 ** 31 - 1.0).astype(np.float32)
+        kw = dict(kernel=po.K_GEMM_TF32, nc=3, flags=3, M=rows, N=side, K=side, aux=B)
+        inp, n_units, ob = A, rows * side, 4
+    kernel, nc, flags = kw.pop("kernel"), kw.pop("nc"), kw.pop("flags")
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        po.run(kernel, nc, inp, n_units, flags=flags, threads=threads, **kw)
+    return (time.perf_counter() - t0) / repeats, "port", ob
+
+
 def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path on this box's host cores, same metric/config."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    t_cal, kind = cpu_tmr_sha(1 << 14, threads)
-    rate = (1 << 14) / max(t_cal, 1e-6)
+    threads = args.threads or (os.cpu_count() or 1)
+    wl = args.workload
+    cal_n = {"gemm": 4096 * 2, "aes": 1 << 16}.get(wl, 1 << 14)
+    t_cal, kind, ob = cpu_xmr(wl, cal_n, threads)
+    rate = cal_n / max(t_cal, 1e-6)
     total_budget = 90.0                                   # whole --steps/--warmup run stays within a few minutes
-    n = int(max(1 << 14, min(N_UNITS, rate * total_budget / max(1, args.steps + args.warmup))))
-    n = 1 << (n.bit_length() - 1)
+    full = {"sha256": N_UNITS, "sha256_2p30": N_UNITS, "crc16": 1 << 20, "aes": 1 << 24, "gemm": 4096 * 4096}[wl]
+    n = int(max(cal_n, min(full, rate * total_budget / max(1, args.steps + args.warmup))))
+    n = (n // 4096) * 4096 if wl == "gemm" else 1 << (n.bit_length() - 1)
     for _ in range(args.warmup):
-        cpu_tmr_sha(n, threads)
-    t, kind = cpu_tmr_sha(n, threads, repeats=args.steps)
-    val = n * OUT_BYTES / t / 1e6
+        cpu_xmr(wl, n, threads)
+    t, kind, ob = cpu_xmr(wl, n, threads, repeats=args.steps)
+    val = n * ob / t / 1e6
     line = {
-        "impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": "MB/s", "n_gpus": args.gpus,
+        "impl": "reference",
+        "metric": METRIC if wl.startswith("sha256") else f"protected-kernel throughput (MB/s voted output), {wl}",
+        "value": round(val, 3), "unit": "MB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t * 1e3, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "sha256 TMR, 64-byte messages (BASELINE configs[1])", "units_per_step": n,
-                   "unit_bytes": UNIT_BYTES, "protection": "-TMR -countErrors -countSyncs",
-                   "note": "reference C sources (tests/sha256_common/sha256_common_tmr.c) compiled in place + restated "
-                           "xMR wrapper; the real opt -TMR binary needs LLVM 7 (absent)"},
+        "scaling": "strong" if wl == "gemm" else "weak", "vs_baseline": None,
+        "dtype": "f32" if wl == "gemm" else ("u8" if wl == "aes" else "u32"), "data": "synthetic",
+        "config": {"workload": wl, "units_per_step": n, "protection": {"aes": "-DWC + injector", }.get(wl, "-TMR -countErrors -countSyncs"),
+                   "note": "reference C sources compiled in place (oracle/_ref) + restated xMR wrapper for sha256; oracle port for the "
+                           "other workloads; the real opt -TMR binary needs LLVM 7 (absent). A step is a bounded sample of the GPU arm's batch."},
         "cpu_baseline": {"value": round(val, 3), "unit": "MB/s", "cores": threads, "kind": kind,
-                         "sample": f"{n} messages per step, {threads} pthreads"},
+                         "sample": f"{n} units per step, {threads} pthreads"},
         "e2e": {"value": round(val, 3), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -174,6 +211,9 @@ def workload_table(cb):
         "sha256": dict(kernel=cb.K_SHA256, nc=3, flags=F, n=1 << 20, unit_bytes=64, in_b=64, out_b=32, alg_b=96, plan=None,
                        name="sha256 TMR, 2^20 x 64-byte messages per GPU (BASELINE configs[1])", kname="xmr_sha256_b64_seg_nc3_inj0",
                        protection="-TMR -countErrors -countSyncs", bound="hbm", sets=4),
+        "sha256_2p30": dict(kernel=cb.K_SHA256, nc=3, flags=F, n=1 << 30, unit_bytes=64, in_b=64, out_b=32, alg_b=96, plan=None, strong=True,
+                            name="batched sha256 TMR, 2^30 x 64-byte messages sharded over the GPUs (BASELINE configs[4])",
+                            kname="xmr_sha256_b64_seg_nc3_inj0", protection="-TMR -countErrors -countSyncs", bound="hbm", sets=1),
         "aes": dict(kernel=cb.K_AES128, nc=2, flags=0, n=1 << 24, unit_bytes=0, in_b=16, out_b=16, alg_b=32,
                     plan=dict(seed=33, p=2.0 ** -10), key=bytes(16),
                     name="aes-128 ECB encrypt DWC, 2^24 x 16-byte blocks, Bernoulli(2^-10) single-bit flips (BASELINE configs[2])",
@@ -232,9 +272,15 @@ def run_ours(args):
                               unit_base=unit_base, plan=plan) for i in range(nsets)] if n else []
         total_out_bytes = side * side * 4
     else:
-        n = W["n"]                                           # weak scaling: the same shard size on every GPU
-        unit_base = rank * n
-        scaling = "weak"
+        if W.get("strong"):                                  # config 5: a fixed 2^30-message batch, contiguous shards
+            lo, hi = shard_range(W["n"], rank, world)
+            n, unit_base, scaling = hi - lo, lo, "strong"
+            if n * 96 > 150 * (1 << 30):
+                raise SystemExit(f"{args.workload}: {n} messages per GPU do not fit 180 GB; use more GPUs")
+        else:
+            n = W["n"]                                       # weak scaling: the same shard size on every GPU
+            unit_base = rank * n
+            scaling = "weak"
         in_b, out_b = W["in_b"], W["out_b"]
         alg_bytes = n * W["alg_b"]
         ins = [torch.empty(n * in_b, dtype=torch.uint8, device=dev) for _ in range(nsets)]
@@ -243,7 +289,7 @@ def run_ours(args):
             rt.fill_philox(t, seed=2, word_base=(unit_base * in_b // 4) + i * 0x10000000)
         descs = [rt.make_desc(W["kernel"], W["nc"], ins[i], outs[i], n, flags=W["flags"], unit_bytes=W["unit_bytes"], key=W.get("key"),
                               unit_base=unit_base, plan=plan) for i in range(nsets)]
-        total_out_bytes = world * n * out_b
+        total_out_bytes = (W["n"] if W.get("strong") else world * n) * out_b
     d_stats = torch.zeros(5, dtype=torch.int64, device=dev)
     launches = 0
 
@@ -277,7 +323,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     timed_launches = launches
     st = rt.sync()                                         # fold counters once (outside the timed region)
-    if args.workload == "sha256":
+    if args.workload.startswith("sha256"):
         assert st.errors_corrected == 0 and st.syncs == 32 * n * (args.steps + args.warmup), st
     if args.workload == "aes":
         assert st.dwc_detected == st.injected > 0, st      # detect-rate parity: every state flip is detected
@@ -304,12 +350,13 @@ def run_ours(args):
                                    unit_base=unit_base, plan=plan)
         h2d, d2h = (rows * side + side * side) * 4, rows * side * 4 + 40
     else:
-        h_in = torch.empty(n * in_b, dtype=torch.uint8).pin_memory()
-        h_in.copy_(ins[0].cpu())
-        h_out = torch.empty(n * out_b, dtype=torch.uint8).pin_memory()
-        call = lambda: rt.run_host(W["kernel"], W["nc"], h_in, h_out, n, unit_bytes=W["unit_bytes"], flags=W["flags"],
+        ne = min(n, 1 << 24)                                 # e2e batch: at most 2^24 units of the shard through host memory
+        h_in = torch.empty(ne * in_b, dtype=torch.uint8).pin_memory()
+        h_in.copy_(ins[0][: ne * in_b].cpu())
+        h_out = torch.empty(ne * out_b, dtype=torch.uint8).pin_memory()
+        call = lambda: rt.run_host(W["kernel"], W["nc"], h_in, h_out, ne, unit_bytes=W["unit_bytes"], flags=W["flags"],
                                    key=W.get("key"), unit_base=unit_base, plan=plan)
-        h2d, d2h = n * in_b, n * out_b + 40
+        h2d, d2h = ne * in_b, ne * out_b + 40
     for _ in range(min(3, args.warmup)):
         call()
     fence()
@@ -320,7 +367,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     sampler.stop()
-    assert torch.equal(h_out.view(torch.uint8), outs[0].cpu().view(torch.uint8))
+    assert torch.equal(h_out.view(torch.uint8), outs[0].view(torch.uint8)[: h_out.numel() * h_out.element_size()].cpu())
+    e2e_units = (h_out.numel() * h_out.element_size()) // out_b      # units per e2e call on this rank
 
     # context for the e2e number: what a bare pinned copy of the same buffers achieves on this box
     def copy_gbs(dst, src, reps=5):
@@ -330,7 +378,8 @@ def run_ours(args):
             dst.copy_(src, non_blocking=True)
         torch.cuda.synchronize()
         return src.numel() * src.element_size() * reps / (time.perf_counter() - t) / 1e9
-    pcie_h2d, pcie_d2h = copy_gbs(ins[1 % nsets], h_in), copy_gbs(h_out, outs[0])
+    pcie_h2d = copy_gbs(ins[1 % nsets].view(torch.uint8)[: h_in.numel() * h_in.element_size()], h_in.view(torch.uint8))
+    pcie_d2h = copy_gbs(h_out.view(torch.uint8), outs[0].view(torch.uint8)[: h_out.numel() * h_out.element_size()])
 
     t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -353,13 +402,13 @@ def run_ours(args):
                         "note": "issued = 3 replicas x 2MNK; useful = one replica"}
         traffic = None
         tp = os.path.join(ROOT, "profiles", f"r01_{args.workload}_traffic.json")
-        if args.workload == "sha256":
+        if args.workload.startswith("sha256"):
             tp = os.path.join(ROOT, "profiles", "r01_sha256_tmr_traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
         line = {
-            "metric": METRIC if args.workload == "sha256" else f"protected-kernel throughput (MB/s voted output), {args.workload}",
+            "metric": METRIC if args.workload.startswith("sha256") else f"protected-kernel throughput (MB/s voted output), {args.workload}",
             "value": round(value, 1), "unit": "MB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f32(tf32 mma)" if is_gemm else ("u8" if args.workload == "aes" else "u32"), "data": "synthetic",
@@ -371,7 +420,7 @@ def run_ours(args):
             "roofline": dict({"bound": W["bound"], "achieved": round(achieved, 2), "peak": peak, "unit": unit,
                               "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
                               "kernel": W["kname"], "kernel_ms": round(k_ms, 5)}, **rl_extra),
-            "e2e": {"value": round(total_out_bytes / e2e_s / 1e6, 1), "unit": "MB/s",
+            "e2e": {"value": round(world * e2e_units * out_b / e2e_s / 1e6, 1), "unit": "MB/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_s * 1e3, 4), "timer": "host clock around the blocking C-ABI call coast_run_host",
                     "pcie_pinned_copy_gbs": {"h2d": round(pcie_h2d, 1), "d2h": round(pcie_d2h, 1)}},
@@ -394,7 +443,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", choices=["sha256", "aes", "crc16", "gemm"], default="sha256",
+    ap.add_argument("--threads", type=int, default=0, help="--impl reference: host threads (default: all; config 1 is 1 thread)")
+    ap.add_argument("--workload", choices=["sha256", "sha256_2p30", "aes", "crc16", "gemm"], default="sha256",
                     help="default sha256 = BASELINE configs[1], the headline line; the others are extra lines")
     args = ap.parse_args()
     if args.warmup < 3:
