@@ -560,15 +560,23 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int call_
     const int per_unit_key = d->kernel == COAST_K_AES128 && (d->mode & COAST_AES_KEY_PER_UNIT);
     /* each chunk is its own launch (own tensor map); the fault plan is keyed by the global unit index so
      * chunking never changes results */
-    /* ~1/16 of the input per chunk, between 1 and 8 MiB: short pipeline fill/drain, few driver calls */
-    uint64_t chunk_bytes = d->n_units * ib / 16ull;
-    if (chunk_bytes < (1ull << 20)) chunk_bytes = 1ull << 20;
-    if (chunk_bytes > (8ull << 20)) chunk_bytes = 8ull << 20;
-    uint64_t chunk = chunk_bytes / ib;
-    if (chunk < 1024ull) chunk = 1024ull;
+    /* Chunk schedule measured on the B200 box (tools/e2e_chunk_sweep.py): 8-16 MiB chunks stream best (~12 us of driver
+     * work per chunk), but a fixed size leaves the copy engines idle while the first chunk goes up and the last comes
+     * down.  So chunks ramp 1,2,4,8,16,16,... MiB and shrink again towards the end (each at most half of what remains). */
+    uint64_t max_chunk_bytes = 16ull << 20;
+    { const char* e = getenv("COAST_HOST_CHUNK_BYTES"); if (e && atoll(e) > 0) max_chunk_bytes = (uint64_t)atoll(e); }   /* tuning knob */
+    const uint64_t min_chunk = ((1ull << 20) / ib) > 1024ull ? ((1ull << 20) / ib) : 1024ull;
+    const uint64_t max_chunk = (max_chunk_bytes / ib) > min_chunk ? (max_chunk_bytes / ib) : min_chunk;
+    const uint64_t chunk = max_chunk;                          /* slot buffers are sized for the largest chunk */
+    uint64_t ramp = min_chunk;
     uint64_t done = 0; int slot = 0;
     while (done < d->n_units) {
-        uint64_t n = d->n_units - done < chunk ? d->n_units - done : chunk;
+        const uint64_t left = d->n_units - done;
+        uint64_t n = ramp < max_chunk ? ramp : max_chunk;          /* ramp up */
+        if (n > left / 2 && left > 2 * min_chunk) n = left / 2;    /* ramp down */
+        if (n < min_chunk) n = min_chunk;
+        if (n > left) n = left;
+        ramp *= 2;
         rc = slot_reserve(&G.h_in[slot], &G.h_in_cap[slot], (size_t)(chunk * ib)); if (rc) return rc;
         rc = slot_reserve(&G.h_out[slot], &G.h_out_cap[slot], (size_t)(chunk * ob)); if (rc) return rc;
         DRV(p_cuMemcpyHtoDAsync_v2(G.h_in[slot], (const uint8_t*)d->d_in + done * ib, (size_t)(n * ib), G.hs[slot]));
