@@ -10,3 +10,4 @@
 #include "xmr_mm.cuh"
 #include "xmr_mm_tiled.cuh"
 #include "xmr_gemm_tf32.cuh"
+#include "xmr_mm_tc.cuh"

@@ -90,6 +90,8 @@ static struct {
     uint32_t def_nc, def_flags; int def_set;
     /* coast_run_host scratch: 3 slots */
     CUstream hs[3]; CUdeviceptr h_in[3], h_out[3], h_aux[3]; size_t h_in_cap[3], h_out_cap[3], h_aux_cap[3];
+    /* limb planes of the tensor-core exact matmul (xmr_mm_tc.cuh) */
+    CUdeviceptr mm_planes; size_t mm_planes_cap;
 } G;
 
 static int fail(int code, const char* fmt, ...) {
@@ -209,6 +211,8 @@ int coast_shutdown(void) {
         if (G.hs[i]) p_cuStreamDestroy_v2(G.hs[i]);
         G.h_in[i] = G.h_out[i] = G.h_aux[i] = 0; G.h_in_cap[i] = G.h_out_cap[i] = G.h_aux_cap[i] = 0; G.hs[i] = NULL;
     }
+    if (G.mm_planes) p_cuMemFree_v2(G.mm_planes);
+    G.mm_planes = 0; G.mm_planes_cap = 0;
     p_cuMemFree_v2(G.counters);
     p_cuMemFreeHost(G.h_counters);
     p_cuModuleUnload(G.mod);
@@ -350,6 +354,59 @@ static int launch_gemm_tf32(const coast_launch_desc* d, xmr_args* a, int inj, CU
     return COAST_OK;
 }
 
+/* Exact integer matmul on tcgen05 kind::i8 (xmr_mm_tc.cuh): split A and B into u8 limb planes (library scratch),
+ * then ten u8 GEMMs per replica into four s32 TMEM accumulators, recombined modulo 2^32 in the epilogue. */
+static int launch_mm_tc(const coast_launch_desc* d, xmr_args* a, int inj, CUstream stream) {
+    const uint32_t nc = d->num_clones, bn = nc == 3 ? 32u : 64u;
+    const size_t a_bytes = (size_t)d->M * d->K * 4u, b_bytes = (size_t)d->K * d->N * 4u;   /* 4 planes of 1 byte per element */
+    if (G.mm_planes_cap < a_bytes + b_bytes) {
+        if (G.mm_planes) { DRV(p_cuStreamSynchronize(stream)); DRV(p_cuMemFree_v2(G.mm_planes)); G.mm_planes = 0; G.mm_planes_cap = 0; }
+        DRV(p_cuMemAlloc_v2(&G.mm_planes, a_bytes + b_bytes));
+        G.mm_planes_cap = a_bytes + b_bytes;
+    }
+    CUdeviceptr pa = G.mm_planes, pb = G.mm_planes + a_bytes;
+    {
+        CUfunction f; int rc = get_fn("xmr_mm_split_a", 0, &f, NULL); if (rc) return rc;
+        unsigned long long rows = d->M, K = d->K; const void* A = d->d_in;
+        void* params[] = { &A, &pa, &rows, &K };
+        DRV(p_cuLaunchKernel(f, (unsigned)G.sm_count * 8u, 1, 1, 256, 1, 1, 0, stream, params, NULL));
+        rc = get_fn("xmr_mm_split_bt", 0, &f, NULL); if (rc) return rc;
+        unsigned int k32 = d->K, n32 = d->N; const void* B = d->d_aux;
+        void* params2[] = { &B, &pb, &k32, &n32 };
+        DRV(p_cuLaunchKernel(f, (unsigned)G.sm_count * 8u, 1, 1, 256, 1, 1, 0, stream, params2, NULL));
+    }
+    const unsigned smem = 2u * (65536u + 4u * bn * 128u) + 1024u + 256u;
+    char name[64];
+    snprintf(name, sizeof name, "xmr_mm_u32_tc_nc%u_inj%d", nc, inj);
+    CUfunction fn; int occ = 1;
+    int rc = get_fn(name, smem, &fn, &occ); if (rc) return rc;
+    CUtensorMap ma, mb;
+    {
+        cuuint64_t gdim[3] = { d->K, d->M, 4 };
+        cuuint64_t gstr[2] = { (cuuint64_t)d->K, (cuuint64_t)d->M * d->K };
+        cuuint32_t box[3] = { 128, 128, 4 };
+        cuuint32_t estr[3] = { 1, 1, 1 };
+        DRV(p_cuTensorMapEncodeTiled(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)pa, gdim, gstr, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+    }
+    {
+        cuuint64_t gdim[3] = { d->K, d->N, 4 };
+        cuuint64_t gstr[2] = { (cuuint64_t)d->K, (cuuint64_t)d->N * d->K };
+        cuuint32_t box[3] = { 128, bn, 4 };
+        cuuint32_t estr[3] = { 1, 1, 1 };
+        DRV(p_cuTensorMapEncodeTiled(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)pb, gdim, gstr, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+    }
+    unsigned tiles = (d->M / 128u) * (d->N / bn);
+    unsigned grid = tiles < (unsigned)G.sm_count ? tiles : (unsigned)G.sm_count;
+    void* params[3] = { a, &ma, &mb };
+    if (d->flags & COAST_F_VERBOSE) fprintf(stderr, "coast_rt: %s grid=%u smem=%u tiles=%u\n", name, grid, smem, tiles);
+    DRV(p_cuLaunchKernel(fn, grid, 1, 1, 256, 1, 1, smem, stream, params, NULL));
+    return COAST_OK;
+}
+
 int coast_launch(const coast_launch_desc* d, void* stream) {
     int rc = ensure_ctx(); if (rc) return rc;
     if (!d) return fail(COAST_ERR_BAD_ARG, "null descriptor");
@@ -424,6 +481,14 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
         if (!d->d_aux || !d->M || !d->N || !d->K) return fail(COAST_ERR_BAD_ARG, "MM needs A (d_in), B (d_aux) and M,N,K");
         if (d->n_units != (uint64_t)d->M * d->N) return fail(COAST_ERR_BAD_ARG, "MM: n_units must be M*N");
         snprintf(name, sizeof name, "xmr_mm_u32_nc%u_inj%d", nc, inj);
+        {   /* tensor-core path (exact, u8 limbs on kind::i8) for tile-aligned problems; COAST_MM_PATH=tiled|naive overrides */
+            const char* path = getenv("COAST_MM_PATH");
+            const int want_tc = !path || !strcmp(path, "tc");
+            if (want_tc && d->M % 128u == 0 && d->N % 64u == 0 && d->K % 128u == 0 && aligned16 &&
+                !(((uintptr_t)d->d_aux) & 15u) && !(((uintptr_t)d->d_out) & 15u))
+                return launch_mm_tc(d, &a, inj, (CUstream)stream);
+            if (path && !strcmp(path, "naive")) break;
+        }
         /* register-tiled fast path: 64 x 128 x 16 tiles, NC x 128 threads (replicas on adjacent warps) */
         if (d->M % 64u == 0 && d->N % 128u == 0 && d->K % 16u == 0 && aligned16 && !(((uintptr_t)d->d_aux) & 15u) &&
             !(((uintptr_t)d->d_out) & 15u)) {

@@ -441,3 +441,25 @@ def test_mm_full_size_properties(rt, oracle):
             exact = (exact + int(hA[i * n + k]) * int(hB[k * n + j])) & 0xFFFFFFFF
         assert int(C[i, j]) == exact
     assert int(np.bitwise_xor.reduce(C.ravel())) == int(np.bitwise_xor.reduce(o1.cpu().numpy().view(np.uint32)))
+
+
+@pytest.mark.parametrize("nc", [1, 2, 3])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 128), (256, 192, 256), (384, 256, 640)])
+def test_mm_tensor_core_limb_kernel_is_bit_exact(rt, oracle, nc, M, N, K, monkeypatch):
+    """tile-aligned sizes take the tcgen05 kind::i8 u8-limb kernel (xmr_mm_tc.cuh): exact modulo 2^32 like the reference loops,
+    with full-range u32 operands, with and without faults; the CUDA-core tiled kernel gives the same bits."""
+    A = oracle.fill_philox(M * K, 0, 4)
+    B = oracle.fill_philox(K * N, 0, 44)
+    A[:7] = 0xFFFFFFFF
+    B[:5] = 0xFFFFFFFF                                  # worst-case limbs
+    monkeypatch.delenv("COAST_MM_PATH", raising=False)
+    g_tc, _ = both(rt, oracle, oracle.K_MM_U32, nc, A, M * N, M=M, N=N, K=K, aux=B, flags=3)
+    both(rt, oracle, oracle.K_MM_U32, nc, A, M * N, M=M, N=N, K=K, aux=B, flags=3, plan_kw=dict(seed=K + nc, p=0.05))
+    tab = np.zeros(M * N, dtype=np.uint32)
+    for u, (r, s, b) in enumerate([(0, 0, 0), (1, K - 1, 31), (2, K // 2, 7), (0, 3, 30), (1, 0, 16)]):
+        tab[u * 89 % (M * N)] = oracle.fault_entry(r, s, b)
+    both(rt, oracle, oracle.K_MM_U32, nc, A, M * N, M=M, N=N, K=K, aux=B, flags=3, table=tab)
+    monkeypatch.setenv("COAST_MM_PATH", "tiled")
+    if N % 128 == 0:
+        g_tiled, _ = both(rt, oracle, oracle.K_MM_U32, nc, A, M * N, M=M, N=N, K=K, aux=B, flags=3)
+        assert g_tiled.tobytes() == g_tc.tobytes()

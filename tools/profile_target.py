@@ -68,6 +68,8 @@ def main():
     st = rt.sync()
     if a.time:
         best = min(ms)
+        if a.kernel in ("mm", "gemm"):
+            n = a.side * a.side
         print(f"{a.kernel} nc={a.nc} n={n} inject={a.inject}: best {best:.4f} ms, median {sorted(ms)[len(ms)//2]:.4f} ms, "
               f"{alg / best / 1e6:.1f} GB/s algorithmic; stats={st.as_dict()}")
         if a.kernel == "gemm":
