@@ -105,3 +105,33 @@ def test_product_never_touches_the_oracle():
                     if pat.search(open(os.path.join(dp, f), errors="ignore").read()):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def _build_c_demo(built_lib, out_dir):
+    import subprocess
+    exe = os.path.join(out_dir, "abi_demo")
+    cmd = ["gcc", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_demo.c"),
+           "-L", os.path.join(ROOT, "coast_b200"), "-lcoast_rt", f"-Wl,-rpath,{os.path.join(ROOT, 'coast_b200')}", "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def test_plain_c_caller_compiles_and_links(built_lib, tmp_path):
+    """include/coast_rt.h is usable from plain C (no CUDA headers) and a user FAULT_DETECTED_DWC overrides the weak default"""
+    import subprocess
+    exe = _build_c_demo(built_lib, str(tmp_path))
+    syms = subprocess.run(["nm", "-D", "--defined-only", exe], capture_output=True, text=True).stdout
+    assert "FAULT_DETECTED_DWC" in syms
+    if not _has_gpu():
+        res = subprocess.run([exe], capture_output=True, text=True)
+        assert res.returncode == 2 and "no CPU fallback" in res.stderr      # fails loudly without a driver
+
+
+@pytest.mark.gpu
+def test_plain_c_caller_runs_on_the_gpu(built_lib, tmp_path):
+    import subprocess
+    exe = _build_c_demo(built_lib, str(tmp_path))
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "result: 5ba3" in res.stdout and "C:0 E:0 F:" in res.stdout and "handler_calls=1" in res.stdout and "abi_demo ok" in res.stdout
