@@ -133,7 +133,10 @@ typedef struct coast_fault_plan {
  *                 (0 encrypt, 1 decrypt, as TI_aes_128.c:107's `dir`; the key passed is
  *                 always the ORIGINAL cipher key, :112-129).
  *   MM_U32   in : A, M x K uint32 row-major; aux: B, K x N uint32 row-major
- *            out: C, M x N uint32; a unit is one C element, n_units must be M*N
+ *            out: C, M x N uint32; a unit is one C element, n_units must be M*N.  Exact modulo 2^32 on every
+ *            path: tcgen05 kind::i8 on u8 limbs when M%128 == N%64 == K%128 == 0 (uses library-owned scratch for
+ *            the limb planes: keep such launches on ONE stream), register-tiled CUDA cores when M%64 == N%128 ==
+ *            K%16 == 0, a plain kernel otherwise (e.g. the 9 x 9 tests).  COAST_MM_PATH=tc|tiled|naive overrides.
  *   GEMM_TF32 same with float.  unit_base/rows: see row_base.
  */
 #define COAST_AES_DECRYPT       0x1u
