@@ -356,8 +356,8 @@ static int launch_gemm_tf32(const coast_launch_desc* d, xmr_args* a, int inj, CU
 
 /* Exact integer matmul on tcgen05 kind::i8 (xmr_mm_tc.cuh): split A and B into u8 limb planes (library scratch),
  * then ten u8 GEMMs per replica into four s32 TMEM accumulators, recombined modulo 2^32 in the epilogue. */
-static int launch_mm_tc(const coast_launch_desc* d, xmr_args* a, int inj, CUstream stream) {
-    const uint32_t nc = d->num_clones, bn = nc == 3 ? 32u : 64u;
+static int launch_mm_tc(const coast_launch_desc* d, xmr_args* a, int inj, CUstream stream, int atmem) {
+    const uint32_t nc = d->num_clones, bn = atmem ? (nc == 1 ? 64u : 32u) : (nc == 3 ? 32u : 64u);
     const size_t a_bytes = (size_t)d->M * d->K * 4u, b_bytes = (size_t)d->K * d->N * 4u;   /* 4 planes of 1 byte per element */
     if (G.mm_planes_cap < a_bytes + b_bytes) {
         if (G.mm_planes) { DRV(p_cuStreamSynchronize(stream)); DRV(p_cuMemFree_v2(G.mm_planes)); G.mm_planes = 0; G.mm_planes_cap = 0; }
@@ -377,7 +377,7 @@ static int launch_mm_tc(const coast_launch_desc* d, xmr_args* a, int inj, CUstre
     }
     const unsigned smem = 2u * (65536u + 4u * bn * 128u) + 1024u + 256u;
     char name[64];
-    snprintf(name, sizeof name, "xmr_mm_u32_tc_nc%u_inj%d", nc, inj);
+    snprintf(name, sizeof name, "xmr_mm_u32_%s_nc%u_inj%d", atmem ? "tct" : "tc", nc, inj);
     CUfunction fn; int occ = 1;
     int rc = get_fn(name, smem, &fn, &occ); if (rc) return rc;
     CUtensorMap ma, mb;
@@ -483,10 +483,11 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
         snprintf(name, sizeof name, "xmr_mm_u32_nc%u_inj%d", nc, inj);
         {   /* tensor-core path (exact, u8 limbs on kind::i8) for tile-aligned problems; COAST_MM_PATH=tiled|naive overrides */
             const char* path = getenv("COAST_MM_PATH");
-            const int want_tc = !path || !strcmp(path, "tc");
+            const int want_tc = !path || !strcmp(path, "tc") || !strcmp(path, "tct");
             if (want_tc && d->M % 128u == 0 && d->N % 64u == 0 && d->K % 128u == 0 && aligned16 &&
                 !(((uintptr_t)d->d_aux) & 15u) && !(((uintptr_t)d->d_out) & 15u))
-                return launch_mm_tc(d, &a, inj, (CUstream)stream);
+                /* measured at 4096^3: A staged in TMEM wins for TMR (1.54 vs 2.45 ms); smem operands win for 1-2 replicas */
+                return launch_mm_tc(d, &a, inj, (CUstream)stream, path ? !strcmp(path, "tct") : nc == 3);
             if (path && !strcmp(path, "naive")) break;
         }
         /* register-tiled fast path: 64 x 128 x 16 tiles, NC x 128 threads (replicas on adjacent warps) */

@@ -76,6 +76,11 @@ __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {       // one lane of a CONVERGED warp (SASS ELECT)
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), fixed 0b001 [46,49),
@@ -138,8 +143,11 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
                 tma_load_3d(sB + s * B_STAGE, map_b, &full[s], 0, (int)(kb * BK), n0 / 32);      // box {32 n, 32 k, 4 chunks}
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer: every MMA is issued NC times into NC accumulators =====
+    } else if (warp == 1) {
+        // ===== MMA issuer: the whole warp walks the pipeline converged, ONE elected lane issues; every MMA is issued NC times
+        // into NC accumulators.  (A lone diverged thread makes ptxas wrap each UTC*MMA in an elect/branch loop and rebuild both
+        // descriptors per instruction; hoisting the descriptor arithmetic leaves one UTCHMMA + one 64-bit add per MMA.)
+        const bool leader = elect_one();
         uint32_t it = 0, tcount = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
             mbar_wait(tmem_empty, (tcount & 1u) ^ 1u);         // epilogue drained the accumulators of the previous tile
@@ -148,21 +156,25 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(sA + s * A_STAGE), b_addr = smem_u32(sB + s * B_STAGE);
-#pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
+                if (leader) {
                     // A: K-major SW128, rows 128 B apart, 8-row groups 1024 B apart; advance 32 B per UMMA_K inside the swizzle row
-                    const uint64_t da = smem_desc(a_addr + k * UMMA_K * 4, 16, 1024, SWZ_128B);
+                    const uint64_t da0 = smem_desc(smem_u32(sA + s * A_STAGE), 16, 1024, SWZ_128B);
                     // B: MN-major, 32B-atom swizzle: atom = 4 k-rows x 128 B (512 B, SBO); N chunks BK*128 B apart (LBO);
                     // one UMMA_K = 8 k-rows = 1024 B further down the chunk
-                    const uint64_t db = smem_desc(b_addr + k * 1024, BK * 128, 512, SWZ_128B_BASE32B);
+                    const uint64_t db0 = smem_desc(smem_u32(sB + s * B_STAGE), BK * 128, 512, SWZ_128B_BASE32B);
 #pragma unroll
-                    for (int r = 0; r < NC; ++r)
-                        tc_mma_tf32(tmem_base + r * BN, da, db, IDESC, (kb | (uint32_t)k) ? 1u : 0u);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t da = da0 + (uint64_t)((k * UMMA_K * 4) >> 4), db = db0 + (uint64_t)((k * 1024) >> 4);
+#pragma unroll
+                        for (int r = 0; r < NC; ++r)
+                            tc_mma_tf32(tmem_base + r * BN, da, db, IDESC, (kb | (uint32_t)k) ? 1u : 0u);
+                    }
+                    tc_commit(&empty[s]);                       // smem slot free once these MMAs retire
                 }
-                tc_commit(&empty[s]);                           // smem slot free once these MMAs retire
+                __syncwarp();
             }
-            tc_commit(tmem_full);                               // accumulators complete
+            if (leader) tc_commit(tmem_full);                   // accumulators complete
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers, vote, count, ONE store =====

@@ -9,8 +9,9 @@
 //
 // Data path:  xmr_mm_split_a / xmr_mm_split_bt (pre-pass, library scratch): A -> 4 u8 planes [l][M][K], B -> 4 TRANSPOSED
 // u8 planes [l][N][K] (both K-major: the plain SWIZZLE_128B K-major descriptor, no MN-major special case);
-// TMA (one 3-D box per operand per stage: {128 k, rows, 4 planes}) -> 2-stage ring; the MMA thread issues, per 32-byte
-// k-step, the 10 limb-pair MMAs NC times into NC x 4 TMEM accumulators (S0..S3 per replica, BN columns each);
+// TMA (one 3-D box per operand per stage: {128 k, rows, 4 planes}) -> 2-stage ring; the elected lane of the MMA warp issues,
+// per 32-byte k-step, the 10 limb-pair MMAs NC times into NC x 4 TMEM accumulators (S0..S3 per replica, BN columns each)
+// (staging A in TMEM with tcgen05.cp + TS-mode MMAs works -- tools/probe/tc_probe_i8.cu -- but measured slower here);
 // the epilogue recombines each replica's C from its four accumulators, votes element-wise (one mm_t vote per unit),
 // counts, and stores ONE C tile.  Fault site s (`sum` after k-step s) is applied lazily and exactly as in xmr_mm_tiled.cuh.
 #pragma once
@@ -23,13 +24,18 @@ namespace mmtc {
 using namespace xmr::gemm;
 
 constexpr int TBM = 128, TBK = 128;                 // 128 u8 of K = one 128-byte swizzle row = 4 MMAs of K=32
-template <int NC> struct Geom {
-    static constexpr int BN = NC == 3 ? 32 : 64;     // NC x 4 accumulators x BN columns <= 512 TMEM columns
+// ATMEM: stage each k-block's A limb planes into TMEM with tcgen05.cp and run the MMAs in TS mode (A from TMEM): every A slice
+// is then fetched from shared memory once instead of by each of the up to 4 x NC MMAs that use it.
+template <int NC, bool ATMEM> struct Geom {
+    static constexpr int BN = ATMEM ? (NC == 1 ? 64 : 32) : (NC == 3 ? 32 : 64);   // accumulators (+128 columns of staged A) <= 512
     static constexpr uint32_t A_STAGE_B = 4u * TBM * TBK;            // 64 KiB: [plane][row][128 B]
     static constexpr uint32_t B_STAGE_B = 4u * BN * TBK;             // 16 / 32 KiB
     static constexpr int STAGES_ = 2;
     static constexpr uint32_t SMEM = STAGES_ * (A_STAGE_B + B_STAGE_B) + 1024 + 256;
-    static constexpr uint32_t TMEM = NC * 4 * BN <= 256 ? 256 : 512;
+    static constexpr uint32_t ACC_COLS = NC * 4 * BN;                // S0..S3 per replica
+    static constexpr uint32_t A_COLS = ATMEM ? 4 * (TBK / 32) * 8 : 0;   // 4 planes x 4 k-steps x (32 bytes = 8 columns)
+    static constexpr uint32_t TMEM = ACC_COLS + A_COLS <= 256 ? 256 : 512;
+    static_assert(ACC_COLS + A_COLS <= 512, "TMEM budget");
 };
 // idesc: c_format S32 (2) [4,6); a/b format 0 = UNSIGNED 8 bit [7,10)/[10,13); both K-major; N>>3 [17,23); M>>4 [24,29)
 template <int BN> struct IdescU8 { static constexpr uint32_t value = (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24); };
@@ -40,14 +46,25 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from TMEM (128 lanes x 8 columns = 128 rows x 32 bytes of K), B from shared memory
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// shared memory (matrix descriptor, 128 rows x 256 bits) -> TMEM (128 lanes x 8 columns); SASS UTCCP
+__device__ __forceinline__ void tc_cp_128x256b(uint32_t taddr, uint64_t s_desc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(s_desc) : "memory");
+}
 __device__ __forceinline__ void tc_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
 }
 
-template <int NC, bool INJECT>
+template <int NC, bool INJECT, bool ATMEM>
 __device__ __forceinline__ void body(const xmr_args& a, const CUtensorMap* map_a, const CUtensorMap* map_b) {
-    using G = Geom<NC>;
+    using G = Geom<NC, ATMEM>;
     constexpr int BN = G::BN, STAGES_ = G::STAGES_;
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023u) & ~(uintptr_t)1023u);
@@ -84,6 +101,7 @@ __device__ __forceinline__ void body(const xmr_args& a, const CUtensorMap* map_a
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_a = tmem_base + G::ACC_COLS;            // ATMEM: staged A operand
 
     if (warp == 0 && lane == 0) {
         uint32_t it = 0;
@@ -97,8 +115,13 @@ __device__ __forceinline__ void body(const xmr_args& a, const CUtensorMap* map_a
                 tma_load_3d(sB + s * G::B_STAGE_B, map_b, &full[s], (int)(kb * TBK), (int)(tn * BN), 0);    // box {128 k, BN n, 4 planes}
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
+        // The WHOLE warp walks the pipeline (converged), one elected lane issues.  With a lone diverged thread ptxas wraps
+        // every UTCIMMA in an elect/branch loop and rebuilds both descriptors per MMA (~50 issue cycles each, measured:
+        // 2.9 ms for the 4096^3 TMR problem, 3x the tensor time); hoisting the descriptor arithmetic and electing inside
+        // converged code leaves one UTCIMMA + one add per MMA.
         constexpr uint32_t IDESC_U8 = IdescU8<BN>::value;
+        const bool leader = elect_one();
         uint32_t it = 0, tcount = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
             mbar_wait(tmem_empty, (tcount & 1u) ^ 1u);
@@ -107,25 +130,41 @@ __device__ __forceinline__ void body(const xmr_args& a, const CUtensorMap* map_a
                 const uint32_t s = it % STAGES_, ph = (it / STAGES_) & 1u;
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(sA + s * G::A_STAGE_B), b_addr = smem_u32(sB + s * G::B_STAGE_B);
+                if (leader) {
+                    // descriptors differ only in the 14-bit start-address field: base + (plane offset + k*32) >> 4
+                    const uint64_t da0 = smem_desc(smem_u32(sA + s * G::A_STAGE_B), 16, 1024, SWZ_128B);
+                    const uint64_t db0 = smem_desc(smem_u32(sB + s * G::B_STAGE_B), 16, 1024, SWZ_128B);
+                    if (ATMEM) {   // tcgen05.cp and tcgen05.mma execute in issue order: this copy cannot overtake MMAs still reading block kb-1
 #pragma unroll
-                for (int k = 0; k < TBK / 32; ++k) {
+                        for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int d = 0; d < 4; ++d) {                // diagonal d = i + j: shift 8d, accumulator S_d
+                            for (int k = 0; k < TBK / 32; ++k)
+                                tc_cp_128x256b(tmem_a + (i * (TBK / 32) + k) * 8, da0 + (uint64_t)((i * (TBM * TBK) + k * 32) >> 4));
+                    }
 #pragma unroll
-                        for (int i = 0; i <= d; ++i) {
-                            const int j = d - i;
-                            const uint64_t da = smem_desc(a_addr + i * (TBM * TBK) + k * 32, 16, 1024, SWZ_128B);
-                            const uint64_t db = smem_desc(b_addr + j * (BN * TBK) + k * 32, 16, 1024, SWZ_128B);
-                            const uint32_t acc = (kb | (uint32_t)k | (uint32_t)i) ? 1u : 0u;   // first MMA into S_d of this tile overwrites
+                    for (int k = 0; k < TBK / 32; ++k) {
 #pragma unroll
-                            for (int r = 0; r < NC; ++r) tc_mma_i8(tmem_base + (r * 4 + d) * BN, da, db, IDESC_U8, acc);
+                        for (int d = 0; d < 4; ++d) {            // diagonal d = i + j: shift 8d, accumulator S_d
+#pragma unroll
+                            for (int i = 0; i <= d; ++i) {
+                                const int j = d - i;
+                                const uint64_t da = da0 + (uint64_t)((i * (TBM * TBK) + k * 32) >> 4);
+                                const uint64_t db = db0 + (uint64_t)((j * (BN * TBK) + k * 32) >> 4);
+                                const uint32_t acc = (kb | (uint32_t)k | (uint32_t)i) ? 1u : 0u;   // first MMA into S_d overwrites
+#pragma unroll
+                                for (int r = 0; r < NC; ++r) {
+                                    if (ATMEM) tc_mma_i8_ts(tmem_base + (r * 4 + d) * BN, tmem_a + (i * (TBK / 32) + k) * 8, db, IDESC_U8, acc);
+                                    else tc_mma_i8(tmem_base + (r * 4 + d) * BN, da, db, IDESC_U8, acc);
+                                }
+                            }
                         }
                     }
+                    tc_commit(&empty[s]);
                 }
-                tc_commit(&empty[s]);
+                __syncwarp();
             }
-            tc_commit(tmem_full);
+            if (leader) tc_commit(tmem_full);
+            __syncwarp();
         }
     } else if (warp >= 4) {
         const int q = warp & 3;
@@ -246,7 +285,12 @@ xmr_mm_split_bt(const uint32_t* __restrict__ B, uint8_t* __restrict__ planes, un
     extern "C" __global__ void __launch_bounds__(256, 1)                                                 \
     xmr_mm_u32_tc_nc##NC##_inj##INJ(const __grid_constant__ xmr_args a, const __grid_constant__ CUtensorMap map_a, \
                                     const __grid_constant__ CUtensorMap map_b) {                         \
-        xmr::mmtc::body<NC, INJ != 0>(a, &map_a, &map_b);                                                \
+        xmr::mmtc::body<NC, INJ != 0, false>(a, &map_a, &map_b);                                         \
+    }                                                                                                    \
+    extern "C" __global__ void __launch_bounds__(256, 1)                                                 \
+    xmr_mm_u32_tct_nc##NC##_inj##INJ(const __grid_constant__ xmr_args a, const __grid_constant__ CUtensorMap map_a, \
+                                     const __grid_constant__ CUtensorMap map_b) {                        \
+        xmr::mmtc::body<NC, INJ != 0, true>(a, &map_a, &map_b);                                          \
     }
 XMR_MMTC_KERNEL(1, 0) XMR_MMTC_KERNEL(2, 0) XMR_MMTC_KERNEL(3, 0)
 XMR_MMTC_KERNEL(1, 1) XMR_MMTC_KERNEL(2, 1) XMR_MMTC_KERNEL(3, 1)

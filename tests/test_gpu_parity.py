@@ -459,6 +459,9 @@ def test_mm_tensor_core_limb_kernel_is_bit_exact(rt, oracle, nc, M, N, K, monkey
     for u, (r, s, b) in enumerate([(0, 0, 0), (1, K - 1, 31), (2, K // 2, 7), (0, 3, 30), (1, 0, 16)]):
         tab[u * 89 % (M * N)] = oracle.fault_entry(r, s, b)
     both(rt, oracle, oracle.K_MM_U32, nc, A, M * N, M=M, N=N, K=K, aux=B, flags=3, table=tab)
+    for variant in ("tc", "tct"):                       # A operand from shared memory / staged in TMEM (tcgen05.cp + TS-mode MMA)
+        monkeypatch.setenv("COAST_MM_PATH", variant)
+        g_v, _ = both(rt, oracle, oracle.K_MM_U32, nc, A, M * N, M=M, N=N, K=K, aux=B, flags=3, plan_kw=dict(seed=K, p=0.02))
     monkeypatch.setenv("COAST_MM_PATH", "tiled")
     if N % 128 == 0:
         g_tiled, _ = both(rt, oracle, oracle.K_MM_U32, nc, A, M * N, M=M, N=N, K=K, aux=B, flags=3)

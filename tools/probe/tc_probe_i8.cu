@@ -22,7 +22,7 @@ __device__ __forceinline__ uint64_t sdesc(uint32_t saddr, uint32_t lbo, uint32_t
 
 constexpr int BN = 32;
 // A: [128][K] u8 K-major, B^T: [BN][K] u8 K-major; C[128][BN] s32 = sum_k A*B, accumulated over K/128 k-blocks
-__global__ void __launch_bounds__(256, 1) probe(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUtensorMap mb, uint32_t* C, int kblocks, int fmt) {
+__global__ void __launch_bounds__(256, 1) probe(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUtensorMap mb, uint32_t* C, int kblocks, int fmt, int a_in_tmem) {
     extern __shared__ uint8_t dyn[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)dyn + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem; uint8_t* sB = smem + 16384;
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256, 1) probe(const __grid_constant__ CUtensor
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(s32(slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(s32(slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -55,10 +55,20 @@ __global__ void __launch_bounds__(256, 1) probe(const __grid_constant__ CUtensor
         for (int kb = 0; kb < kblocks; ++kb) {
             mbar_wait(full, kb & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (a_in_tmem) {
+                // stage the whole 128 x 128-byte A tile into TMEM columns [32, 64): 4 copies of 128 rows x 256 bits (one per K=32 step)
+                for (int k = 0; k < 4; ++k) {
+                    uint64_t da = sdesc(s32(sA) + k * 32, 16, 1024, 2);
+                    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tb + 32 + k * 8), "l"(da) : "memory");
+                }
+            }
             for (int k = 0; k < 4; ++k) {
                 uint64_t da = sdesc(s32(sA) + k * 32, 16, 1024, 2), db = sdesc(s32(sB) + k * 32, 16, 1024, 2);
                 uint32_t acc = (kb | k) ? 1u : 0u;
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tb), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                if (a_in_tmem)
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tb), "r"(tb + 32 + k * 8), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                else
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tb), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(empty)) : "memory");
         }
@@ -77,18 +87,19 @@ __global__ void __launch_bounds__(256, 1) probe(const __grid_constant__ CUtensor
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tb) : "memory");
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tb) : "memory");
 }
 
 int main() {
     RK(cudaSetDevice(0)); RK(cudaFree(0));
     const int M = 128;
-    for (int test = 0; test < 3; ++test) {
-        const int K = test == 0 ? 128 : (test == 1 ? 512 : 128 * 300);      // test 2: 255*255*38400 = 2.5e9 > 2^31 -> wrap or saturate?
+    for (int test = 0; test < 6; ++test) {
+        const int a_in_tmem = test >= 3;
+        const int K = test % 3 == 0 ? 128 : (test % 3 == 1 ? 512 : 128 * 300);      // test 2: 255*255*38400 = 2.5e9 > 2^31 -> wrap or saturate?
         std::vector<uint8_t> A((size_t)M * K), Bt((size_t)BN * K);
         std::vector<uint32_t> C(M * BN), ref(M * BN);
-        for (int i = 0; i < M; ++i) for (int k = 0; k < K; ++k) A[(size_t)i * K + k] = test == 2 ? 255 : (uint8_t)((i * 7 + k * 13 + 200) & 0xFF);
-        for (int j = 0; j < BN; ++j) for (int k = 0; k < K; ++k) Bt[(size_t)j * K + k] = test == 2 ? (uint8_t)(255 - (j & 1)) : (uint8_t)((j * 11 + k * 3 + 130) & 0xFF);
+        for (int i = 0; i < M; ++i) for (int k = 0; k < K; ++k) A[(size_t)i * K + k] = test % 3 == 2 ? 255 : (uint8_t)((i * 7 + k * 13 + 200) & 0xFF);
+        for (int j = 0; j < BN; ++j) for (int k = 0; k < K; ++k) Bt[(size_t)j * K + k] = test % 3 == 2 ? (uint8_t)(255 - (j & 1)) : (uint8_t)((j * 11 + k * 3 + 130) & 0xFF);
         for (int i = 0; i < M; ++i) for (int j = 0; j < BN; ++j) { uint32_t s = 0; for (int k = 0; k < K; ++k) s += (uint32_t)A[(size_t)i * K + k] * Bt[(size_t)j * K + k]; ref[i * BN + j] = s; }
         uint8_t *dA, *dB; uint32_t* dC;
         RK(cudaMalloc(&dA, A.size())); RK(cudaMalloc(&dB, Bt.size())); RK(cudaMalloc(&dC, C.size() * 4));
@@ -100,9 +111,9 @@ int main() {
           CK(cuTensorMapEncodeTiled(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dB, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)); }
         RK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
         RK(cudaMemset(dC, 0xff, C.size() * 4));
-        probe<<<1, 256, 32768>>>(ma, mb, dC, K / 128, 0);
+        probe<<<1, 256, 32768>>>(ma, mb, dC, K / 128, 0, a_in_tmem);
         cudaError_t e = cudaDeviceSynchronize();
-        printf("test %d (K=%d): sync = %s\n", test, K, cudaGetErrorString(e));
+        printf("test %d (K=%d, A %s): sync = %s\n", test, K, a_in_tmem ? "in TMEM via tcgen05.cp" : "from smem", cudaGetErrorString(e));
         if (e != cudaSuccess) return 1;
         RK(cudaMemcpy(C.data(), dC, C.size() * 4, cudaMemcpyDeviceToHost));
         int bad = 0; for (int i = 0; i < M * BN; ++i) bad += C[i] != ref[i];
