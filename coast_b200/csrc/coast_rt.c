@@ -656,6 +656,8 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int call_
         }
         rc = coast_launch(&c, G.hs[slot]); if (rc) return rc;
         DRV(p_cuMemcpyDtoHAsync_v2((uint8_t*)d->d_out + done * ob, G.h_out[slot], (size_t)(n * ob), G.hs[slot]));
+        if (per_unit_key && (d->mode & COAST_AES_KEY_WRITEBACK))
+            DRV(p_cuMemcpyDtoHAsync_v2((uint8_t*)d->d_aux + done * 16, G.h_aux[slot], (size_t)(n * 16), G.hs[slot]));
         done += n; slot = (slot + 1) % 3;
     }
     DRV(p_cuStreamSynchronize(G.hs[0])); DRV(p_cuStreamSynchronize(G.hs[1]));
@@ -702,8 +704,9 @@ void coast_xmr_sha256_hash(unsigned char ctx_data[], uint32_t ctx_bitlen[], uint
 void coast_xmr_aes_enc_dec(unsigned char* state, unsigned char* key, unsigned char dir) {
     coast_launch_desc d; memset(&d, 0, sizeof d);
     entry_mode(&d.num_clones, &d.flags);
-    d.kernel = COAST_K_AES128; d.n_units = 1; d.mode = dir ? COAST_AES_DECRYPT : 0; d.d_in = state; d.d_out = state;
-    memcpy(d.key, key, 16);
+    /* per-unit-key mode with write-back so key[] is mutated exactly as TI_aes_128.c:107-231 does */
+    d.kernel = COAST_K_AES128; d.n_units = 1; d.d_in = state; d.d_out = state; d.d_aux = key;
+    d.mode = (dir ? COAST_AES_DECRYPT : 0) | COAST_AES_KEY_PER_UNIT | COAST_AES_KEY_WRITEBACK;
     entry_run(&d);
 }
 void coast_xmr_matrix_multiply_u32(const uint32_t* f, const uint32_t* s, uint32_t* r, int side) {

@@ -290,6 +290,13 @@ __device__ __forceinline__ void aes128_gen_body(const xmr_args& a) {
         for (int i = 0; i < 4; ++i)
             c[i] = (uint32_t)s[4 * i] | ((uint32_t)s[4 * i + 1] << 8) | ((uint32_t)s[4 * i + 2] << 16) | ((uint32_t)s[4 * i + 3] << 24);
         aes_vote_store<NC>(c, static_cast<uint8_t*>(a.out), local, a.unit_base + local, valid, lane, a.flags, tally);
+        if ((a.mode & 4u) && per_unit && valid && Lanes<NC>::voter(lane)) {      // COAST_AES_KEY_WRITEBACK: replica 0's mutated key[]
+            uint32_t kw[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                kw[i] = (uint32_t)k[4 * i] | ((uint32_t)k[4 * i + 1] << 8) | ((uint32_t)k[4 * i + 2] << 16) | ((uint32_t)k[4 * i + 3] << 24);
+            *reinterpret_cast<uint4*>(static_cast<uint8_t*>(const_cast<void*>(a.aux)) + local * 16ull) = make_uint4(kw[0], kw[1], kw[2], kw[3]);
+        }
     }
     tally.flush(a.counters);
 }

@@ -16,7 +16,7 @@ K_CRC16, K_SHA256, K_AES128, K_MM_U32, K_GEMM_TF32 = range(5)
 F_COUNT_ERRORS, F_COUNT_SYNCS, F_NO_MEM_REPLICATION = 0x1, 0x2, 0x4
 F_INTERLEAVE, F_SEGMENT, F_VERBOSE, F_MAJORITY_VOTER = 0x8, 0x10, 0x20, 0x100
 PLAN_NONE, PLAN_BERNOULLI, PLAN_TABLE = 0, 1, 2
-AES_DECRYPT, AES_KEY_PER_UNIT = 1, 2
+AES_DECRYPT, AES_KEY_PER_UNIT, AES_KEY_WRITEBACK = 1, 2, 4
 NO_FAULT_UNIT = 0xFFFFFFFFFFFFFFFF
 ERR_NO_DRIVER, ERR_NOT_INIT, ERR_BAD_ARG, ERR_UNSUPPORTED = -100001, -100002, -100003, -100004
 

@@ -141,6 +141,10 @@ typedef struct coast_fault_plan {
  */
 #define COAST_AES_DECRYPT       0x1u
 #define COAST_AES_KEY_PER_UNIT  0x2u
+#define COAST_AES_KEY_WRITEBACK 0x4u   /* with KEY_PER_UNIT: store what aes_enc_dec() leaves in key[] (TI_aes_128.c:214-221 mutates
+                                          it: the last round key after encrypt, the original key after decrypt) back into d_aux.
+                                          key[] is replica memory that never crosses the SoR through a vote, so -- like unprotected
+                                          code reading a protected global (verification.cpp:690-710) -- copy 0 is what is stored. */
 
 typedef struct coast_launch_desc {
     uint32_t kernel;       /* coast_kernel_id                                    */

@@ -466,3 +466,27 @@ def test_mm_tensor_core_limb_kernel_is_bit_exact(rt, oracle, nc, M, N, K, monkey
     if N % 128 == 0:
         g_tiled, _ = both(rt, oracle, oracle.K_MM_U32, nc, A, M * N, M=M, N=N, K=K, aux=B, flags=3)
         assert g_tiled.tobytes() == g_tc.tobytes()
+
+
+def test_aes_key_mutation_matches_the_reference(rt, oracle, golden):
+    """aes_enc_dec() leaves the last round key in key[] after encrypt and the original key after decrypt
+    (TI_aes_128.c:214-221,133-141); pinned by running the reference (tests/golden: key_after_enc/dec)."""
+    import ctypes as C
+    import coast_b200 as cb
+    rec = np.frombuffer(H(golden["aes"]["records"]), dtype=np.uint8).reshape(568, 80)
+    kenc = np.frombuffer(H(golden["aes"]["key_after_enc"]), dtype=np.uint8)
+    kdec = np.frombuffer(H(golden["aes"]["key_after_dec"]), dtype=np.uint8)
+    keys = dev(rt, np.ascontiguousarray(rec[:, 0:16]))
+    enc, _ = rt.run(cb.K_AES128, 3, dev(rt, np.ascontiguousarray(rec[:, 64:80])), 568, aux=keys,
+                    mode=cb.AES_KEY_PER_UNIT | cb.AES_KEY_WRITEBACK, flags=3)
+    assert host(enc).tobytes() == np.ascontiguousarray(rec[:, 32:48]).tobytes() and host(keys).tobytes() == kenc.tobytes()
+    keys2 = dev(rt, np.ascontiguousarray(rec[:, 16:32]))
+    dec, _ = rt.run(cb.K_AES128, 2, enc, 568, aux=keys2, mode=cb.AES_KEY_PER_UNIT | cb.AES_KEY_WRITEBACK | cb.AES_DECRYPT)
+    assert host(dec).tobytes() == np.ascontiguousarray(rec[:, 48:64]).tobytes() and host(keys2).tobytes() == kdec.tobytes()
+    # and through the reference-facing entry point
+    L = rt.L
+    assert L.coast_set_opt_passes(b"-TMR") == 0
+    r = rec[300].tobytes()
+    state, key = C.create_string_buffer(r[64:80], 16), C.create_string_buffer(r[0:16], 16)
+    L.coast_xmr_aes_enc_dec(state, key, 0)
+    assert state.raw == r[32:48] and key.raw == kenc[16 * 300: 16 * 301].tobytes()
