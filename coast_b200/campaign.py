@@ -24,7 +24,7 @@ import numpy as np
 
 from . import runtime as R
 
-WORKLOADS = {"crc16": R.K_CRC16, "sha256": R.K_SHA256, "aes": R.K_AES128, "mm": R.K_MM_U32}
+WORKLOADS = {"crc16": R.K_CRC16, "sha256": R.K_SHA256, "aes": R.K_AES128, "mm": R.K_MM_U32, "qsort": R.K_QSORT}
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -79,6 +79,9 @@ def site_name(kernel, unit_bytes, site):
         return f"aes.state_in[{site}]" if site < 16 else f"aes.round{(site - 16) // 16}.state[{(site - 16) % 16}]"
     if kernel == R.K_MM_U32:
         return f"mm.sum@k{site}"
+    if kernel == R.K_QSORT:
+        L = unit_bytes // 4
+        return f"qsort.cmp_operand@event{site}" if site < 32 * L else f"qsort.array[{site - 32 * L}]"
     return f"site{site}"
 
 
@@ -155,7 +158,7 @@ def run_campaign(rt, workload: str, opt_passes: str, n_injections: int, seed: in
         inp, kw = A, dict(M=side, N=side, K=side, aux=B)
         ub = 0
     else:
-        ub = {R.K_CRC16: 64, R.K_SHA256: 64, R.K_AES128: 16}[kernel] if unit_bytes is None else unit_bytes
+        ub = {R.K_CRC16: 64, R.K_SHA256: 64, R.K_AES128: 16, R.K_QSORT: 4 * 580}[kernel] if unit_bytes is None else unit_bytes
         nbytes = (n * ub + 3) // 4 * 4
         inp = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         rt.fill_philox(inp, data_seed)
@@ -173,7 +176,7 @@ def run_campaign(rt, workload: str, opt_passes: str, n_injections: int, seed: in
     t1.record()
     t1.synchronize()
     per_run_s = t0.elapsed_time(t1) * 1e-3 / n
-    ob = R.OUT_BYTES[kernel]
+    ob = R.out_bytes(kernel, ub)
     wrong = (out.view(n, ob) != golden.view(n, ob)).any(dim=1).cpu().numpy()[:n_injections]
     stat = status.cpu().numpy()[:n_injections]
     active, replica, site, bit = plan_faults(kernel, nc, ub, K, n_injections, seed, 0xFFFFFFFF)
@@ -181,7 +184,7 @@ def run_campaign(rt, workload: str, opt_passes: str, n_injections: int, seed: in
     records = []
     for u in range(n_injections):
         name = site_name(kernel, ub, site[u])
-        section = "memory" if (".data[" in name or ".m[" in name or "state_in" in name) else "registers"
+        section = "memory" if (".data[" in name or ".m[" in name or "state_in" in name or ".array[" in name) else "registers"
         if nc == 2 and stat[u]:
             res = abort_result("FAULT_DETECTED_DWC")
             summ.detected += 1

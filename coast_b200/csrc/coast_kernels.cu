@@ -11,3 +11,4 @@
 #include "xmr_mm_tiled.cuh"
 #include "xmr_gemm_tf32.cuh"
 #include "xmr_mm_tc.cuh"
+#include "xmr_qsort.cuh"

@@ -273,6 +273,7 @@ uint32_t coast_fault_sites(uint32_t kernel, uint32_t unit_bytes, uint32_t K) {
     case COAST_K_AES128:    return 176u;
     case COAST_K_MM_U32:    return K;
     case COAST_K_GEMM_TF32: return 1u;
+    case COAST_K_QSORT:     return 33u * (unit_bytes / 4u);
     default:                return 0u;
     }
 }
@@ -283,16 +284,19 @@ uint32_t coast_fault_site_bits(uint32_t kernel, uint32_t unit_bytes, uint32_t K,
     return 32u;
 }
 uint32_t coast_out_bytes_per_unit(uint32_t kernel) {
-    static const uint32_t ob[COAST_K_COUNT_] = { 2, 32, 16, 4, 4 };
+    static const uint32_t ob[COAST_K_COUNT_] = { 2, 32, 16, 4, 4, 0 };
     return kernel < COAST_K_COUNT_ ? ob[kernel] : 0;
 }
 uint32_t coast_votes_per_unit(uint32_t kernel) {
-    static const uint32_t nv[COAST_K_COUNT_] = { 1, 32, 16, 1, 1 };
+    static const uint32_t nv[COAST_K_COUNT_] = { 1, 32, 16, 1, 1, 0 };
     return kernel < COAST_K_COUNT_ ? nv[kernel] : 0;
+}
+uint32_t coast_out_bytes(uint32_t kernel, uint32_t unit_bytes) {
+    return kernel == COAST_K_QSORT ? unit_bytes : coast_out_bytes_per_unit(kernel);
 }
 static uint64_t in_bytes_per_unit(const coast_launch_desc* d) {
     switch (d->kernel) {
-    case COAST_K_CRC16: case COAST_K_SHA256: return d->unit_bytes;
+    case COAST_K_CRC16: case COAST_K_SHA256: case COAST_K_QSORT: return d->unit_bytes;
     case COAST_K_AES128: return 16;
     default: return 0;
     }
@@ -497,6 +501,12 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
             snprintf(name, sizeof name, "xmr_mm_u32_tiled_nc%u_inj%d", nc, inj);
         }
         break;
+    case COAST_K_QSORT:
+        if (d->unit_bytes < 4 || (d->unit_bytes & 3u) || d->unit_bytes > 4096u)
+            return fail(COAST_ERR_BAD_ARG, "quicksort arrays are 1..1024 int32 (unit_bytes = 4*L, got %u)", d->unit_bytes);
+        block = 128;
+        snprintf(name, sizeof name, "xmr_qsort_nc%u_inj%d", nc, inj);
+        break;
     case COAST_K_GEMM_TF32:
         if (!d->d_aux || !d->M || !d->N || !d->K) return fail(COAST_ERR_BAD_ARG, "GEMM needs A (d_in), B (d_aux) and M,N,K");
         if (d->n_units != (uint64_t)d->M * d->N) return fail(COAST_ERR_BAD_ARG, "GEMM: n_units must be M*N");
@@ -526,7 +536,8 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
         grid = (d->M / 64u) * (d->N / 128u);
     } else {
         uint64_t warps = (d->n_units + upw - 1) / upw;
-        uint64_t ctas = (warps + XMR_WARPS - 1) / XMR_WARPS;
+        uint64_t wpc = (uint64_t)block / 32u;
+        uint64_t ctas = (warps + wpc - 1) / wpc;
         uint64_t cap = (uint64_t)G.sm_count * (unsigned)occ * 4u;
         grid = (unsigned)(ctas < cap ? ctas : cap);
     }
@@ -608,7 +619,7 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int call_
     if (!d) return fail(COAST_ERR_BAD_ARG, "null descriptor");
     if (d->plan && d->plan->mode == COAST_PLAN_TABLE) return fail(COAST_ERR_UNSUPPORTED, "coast_run_host: TABLE plans need device pointers; use coast_launch");
     for (int i = 0; i < 3; ++i) if (!G.hs[i]) DRV(p_cuStreamCreate(&G.hs[i], CU_STREAM_NON_BLOCKING));
-    const uint64_t ob = coast_out_bytes_per_unit(d->kernel);
+    const uint64_t ob = coast_out_bytes(d->kernel, d->unit_bytes);
     if (d->kernel == COAST_K_MM_U32 || d->kernel == COAST_K_GEMM_TF32) {   /* one shot: A, B in; C out */
         size_t ab = (size_t)d->M * d->K * 4, bb = (size_t)d->K * d->N * 4, cb = (size_t)d->M * d->N * 4;
         rc = slot_reserve(&G.h_in[0], &G.h_in_cap[0], ab); if (rc) return rc;

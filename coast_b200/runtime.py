@@ -12,7 +12,7 @@ from dataclasses import dataclass
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-K_CRC16, K_SHA256, K_AES128, K_MM_U32, K_GEMM_TF32 = range(5)
+K_CRC16, K_SHA256, K_AES128, K_MM_U32, K_GEMM_TF32, K_QSORT = range(6)
 F_COUNT_ERRORS, F_COUNT_SYNCS, F_NO_MEM_REPLICATION = 0x1, 0x2, 0x4
 F_INTERLEAVE, F_SEGMENT, F_VERBOSE, F_MAJORITY_VOTER = 0x8, 0x10, 0x20, 0x100
 PLAN_NONE, PLAN_BERNOULLI, PLAN_TABLE = 0, 1, 2
@@ -21,6 +21,10 @@ NO_FAULT_UNIT = 0xFFFFFFFFFFFFFFFF
 ERR_NO_DRIVER, ERR_NOT_INIT, ERR_BAD_ARG, ERR_UNSUPPORTED = -100001, -100002, -100003, -100004
 
 OUT_BYTES = {K_CRC16: 2, K_SHA256: 32, K_AES128: 16, K_MM_U32: 4, K_GEMM_TF32: 4}
+
+
+def out_bytes(kernel: int, unit_bytes: int = 0) -> int:
+    return unit_bytes if kernel == K_QSORT else OUT_BYTES[kernel]
 
 
 class CoastError(RuntimeError):
@@ -93,7 +97,7 @@ _LIB = None
 EXPORTS = [
     "coast_init", "coast_shutdown", "coast_last_error", "coast_version", "coast_parse_opt_passes", "coast_launch",
     "coast_sync", "coast_sync_noabort", "coast_stats_snapshot", "coast_stats_reset", "coast_fault_sites",
-    "coast_fault_site_bits", "coast_out_bytes_per_unit", "coast_votes_per_unit", "coast_malloc", "coast_free",
+    "coast_fault_site_bits", "coast_out_bytes_per_unit", "coast_out_bytes", "coast_votes_per_unit", "coast_malloc", "coast_free",
     "coast_memcpy_h2d", "coast_memcpy_d2h", "coast_memset", "coast_host_alloc", "coast_host_free",
     "coast_stream_create", "coast_stream_destroy", "coast_stream_sync", "coast_fill_philox", "coast_run_host",
     "coast_run_host_noabort",
@@ -229,7 +233,7 @@ class Runtime:
             key: bytes | None = None, plan: FaultPlan | None = None, unit_base=0, out=None, stream=None, status=None):
         torch = self.torch
         if out is None:
-            out = torch.empty(n_units * OUT_BYTES[kernel], dtype=torch.uint8, device=f"cuda:{self.device}")
+            out = torch.empty(n_units * out_bytes(kernel, unit_bytes), dtype=torch.uint8, device=f"cuda:{self.device}")
         d = self.make_desc(kernel, num_clones, inp, out, n_units, flags=flags, mode=mode, unit_bytes=unit_bytes,
                            M=M, N=N, K=K, d_aux=aux, key=key, plan=plan, unit_base=unit_base, d_status=status)
         self.launch(d, stream)

@@ -60,7 +60,9 @@ typedef enum coast_kernel_id {
     COAST_K_MM_U32    = 3, /* tests/mm_common/mm_common_tmr.c:3-20 (exact, mod 2^32;
                               same low 32 bits as matrixMultiply.c:95-112)      */
     COAST_K_GEMM_TF32 = 4, /* BASELINE config 4: fp32 in/out, tcgen05 kind::tf32 */
-    COAST_K_COUNT_    = 5
+    COAST_K_QSORT     = 5, /* tests/quicksort/quicksort.c:121-136: data-dependent branches -> the
+                              branch conditions are the sync points, voted inside the loops */
+    COAST_K_COUNT_    = 6
 } coast_kernel_id;
 
 /* numClones of dataflowProtection::run: 3 = -TMR, 2 = -DWC, 1 = unprotected
@@ -137,7 +139,8 @@ typedef struct coast_fault_plan {
  *            path: tcgen05 kind::i8 on u8 limbs when M%128 == N%64 == K%128 == 0 (uses library-owned scratch for
  *            the limb planes: keep such launches on ONE stream), register-tiled CUDA cores when M%64 == N%128 ==
  *            K%16 == 0, a plain kernel otherwise (e.g. the 9 x 9 tests).  COAST_MM_PATH=tc|tiled|naive overrides.
- *   GEMM_TF32 same with float.  unit_base/rows: see row_base.
+ *   GEMM_TF32 same with float.
+ *   QSORT    in : n_units x unit_bytes, arrays of L = unit_bytes/4 int32 (L <= 1024)   out: the sorted arrays
  */
 #define COAST_AES_DECRYPT       0x1u
 #define COAST_AES_KEY_PER_UNIT  0x2u
@@ -212,7 +215,8 @@ int  coast_stats_reset(void* stream);
 /* --- fault-site geometry (shared by oracle and kernels) ------------- */
 uint32_t coast_fault_sites(uint32_t kernel, uint32_t unit_bytes, uint32_t K);
 uint32_t coast_fault_site_bits(uint32_t kernel, uint32_t unit_bytes, uint32_t K, uint32_t site);
-uint32_t coast_out_bytes_per_unit(uint32_t kernel);
+uint32_t coast_out_bytes_per_unit(uint32_t kernel);                      /* 0 for QSORT (variable) */
+uint32_t coast_out_bytes(uint32_t kernel, uint32_t unit_bytes);          /* QSORT: unit_bytes, the sorted array */
 uint32_t coast_votes_per_unit(uint32_t kernel);  /* sync points per unit at the SoR exit */
 
 /* --- thin memory helpers for pure-C callers (no torch) --------------- */

@@ -60,6 +60,7 @@ uint32_t orc_fault_sites(uint32_t kernel, uint32_t unit_bytes, uint32_t K) {
     case ORC_K_AES128:    return 16u + 160u;
     case ORC_K_MM_U32:    return K;
     case ORC_K_GEMM_TF32: return 1u;
+    case ORC_K_QSORT:     return 33u * (unit_bytes / 4u);   /* 32*L dynamic compare events + L input-copy elements */
     default:              return 0u;
     }
 }
@@ -83,6 +84,10 @@ uint32_t orc_out_bytes_per_unit(uint32_t kernel) {
 /* One vote per output element OF THE C TYPE THE REFERENCE STORES:
  * u16 crc (crc16.c:30), u8 digest byte (sha256_common_tmr.c:169-178),
  * u8 state byte (TI_aes_128.c:226-229), mm_t element (mm_common_tmr.c:16). */
+uint32_t orc_out_bytes(uint32_t kernel, uint32_t unit_bytes) {
+    return kernel == ORC_K_QSORT ? unit_bytes : orc_out_bytes_per_unit(kernel);
+}
+
 uint32_t orc_votes_per_unit(uint32_t kernel) {
     switch (kernel) {
     case ORC_K_CRC16: return 1; case ORC_K_SHA256: return 32; case ORC_K_AES128: return 16;
@@ -337,6 +342,90 @@ float orc_gemm_tf32_elem(const float* A, const float* B, uint32_t K, uint32_t N,
 }
 
 /* ------------------------------------------------------------------ */
+/* quick_sort()  tests/quicksort/quicksort.c:121-136         */
+/* The one workload whose BRANCHES depend on data, so the sync points are */
+/* the conditional-branch conditions inside the loops (populateSyncPoints */
+/* synchronization.cpp:146-155, syncTerminator :741-1113, voter :934-938):*/
+/* the replicas run in lockstep, every data-dependent condition is voted  */
+/* and the ONE control flow follows the voted value; each replica keeps   */
+/* swapping inside its own copy of the array (memory replication).  The   */
+/* SoR exit votes each stored element.  Recursion is an explicit stack in */
+/* the reference's order (left part first, :134-135).                     */
+/* Fault sites: s < 32L: the value loaded for the s-th executed data      */
+/* comparison (a register flip); 32L <= s < 33L: element s-32L of the     */
+/* replica's private copy before sorting (an input-copy flip).            */
+/* ------------------------------------------------------------------ */
+typedef struct { int nc, majority, count_errors; uint64_t errors, syncs; int disagree; } qs_ctx;
+
+static int qs_vote_cond(qs_ctx* q, const int c[3]) {
+    q->syncs++;
+    if (q->nc == 1) return c[0];
+    if (q->nc == 2) { if (c[0] != c[1]) q->disagree = 1; return c[0]; }
+    const int c01 = c[0] == c[1], c02 = c[0] == c[2];
+    if (!(c01 && c02)) { q->disagree = 1; if (q->count_errors) q->errors++; }
+    if (q->majority) return (c[0] & c[1]) | (c[0] & c[2]) | (c[1] & c[2]);
+    return c01 ? c[0] : c[2];
+}
+
+static void orc_qsort_unit(const int32_t* in, uint32_t L, uint32_t nc, const orc_fault* f, uint32_t flags,
+                           int32_t rep[3][1024], qs_ctx* q) {
+    q->nc = (int)nc; q->majority = (flags & ORC_F_MAJORITY) != 0; q->count_errors = (flags & ORC_F_COUNT_ERRORS) != 0;
+    q->errors = q->syncs = 0; q->disagree = 0;
+    for (uint32_t r = 0; r < nc; ++r) memcpy(rep[r], in, 4u * L);
+    const int has = f && f->active;
+    if (has && f->site >= 32u * L) rep[f->replica][f->site - 32u * L] ^= (int32_t)(1u << f->bit);
+    uint32_t ev = 0;                                         /* dynamic index of the next data comparison */
+    uint32_t stack_off[1024], stack_len[1024]; int sp = 0;
+    stack_off[0] = 0; stack_len[0] = L; sp = 1;
+    while (sp > 0) {
+        --sp;
+        const uint32_t off = stack_off[sp], len = stack_len[sp];
+        q->syncs++;                                          /* `if (len < 2) return;` -- indices are never faulted, always agree */
+        if (len < 2) continue;
+        int32_t pivot[3];
+        for (uint32_t r = 0; r < nc; ++r) pivot[r] = rep[r][off + len / 2];              /* :123 */
+        int32_t i = 0, j = (int32_t)len - 1;
+        for (;; i++, j--) {                                  /* :125 */
+            for (;;) {                                       /* while (A[i] < pivot) i++;  :126 */
+                int c[3] = {0, 0, 0};
+                for (uint32_t r = 0; r < nc; ++r) {
+                    int32_t v = rep[r][off + i];
+                    if (has && f->replica == r && f->site == ev) v ^= (int32_t)(1u << f->bit);
+                    c[r] = v < pivot[r];
+                }
+                if (i >= (int32_t)len - 1) c[0] = c[1] = c[2] = 0;   /* trap guard: a mis-steered scan stops at the partition edge
+                                                                        (on the reference target it would run off the array) */
+                ++ev;
+                if (!qs_vote_cond(q, c)) break;
+                i++;
+            }
+            for (;;) {                                       /* while (A[j] > pivot) j--;  :127 */
+                int c[3] = {0, 0, 0};
+                for (uint32_t r = 0; r < nc; ++r) {
+                    int32_t v = rep[r][off + j];
+                    if (has && f->replica == r && f->site == ev) v ^= (int32_t)(1u << f->bit);
+                    c[r] = v > pivot[r];
+                }
+                if (j <= 0) c[0] = c[1] = c[2] = 0;                   /* trap guard */
+                ++ev;
+                if (!qs_vote_cond(q, c)) break;
+                j--;
+            }
+            q->syncs++;                                      /* if (i >= j) break;  :128 */
+            if (i >= j) break;
+            for (uint32_t r = 0; r < nc; ++r) {              /* :129-131, each replica in its own copy */
+                int32_t t = rep[r][off + i]; rep[r][off + i] = rep[r][off + j]; rep[r][off + j] = t;
+            }
+        }
+        if (i < 1) i = 1;                                    /* progress guard (only reachable through a mis-steered partition) */
+        if (i > (int32_t)len - 1) i = (int32_t)len - 1;
+        /* quick_sort(A, i); quick_sort(A + i, len - i);  -- left first: push right, then left */
+        stack_off[sp] = off + (uint32_t)i; stack_len[sp] = len - (uint32_t)i; ++sp;
+        stack_off[sp] = off; stack_len[sp] = (uint32_t)i; ++sp;
+    }
+}
+
+/* ------------------------------------------------------------------ */
 /* a9-a13: the protected region                                          */
 /* ------------------------------------------------------------------ */
 /* TMR voter, identical shape at all four sites (synchronization.cpp:439-448,
@@ -380,7 +469,39 @@ static void run_replica(const orc_desc* d, uint64_t local, const orc_fault* f, u
 }
 
 int orc_run_range(const orc_desc* d, uint64_t u0, uint64_t u1, orc_stats* st) {
-    if (!d || d->num_clones < 1 || d->num_clones > 3 || d->kernel > ORC_K_GEMM_TF32) return -1;
+    if (!d || d->num_clones < 1 || d->num_clones > 3 || d->kernel > ORC_K_QSORT) return -1;
+    if (d->kernel == ORC_K_QSORT) {
+        const uint32_t L = d->unit_bytes / 4u, nc = d->num_clones;
+        if (L < 1 || L > 1024 || (d->unit_bytes & 3u)) return -1;
+        static __thread int32_t rep[3][1024];
+        for (uint64_t local = u0; local < u1; ++local) {
+            orc_fault f;
+            orc_fault_for_unit(d->plan, d->kernel, nc, d->unit_bytes, d->K, d->unit_base + local, local, &f);
+            if (f.active) st->injected++;
+            qs_ctx q;
+            orc_qsort_unit((const int32_t*)d->in + local * L, L, nc, &f, d->flags, rep, &q);
+            int32_t* out = (int32_t*)d->out + local * L;
+            int disagree = q.disagree;
+            uint64_t errors = q.errors;
+            for (uint32_t e = 0; e < L; ++e) {                  /* SoR exit: one vote per stored element */
+                const int32_t r0 = rep[0][e], r1 = nc > 1 ? rep[1][e] : r0, r2 = nc > 2 ? rep[2][e] : r0;
+                int32_t v = r0;
+                if (nc == 2 && r0 != r1) disagree = 1;
+                if (nc == 3) {
+                    const int c01 = r0 == r1, c02 = r0 == r2;
+                    v = (d->flags & ORC_F_MAJORITY) ? ((r0 & r1) | (r0 & r2) | (r1 & r2)) : (c01 ? r0 : r2);
+                    if (!(c01 && c02)) { disagree = 1; if (d->flags & ORC_F_COUNT_ERRORS) errors++; }
+                }
+                out[e] = v;
+            }
+            if (nc == 3) {
+                st->errors_corrected += errors;
+                if ((d->flags & ORC_F_COUNT_SYNCS) && (d->flags & ORC_F_COUNT_ERRORS)) st->syncs += q.syncs + L;
+            } else if (nc == 2 && disagree) st->dwc_detected++;
+            if (nc > 1 && disagree && d->unit_base + local < st->first_fault_unit) st->first_fault_unit = d->unit_base + local;
+        }
+        return 0;
+    }
     const uint32_t ob = orc_out_bytes_per_unit(d->kernel);
     const uint32_t nv = orc_votes_per_unit(d->kernel);
     const uint32_t es = ob / nv;

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-enum { ORC_K_CRC16 = 0, ORC_K_SHA256 = 1, ORC_K_AES128 = 2, ORC_K_MM_U32 = 3, ORC_K_GEMM_TF32 = 4 };
+enum { ORC_K_CRC16 = 0, ORC_K_SHA256 = 1, ORC_K_AES128 = 2, ORC_K_MM_U32 = 3, ORC_K_GEMM_TF32 = 4, ORC_K_QSORT = 5 };
 enum { ORC_F_COUNT_ERRORS = 1, ORC_F_COUNT_SYNCS = 2, ORC_F_MAJORITY = 0x100 };
 enum { ORC_PLAN_NONE = 0, ORC_PLAN_BERNOULLI = 1, ORC_PLAN_TABLE = 2 };
 enum { ORC_AES_DECRYPT = 1, ORC_AES_KEY_PER_UNIT = 2 };
@@ -62,6 +62,7 @@ void orc_fill_philox(uint32_t* dst, uint64_t n_words, uint64_t word_base, uint32
 uint32_t orc_fault_sites(uint32_t kernel, uint32_t unit_bytes, uint32_t K);
 uint32_t orc_fault_site_bits(uint32_t kernel, uint32_t unit_bytes, uint32_t K, uint32_t site);
 uint32_t orc_out_bytes_per_unit(uint32_t kernel);
+uint32_t orc_out_bytes(uint32_t kernel, uint32_t unit_bytes);   /* QSORT: unit_bytes (the sorted array) */
 uint32_t orc_votes_per_unit(uint32_t kernel);
 /* Decide the fault (if any) of GLOBAL unit `unit` (local index unit - unit_base for TABLE). */
 void orc_fault_for_unit(const orc_plan* plan, uint32_t kernel, uint32_t num_clones, uint32_t unit_bytes,

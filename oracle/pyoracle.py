@@ -14,7 +14,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-K_CRC16, K_SHA256, K_AES128, K_MM_U32, K_GEMM_TF32 = range(5)
+K_CRC16, K_SHA256, K_AES128, K_MM_U32, K_GEMM_TF32, K_QSORT = range(6)
 F_COUNT_ERRORS, F_COUNT_SYNCS, F_MAJORITY = 1, 2, 0x100
 PLAN_NONE, PLAN_BERNOULLI, PLAN_TABLE = 0, 1, 2
 AES_DECRYPT, AES_KEY_PER_UNIT = 1, 2
@@ -142,7 +142,7 @@ def run(kernel, num_clones, inp: np.ndarray, n_units, *, flags=0, mode=0, unit_b
         threads=1):
     """Run the protected region on the CPU oracle.  Returns (out: np.ndarray[uint8], stats: dict)."""
     L = lib()
-    ob = out_bytes_per_unit(kernel)
+    ob = unit_bytes if kernel == K_QSORT else out_bytes_per_unit(kernel)
     out = np.zeros(n_units * ob, dtype=np.uint8)
     d = OrcDesc()
     d.kernel, d.num_clones, d.flags, d.mode = kernel, num_clones, flags, mode

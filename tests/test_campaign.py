@@ -81,6 +81,12 @@ def test_campaigns_reproduce_the_table_shape(rt, oracle, tmp_path):
     assert len(data) == n and set(data[0]) >= {"timestamp", "number", "section", "oldValue", "newValue", "address", "sleepTime",
                                                "cycles", "PC", "name", "result", "cacheInfo"}
     # SHA-256 and AES: TMR never lets a single flip through; unmitigated SDC rate == fraction of flips that matter (all, here)
+    q3, _ = cp.run_campaign(rt, "qsort", "-TMR -countErrors", 2000, seed=5)
+    q2, _ = cp.run_campaign(rt, "qsort", "-DWC", 2000, seed=5)
+    q1, _ = cp.run_campaign(rt, "qsort", "", 2000, seed=5)
+    # quicksort is the workload where most flips are MASKED (a compare operand flip rarely changes the branch): like the
+    # published table, unmitigated still sorts correctly most of the time; TMR never fails; DWC flags a superset of the SDCs
+    assert q3.errors == 0 and q1.errors < 1000 and q1.success > 1000 and q2.errors <= 2 and q2.detected >= q1.errors * 0.5
     for wl in ("sha256", "aes", "mm"):
         t, _ = cp.run_campaign(rt, wl, "-TMR -countErrors", 2000, seed=5)
         assert t.errors == 0

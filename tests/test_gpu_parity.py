@@ -38,7 +38,7 @@ def both(rt, oracle, kernel, nc, inp, n, *, flags=0, mode=0, unit_bytes=0, M=0, 
         gplan = cb.FaultPlan(mode=cb.PLAN_TABLE, table=dev(rt, table))
     elif plan_kw:
         oplan = oracle.make_plan(oracle.PLAN_BERNOULLI, **plan_kw)
-        gplan = cb.FaultPlan(mode=cb.PLAN_BERNOULLI, **plan_kw)
+        gplan = cb.FaultPlan(mode=cb.PLAN_BERNOULLI, **plan_kw)     # seed + (p | threshold)
     o_out, o_st = oracle.run(kernel, nc, inp, n, flags=flags, mode=mode, unit_bytes=unit_bytes, M=M, N=N, K=K, aux=aux,
                              key=key, plan=oplan, unit_base=unit_base)
     g_out, g_st = rt.run(kernel, nc, dev(rt, inp), n, flags=flags, mode=mode, unit_bytes=unit_bytes, M=M, N=N, K=K,
@@ -490,3 +490,24 @@ def test_aes_key_mutation_matches_the_reference(rt, oracle, golden):
     state, key = C.create_string_buffer(r[64:80], 16), C.create_string_buffer(r[0:16], 16)
     L.coast_xmr_aes_enc_dec(state, key, 0)
     assert state.raw == r[32:48] and key.raw == kenc[16 * 300: 16 * 301].tobytes()
+
+
+# ------------------------------------------------------------------------------------------ quicksort
+@pytest.mark.parametrize("nc", [1, 2, 3])
+@pytest.mark.parametrize("L,n", [(580, 64), (1, 5), (2, 33), (17, 100), (1024, 21)])
+def test_quicksort_branch_votes_match_oracle(rt, oracle, nc, L, n):
+    a = oracle.fill_philox(n * L, 0, 9 + L).view(np.int32)
+    g, _ = both(rt, oracle, oracle.K_QSORT, nc, a, n, unit_bytes=4 * L, flags=3)
+    assert (g.view(np.int32).reshape(n, L) == np.sort(a.reshape(n, L), axis=1)).all()
+    both(rt, oracle, oracle.K_QSORT, nc, a, n, unit_bytes=4 * L, flags=3, plan_kw=dict(seed=L, threshold=0xFFFFFFFF))
+    both(rt, oracle, oracle.K_QSORT, nc, a, n, unit_bytes=4 * L, flags=3 | 0x100, plan_kw=dict(seed=L + 1, p=0.5))
+
+
+def test_quicksort_already_sorted_and_duplicates(rt, oracle):
+    L, n = 580, 30
+    a = np.sort(oracle.fill_philox(n * L, 0, 3).view(np.int32).reshape(n, L), axis=1)      # sorted input (the reference re-sorts sorted arrays)
+    a[10:20] = a[10:20, ::-1]                                                               # reverse-sorted
+    a[20:] = (a[20:] & 7)                                                                   # many duplicates
+    a = np.ascontiguousarray(a).ravel()
+    for nc in (2, 3):
+        both(rt, oracle, oracle.K_QSORT, nc, a, n, unit_bytes=4 * L, flags=3, plan_kw=dict(seed=77, threshold=0xFFFFFFFF))

@@ -103,3 +103,29 @@ def test_mt_matches_single_thread(oracle):
     a, sa = oracle.run(oracle.K_SHA256, 3, m, n, unit_bytes=64, plan=plan, flags=3)
     b, sb = oracle.run(oracle.K_SHA256, 3, m, n, unit_bytes=64, plan=plan, flags=3, threads=4)
     assert (a == b).all() and sa == sb
+
+
+def test_quicksort_branch_sync_points(oracle):
+    """quick_sort (tests/quicksort/quicksort.c:121-136): the data-dependent branch conditions are the sync points"""
+    L, n = 580, 40                                           # array_elements = 580 (quicksort.c:83)
+    a = oracle.fill_philox(n * L, 0, 9).view(np.int32)
+    want = np.sort(a.reshape(n, L), axis=1)
+    for nc in (1, 2, 3):
+        out, st = oracle.run(oracle.K_QSORT, nc, a, n, unit_bytes=4 * L, flags=3)
+        assert (out.view(np.int32).reshape(n, L) == want).all()
+        assert st["errors_corrected"] == 0 and st["dwc_detected"] == 0
+    assert st["syncs"] > n * L * 8                            # many more sync points than SoR-exit stores
+    plan = oracle.make_plan(oracle.PLAN_BERNOULLI, seed=3, threshold=0xFFFFFFFF)
+    out3, st3 = oracle.run(oracle.K_QSORT, 3, a, n, unit_bytes=4 * L, flags=3, plan=plan)
+    assert (out3.view(np.int32).reshape(n, L) == want).all()  # every voted branch follows the majority -> always sorted
+    out2, st2 = oracle.run(oracle.K_QSORT, 2, a, n, unit_bytes=4 * L, plan=plan)
+    out1, _ = oracle.run(oracle.K_QSORT, 1, a, n, unit_bytes=4 * L, plan=plan)
+    wrong1 = (out1.view(np.int32).reshape(n, L) != want).any(axis=1).sum()
+    assert st3["injected"] == n and 0 < st3["errors_corrected"] and st2["dwc_detected"] > 0
+    assert wrong1 <= st2["dwc_detected"] + 2                  # what corrupts the unprotected sort is what DWC flags (replica choice aside)
+    # an input-copy flip (site >= 32L) in one TMR replica: exactly one element vote disagrees at the SoR exit,
+    # plus the branch votes that element took part in
+    tab = np.zeros(n, dtype=np.uint32)
+    tab[5] = oracle.fault_entry(1, 32 * L + 17, 30)
+    o, s = oracle.run(oracle.K_QSORT, 3, a, n, unit_bytes=4 * L, flags=3, plan=oracle.make_plan(oracle.PLAN_TABLE, table=tab))
+    assert (o.view(np.int32).reshape(n, L) == want).all() and s["injected"] == 1 and s["errors_corrected"] >= 1 and s["first_fault_unit"] == 5

@@ -17,11 +17,11 @@ rows = []
 t0 = time.time()
 for mode, name in (("", "Unmitigated"), ("-DWC", "-DWC"), ("-TMR", "-TMR"), ("-TMR -countErrors", "-TMR -countErrors")):
     cells = []
-    for wl in ("mm", "crc16", "sha256", "aes"):
+    for wl in ("mm", "crc16", "qsort", "sha256", "aes"):
         s, _ = cp.run_campaign(rt, wl, mode, n, seed=7)
         cells.append(s.row())
     rows.append((name, cells))
-print(f"| Config | MxM (exact int) | CRC16 | SHA-256 | AES-128 |  ({n} single-bit flips of live replica values per cell, {time.time() - t0:.1f} s total)")
-print("|---|---|---|---|---|")
+print(f"| Config | MxM (exact int) | CRC16 | QS (580 ints) | SHA-256 | AES-128 |  ({n} single-bit flips of live replica values per cell, {time.time() - t0:.1f} s total)")
+print("|---|---|---|---|---|---|")
 for name, cells in rows:
     print(f"| {name} | " + " | ".join(cells) + " |")
