@@ -17,17 +17,17 @@ constexpr int QS_MAX = 1024;
 
 template <int NC>
 struct QsVote {
-    uint32_t gmask; int base; bool majority, count, leader;
-    uint32_t errors = 0, syncs = 0; bool disagree = false;
+    uint32_t gmask; int base; bool majority, leader;
+    uint32_t ndis = 0, syncs = 0;                               // disagreeing branch votes, executed sync points
     // all NC lanes of the group call this together; every lane gets the same voted condition
     __device__ __forceinline__ bool operator()(bool c) {
         syncs++;
         if (NC == 1) return c;
         const int c0 = __shfl_sync(gmask, (int)c, base), c1 = __shfl_sync(gmask, (int)c, base + 1);
-        if (NC == 2) { if (c0 != c1) disagree = true; return c0; }
+        if (NC == 2) { if (c0 != c1 && leader) ndis++; return c0; }
         const int c2 = __shfl_sync(gmask, (int)c, base + 2);
         const bool c01 = c0 == c1, c02 = c0 == c2;
-        if (!(c01 && c02)) { disagree = true; if (count && leader) errors++; }
+        if (!(c01 && c02) && leader) ndis++;
         return majority ? ((c0 & c1) | (c0 & c2) | (c1 & c2)) : (c01 ? c0 : c2);
     }
 };
@@ -61,7 +61,7 @@ __device__ __forceinline__ void qsort_body(const xmr_args& a) {
                 }
                 if (fsite >= 32u * L && fsite != 0xFFFFFFFFu) A[fsite - 32u * L] ^= (int32_t)fmask;
             }
-            QsVote<NC> vote{gmask, base, (a.flags & COAST_F_MAJORITY_D) != 0, (a.flags & COAST_F_COUNT_ERRORS_D) != 0, r == 0};
+            QsVote<NC> vote{gmask, base, (a.flags & COAST_F_MAJORITY_D) != 0, r == 0};
             uint32_t ev = 0;
             int sp = 0;
             stack[sp++] = L;                                    // off = 0
@@ -122,13 +122,13 @@ __device__ __forceinline__ void qsort_body(const xmr_args& a) {
                 const unsigned long long gunit = a.unit_base + local;
                 if (NC == 3) {
                     if (a.flags & COAST_F_COUNT_ERRORS_D) {
-                        tally.errors += bad + vote.errors;
+                        tally.errors += bad + vote.ndis;
                         if (a.flags & COAST_F_COUNT_SYNCS_D) tally.syncs += vote.syncs + L;
                     }
                 } else if (NC == 2) {
-                    tally.dwc += (bad || vote.disagree) ? 1u : 0u;
+                    tally.dwc += (bad || vote.ndis) ? 1u : 0u;
                 }
-                const uint32_t dis = bad + vote.errors + (vote.disagree ? 1u : 0u);
+                const uint32_t dis = bad + vote.ndis;
                 if (NC > 1 && dis && gunit < tally.first) tally.first = gunit;
                 if (tally.status) tally.status[local] = (unsigned char)(NC > 1 ? (dis > 255u ? 255u : dis) : 0u);
             }
