@@ -46,6 +46,7 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.period = 0.002
         self._stop = threading.Event()
         self._th = None
         try:
@@ -70,9 +71,13 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
-    def start(self):
+    def start(self, period=0.002):
+        """period: NVML polling interval.  2 ms inside the device-timed region (GPU-bound, launches are cheap); 25 ms inside
+        the host-call region, where NVML queries contend with the copy/launch submissions on the driver lock and were
+        measured to slow the pipeline by up to 1.8x."""
+        self.period = period
         if self.nv:
             self._stop.clear()
             self._th = threading.Thread(target=self._run, daemon=True)
@@ -290,7 +295,9 @@ def run_ours(args):
         descs = [rt.make_desc(W["kernel"], W["nc"], ins[i], outs[i], n, flags=W["flags"], unit_bytes=W["unit_bytes"], key=W.get("key"),
                               unit_base=unit_base, plan=plan) for i in range(nsets)]
         total_out_bytes = (W["n"] if W.get("strong") else world * n) * out_b
-    d_stats = torch.zeros(5, dtype=torch.int64, device=dev)
+    NSTAT = 8                                              # counter-exchange buffers in flight
+    d_stats = [torch.zeros(5, dtype=torch.int64, device=dev) for _ in range(NSTAT)]
+    pending = [None] * NSTAT
     launches = 0
 
     def step(i):
@@ -299,10 +306,23 @@ def run_ours(args):
             rt.launch(descs[i % nsets])                    # ONE kernel: replicas + voter + counters (+ injector)
             launches += 1
         if dist is not None:
-            rt.stats_snapshot(d_stats)                     # D2D copy of the counters
-            dist.all_reduce(d_stats[:4])                   # the only exchange step: 32 bytes over NVLink
+            # the only exchange step: 32 bytes of counters over NVLink.  Issued asynchronously on NCCL's stream (it waits for
+            # the snapshot, the compute stream does not wait for it), so it overlaps the next step's kernel; every exchange
+            # is completed inside the timed region (drain() before the stop event).
+            k = i % NSTAT
+            if pending[k] is not None:
+                pending[k].wait()
+            rt.stats_snapshot(d_stats[k])                  # D2D copy of the counters
+            pending[k] = dist.all_reduce(d_stats[k][:4], async_op=True)
+
+    def drain():
+        for k in range(NSTAT):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
 
     def fence():
+        drain()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
@@ -317,6 +337,7 @@ def run_ours(args):
     e0.record()
     for i in range(args.steps):
         step(i)
+    drain()                                                # all counter exchanges complete before the clock stops
     e1.record()
     fence()
     sampler.stop()
@@ -360,7 +381,7 @@ def run_ours(args):
     for _ in range(min(3, args.warmup)):
         call()
     fence()
-    sampler.start()
+    sampler.start(period=0.025)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         call()
