@@ -511,3 +511,24 @@ def test_quicksort_already_sorted_and_duplicates(rt, oracle):
     a = np.ascontiguousarray(a).ravel()
     for nc in (2, 3):
         both(rt, oracle, oracle.K_QSORT, nc, a, n, unit_bytes=4 * L, flags=3, plan_kw=dict(seed=77, threshold=0xFFFFFFFF))
+
+
+def test_dwc_default_handler_aborts_like_the_reference(built_lib):
+    """-DWC mismatch with no user FAULT_DETECTED_DWC: the synthesised handler calls abort() (synchronization.cpp:1251-1266),
+    here after kernel completion.  Run in a child process and expect SIGABRT."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import torch, coast_b200 as cb\n"
+        "rt = cb.Runtime(0)\n"
+        "d = torch.zeros(4096 * 16, dtype=torch.uint8, device='cuda')\n"
+        "o = torch.empty_like(d)\n"
+        "desc = rt.make_desc(cb.K_AES128, 2, d, o, 4096, key=bytes(16), plan=cb.FaultPlan(mode=cb.PLAN_BERNOULLI, seed=1, p=0.5))\n"
+        "rt.launch(desc)\n"
+        "print('before sync', flush=True)\n"
+        "rt.sync(abort_on_dwc=True)\n"
+        "print('NOT REACHED', flush=True)\n" % __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
+    assert res.returncode == -6, (res.returncode, res.stdout, res.stderr)          # SIGABRT
+    assert "before sync" in res.stdout and "NOT REACHED" not in res.stdout and "FAULT_DETECTED_DWC" in res.stderr
