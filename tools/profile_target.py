@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--kernel", choices=["sha256", "aes", "crc16", "mm", "gemm"], default="sha256")
+    ap.add_argument("--kernel", choices=["sha256", "aes", "crc16", "mm", "gemm", "qsort"], default="sha256")
     ap.add_argument("--nc", type=int, default=3)
     ap.add_argument("--log2n", type=int, default=20)
     ap.add_argument("--iters", type=int, default=3)
@@ -44,6 +44,12 @@ def main():
         out = torch.empty(n * 16, dtype=torch.uint8, device="cuda")
         d = rt.make_desc(cb.K_AES128, a.nc, d_in, out, n, flags=flags, key=bytes(16), plan=plan)
         alg = n * 32
+    elif a.kernel == "qsort":
+        L = 580
+        d_in = torch.empty(n * L, dtype=torch.int32, device="cuda"); rt.fill_philox(d_in, 9)
+        out = torch.empty(n * L, dtype=torch.int32, device="cuda")
+        d = rt.make_desc(cb.K_QSORT, a.nc, d_in, out, n, flags=flags, unit_bytes=4 * L, plan=plan)
+        alg = n * L * 8
     elif a.kernel == "gemm":
         s = a.side
         A = torch.rand(s * s, dtype=torch.float32, device="cuda") * 2 - 1
