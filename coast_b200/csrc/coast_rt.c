@@ -462,8 +462,11 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
     case COAST_K_CRC16:
         if (d->unit_bytes < 1 || d->unit_bytes > 255) return fail(COAST_ERR_BAD_ARG, "crc16 length is an unsigned char (1..255)");
         if (d->unit_bytes == 64 && aligned16 && d->n_units < 0x7FFFFF00ull) {
-            tma = 1; tile_rows = XMR_WARPS * upw; row_bytes = 64; swz = CU_TENSOR_MAP_SWIZZLE_64B;
-            smem = ring_smem(tile_rows, row_bytes);
+            /* table kernel: 1024-thread CTAs (768 unprotected), shared window = [.., 0x10000) unused | 64 KiB byte-step
+             * table | tile ring at 0x20000 (CrcGeom in xmr_crc16.cuh) */
+            tma = 1; block = nc == 1 ? 768 : 1024; tile_rows = (unsigned)(block / 32) * upw; row_bytes = 64;
+            swz = CU_TENSOR_MAP_SWIZZLE_64B;
+            smem = 0x20000u + ring_smem(tile_rows, row_bytes);
             snprintf(name, sizeof name, "xmr_crc16_b64_nc%u_inj%d", nc, inj);
         } else {
             snprintf(name, sizeof name, "xmr_crc16_gen_nc%u_inj%d", nc, inj);
