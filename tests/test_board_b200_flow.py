@@ -73,3 +73,55 @@ def test_unchanged_reference_tests_run_on_the_gpu(tdir, target, extra, entry, re
     res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert res.returncode == rc, res.stdout + res.stderr          # unittest.py:76-78: non-zero exit = fail
     assert re.search(regex, res.stdout), res.stdout + res.stderr   # unittest.py:80-86 regex on stdout
+
+
+# unittest/cfg/full.yml:17-36 -- the OPT_PASSES sweep unittest.py runs over every benchmark (by rebuilding with
+# `make exe OPT_PASSES=...`, unittest.py:61).  The sources are not on the GPU box, so the built binaries are re-protected
+# through COAST_OPT_PASSES_OVERRIDE (coast_glue.c) instead.
+FULL_YML_SWEEP = [
+    "", "-DWC", "-TMR", "-TMR -countErrors",
+    "-DWC -noMemReplication", "-TMR -noMemReplication",
+    "-DWC -noLoadSync", "-TMR -noLoadSync",
+    "-DWC -noStoreDataSync", "-TMR -noStoreDataSync",
+    "-DWC -noStoreAddrSync", "-TMR -noStoreAddrSync",
+    "-DWC -noMemReplication -noLoadSync", "-TMR -noMemReplication -noLoadSync",
+    "-DWC -noMemReplication -noStoreDataSync", "-TMR -noMemReplication -noStoreDataSync",
+    "-DWC -noMemReplication -noStoreAddrSync", "-TMR -noMemReplication -noStoreAddrSync",
+]
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/unittest/cfg/full.yml"), reason="reference checkout absent (GPU box)")
+def test_sweep_list_is_the_reference_one():
+    import yaml
+    cfg = yaml.safe_load(open("/root/reference/unittest/cfg/full.yml"))
+    assert cfg["OPT_PASSES"] == FULL_YML_SWEEP
+
+
+def test_every_sweep_entry_parses_without_an_ignored_token(built_lib):
+    import ctypes as C
+    lib = C.CDLL(built_lib)
+    for passes in FULL_YML_SWEEP:
+        nc, fl = C.c_uint32(), C.c_uint32()
+        code = ("import ctypes as C,sys; l=C.CDLL(sys.argv[1]); n=C.c_uint32(); f=C.c_uint32(); "
+                "sys.exit(l.coast_parse_opt_passes(sys.argv[2].encode(), C.byref(n), C.byref(f)) * 0 + n.value)")
+        res = subprocess.run([os.sys.executable, "-c", code, built_lib, passes], capture_output=True, text=True)
+        assert "ignored" not in res.stderr and "not emulated" not in res.stderr, (passes, res.stderr)
+        assert res.returncode == (3 if "-TMR" in passes else 2 if "-DWC" in passes else 1), passes
+        assert lib.coast_parse_opt_passes(passes.encode(), C.byref(nc), C.byref(fl)) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("target,regex", [("matrixMultiply", r"Number of errors: 0"), ("crc16", r"result: 5ba3"),
+                                          ("aes", r"Number of errors: 0")])
+def test_unittest_full_yml_sweep_on_the_gpu(target, regex):
+    """unittest.py:61-86 over cfg/full.yml: every benchmark x every OPT_PASSES must exit 0 and match its regex"""
+    exe = os.path.join(OUT, target, target + ".out")
+    if not os.path.exists(exe):
+        pytest.skip("binary was not built on the CPU box (needs the reference checkout)")
+    for passes in FULL_YML_SWEEP:
+        env = dict(os.environ, COAST_OPT_PASSES_OVERRIDE=passes + " -verbose")
+        res = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env)
+        assert res.returncode == 0, (passes, res.stdout + res.stderr)
+        assert re.search(regex, res.stdout), (passes, res.stdout + res.stderr)
+        want = "_nc3_" if "-TMR" in passes else "_nc2_" if "-DWC" in passes else "_nc1_"
+        assert want in res.stderr, (passes, res.stderr)      # -verbose names the kernel actually launched
