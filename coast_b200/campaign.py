@@ -24,7 +24,8 @@ import numpy as np
 
 from . import runtime as R
 
-WORKLOADS = {"crc16": R.K_CRC16, "sha256": R.K_SHA256, "aes": R.K_AES128, "mm": R.K_MM_U32, "qsort": R.K_QSORT}
+WORKLOADS = {"crc16": R.K_CRC16, "sha256": R.K_SHA256, "aes": R.K_AES128, "mm": R.K_MM_U32, "qsort": R.K_QSORT,
+             "chsha": R.K_CHSTONE_SHA}
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -82,6 +83,13 @@ def site_name(kernel, unit_bytes, site):
     if kernel == R.K_QSORT:
         L = unit_bytes // 4
         return f"qsort.cmp_operand@event{site}" if site < 32 * L else f"qsort.array[{site - 32 * L}]"
+    if kernel == R.K_CHSTONE_SHA:
+        blk, s = divmod(site, 421)
+        if s < 16:
+            return f"chsha.blk{blk}.W[{s}]"
+        if s < 416:
+            return f"chsha.blk{blk}.round{(s - 16) // 5}.{'ABCDE'[(s - 16) % 5]}"
+        return f"chsha.blk{blk}.sha_info_digest[{s - 416}]"
     return f"site{site}"
 
 
@@ -158,7 +166,7 @@ def run_campaign(rt, workload: str, opt_passes: str, n_injections: int, seed: in
         inp, kw = A, dict(M=side, N=side, K=side, aux=B)
         ub = 0
     else:
-        ub = {R.K_CRC16: 64, R.K_SHA256: 64, R.K_AES128: 16, R.K_QSORT: 4 * 580}[kernel] if unit_bytes is None else unit_bytes
+        ub = {R.K_CRC16: 64, R.K_SHA256: 64, R.K_AES128: 16, R.K_QSORT: 4 * 580, R.K_CHSTONE_SHA: 1024}[kernel] if unit_bytes is None else unit_bytes
         nbytes = (n * ub + 3) // 4 * 4
         inp = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         rt.fill_philox(inp, data_seed)
@@ -184,7 +192,7 @@ def run_campaign(rt, workload: str, opt_passes: str, n_injections: int, seed: in
     records = []
     for u in range(n_injections):
         name = site_name(kernel, ub, site[u])
-        section = "memory" if (".data[" in name or ".m[" in name or "state_in" in name or ".array[" in name) else "registers"
+        section = "memory" if (".data[" in name or ".m[" in name or ".W[" in name or "state_in" in name or ".array[" in name) else "registers"
         if nc == 2 and stat[u]:
             res = abort_result("FAULT_DETECTED_DWC")
             summ.detected += 1

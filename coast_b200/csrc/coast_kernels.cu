@@ -12,3 +12,4 @@
 #include "xmr_gemm_tf32.cuh"
 #include "xmr_mm_tc.cuh"
 #include "xmr_qsort.cuh"
+#include "xmr_chstone_sha.cuh"

@@ -274,6 +274,7 @@ uint32_t coast_fault_sites(uint32_t kernel, uint32_t unit_bytes, uint32_t K) {
     case COAST_K_MM_U32:    return K;
     case COAST_K_GEMM_TF32: return 1u;
     case COAST_K_QSORT:     return 33u * (unit_bytes / 4u);
+    case COAST_K_CHSTONE_SHA: return 421u * (unit_bytes / 64u + 1u);
     default:                return 0u;
     }
 }
@@ -284,11 +285,11 @@ uint32_t coast_fault_site_bits(uint32_t kernel, uint32_t unit_bytes, uint32_t K,
     return 32u;
 }
 uint32_t coast_out_bytes_per_unit(uint32_t kernel) {
-    static const uint32_t ob[COAST_K_COUNT_] = { 2, 32, 16, 4, 4, 0 };
+    static const uint32_t ob[COAST_K_COUNT_] = { 2, 32, 16, 4, 4, 0, 20 };
     return kernel < COAST_K_COUNT_ ? ob[kernel] : 0;
 }
 uint32_t coast_votes_per_unit(uint32_t kernel) {
-    static const uint32_t nv[COAST_K_COUNT_] = { 1, 32, 16, 1, 1, 0 };
+    static const uint32_t nv[COAST_K_COUNT_] = { 1, 32, 16, 1, 1, 0, 5 };
     return kernel < COAST_K_COUNT_ ? nv[kernel] : 0;
 }
 uint32_t coast_out_bytes(uint32_t kernel, uint32_t unit_bytes) {
@@ -296,7 +297,7 @@ uint32_t coast_out_bytes(uint32_t kernel, uint32_t unit_bytes) {
 }
 static uint64_t in_bytes_per_unit(const coast_launch_desc* d) {
     switch (d->kernel) {
-    case COAST_K_CRC16: case COAST_K_SHA256: case COAST_K_QSORT: return d->unit_bytes;
+    case COAST_K_CRC16: case COAST_K_SHA256: case COAST_K_QSORT: case COAST_K_CHSTONE_SHA: return d->unit_bytes;
     case COAST_K_AES128: return 16;
     default: return 0;
     }
@@ -510,6 +511,12 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
         block = 128;
         snprintf(name, sizeof name, "xmr_qsort_nc%u_inj%d", nc, inj);
         break;
+    case COAST_K_CHSTONE_SHA:
+        if (d->unit_bytes < 64u || (d->unit_bytes & 63u) || d->unit_bytes >= (1u << 29))
+            return fail(COAST_ERR_BAD_ARG, "CHStone sha streams are whole 64-byte blocks, 64 <= unit_bytes < 2^29 (got %u)", d->unit_bytes);
+        if (!aligned16 || (((uintptr_t)d->d_out) & 3u)) return fail(COAST_ERR_BAD_ARG, "CHStone sha: d_in must be 16-byte and d_out 4-byte aligned");
+        snprintf(name, sizeof name, "xmr_chsha_nc%u_inj%d", nc, inj);
+        break;
     case COAST_K_GEMM_TF32:
         if (!d->d_aux || !d->M || !d->N || !d->K) return fail(COAST_ERR_BAD_ARG, "GEMM needs A (d_in), B (d_aux) and M,N,K");
         if (d->n_units != (uint64_t)d->M * d->N) return fail(COAST_ERR_BAD_ARG, "GEMM: n_units must be M*N");
@@ -722,6 +729,27 @@ void coast_xmr_aes_enc_dec(unsigned char* state, unsigned char* key, unsigned ch
     d.kernel = COAST_K_AES128; d.n_units = 1; d.d_in = state; d.d_out = state; d.d_aux = key;
     d.mode = (dir ? COAST_AES_DECRYPT : 0) | COAST_AES_KEY_PER_UNIT | COAST_AES_KEY_WRITEBACK;
     entry_run(&d);
+}
+void coast_xmr_chstone_sha_stream(const unsigned char* indata, const int* in_i, int vsize, int block_size, uint32_t* digest) {
+    /* sha_stream (sha.c:182-193) feeds chunk j = indata[j][0 .. in_i[j]) to sha_update; with whole-block chunks that is the
+     * hash of the concatenation, which is what one unit of the kernel computes */
+    size_t total = 0;
+    for (int j = 0; j < vsize; ++j) {
+        if (in_i[j] < 0 || in_i[j] > block_size || (in_i[j] & 63)) {
+            fprintf(stderr, "coast_rt: sha_stream chunk %d has %d bytes; only whole 64-byte blocks are supported\n", j, in_i[j]);
+            abort();
+        }
+        total += (size_t)in_i[j];
+    }
+    unsigned char* cat = (unsigned char*)malloc(total ? total : 1);
+    if (!cat) abort();
+    size_t off = 0;
+    for (int j = 0; j < vsize; ++j) { memcpy(cat + off, indata + (size_t)j * (size_t)block_size, (size_t)in_i[j]); off += (size_t)in_i[j]; }
+    coast_launch_desc d; memset(&d, 0, sizeof d);
+    entry_mode(&d.num_clones, &d.flags);
+    d.kernel = COAST_K_CHSTONE_SHA; d.n_units = 1; d.unit_bytes = (uint32_t)total; d.d_in = cat; d.d_out = digest;
+    entry_run(&d);
+    free(cat);
 }
 void coast_xmr_matrix_multiply_u32(const uint32_t* f, const uint32_t* s, uint32_t* r, int side) {
     coast_launch_desc d; memset(&d, 0, sizeof d);

@@ -62,7 +62,9 @@ typedef enum coast_kernel_id {
     COAST_K_GEMM_TF32 = 4, /* BASELINE config 4: fp32 in/out, tcgen05 kind::tf32 */
     COAST_K_QSORT     = 5, /* tests/quicksort/quicksort.c:121-136: data-dependent branches -> the
                               branch conditions are the sync points, voted inside the loops */
-    COAST_K_COUNT_    = 6
+    COAST_K_CHSTONE_SHA = 6, /* tests/chstone/sha/sha.c:93-193: the CHStone `sha` benchmark -- one unit
+                                is one STREAM (a serial chain of unit_bytes/64 + 1 compressions), five u32 votes */
+    COAST_K_COUNT_    = 7
 } coast_kernel_id;
 
 /* numClones of dataflowProtection::run: 3 = -TMR, 2 = -DWC, 1 = unprotected
@@ -141,6 +143,8 @@ typedef struct coast_fault_plan {
  *            K%16 == 0, a plain kernel otherwise (e.g. the 9 x 9 tests).  COAST_MM_PATH=tc|tiled|naive overrides.
  *   GEMM_TF32 same with float.
  *   QSORT    in : n_units x unit_bytes, arrays of L = unit_bytes/4 int32 (L <= 1024)   out: the sorted arrays
+ *   CHSTONE_SHA in : n_units x unit_bytes stream bytes (unit_bytes a multiple of 64, 64 <= unit_bytes < 2^29)
+ *            out: n_units x 5 uint32 = sha_info_digest[5] (sha.h:38)
  */
 #define COAST_AES_DECRYPT       0x1u
 #define COAST_AES_KEY_PER_UNIT  0x2u
@@ -252,6 +256,9 @@ void coast_xmr_sha256_hash(unsigned char ctx_data[], uint32_t ctx_bitlen[], uint
                            unsigned char data[], uint32_t len, unsigned char hash[]);   /* sha256_common_tmr.c:101 */
 void coast_xmr_aes_enc_dec(unsigned char* state, unsigned char* key, unsigned char dir); /* TI_aes_128.c:107 */
 void coast_xmr_matrix_multiply_u32(const uint32_t* f, const uint32_t* s, uint32_t* r, int side); /* mm_common_tmr.c:3 */
+/* chstone/sha/sha.c:182-193 sha_stream(): hashes the vsize chunks indata[j][0 .. in_i[j]) (rows block_size bytes apart)
+ * into digest[5].  The benchmark's globals are passed in by the generated glue; chunks must be multiples of 64 bytes. */
+void coast_xmr_chstone_sha_stream(const unsigned char* indata, const int* in_i, int vsize, int block_size, uint32_t* digest);
 
 #ifdef __cplusplus
 }

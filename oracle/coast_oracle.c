@@ -50,6 +50,7 @@ void orc_fill_philox(uint32_t* dst, uint64_t n_words, uint64_t word_base, uint32
 /*  one single-bit flip `val ^ (1 << bit)` per run; a run = one unit)   */
 /* ------------------------------------------------------------------ */
 #define SHA_SITES_PER_BLOCK 536u /* 16 m[] + 64*8 working vars + 8 ctx_state */
+#define CHS_SITES_PER_BLOCK 421u /* CHStone sha: 16 W[] + 80*5 working vars + 5 sha_info_digest */
 
 static uint32_t sha_blocks(uint32_t len) { return (len + 8u) / 64u + 1u; }
 
@@ -61,6 +62,7 @@ uint32_t orc_fault_sites(uint32_t kernel, uint32_t unit_bytes, uint32_t K) {
     case ORC_K_MM_U32:    return K;
     case ORC_K_GEMM_TF32: return 1u;
     case ORC_K_QSORT:     return 33u * (unit_bytes / 4u);   /* 32*L dynamic compare events + L input-copy elements */
+    case ORC_K_CHSTONE_SHA: return CHS_SITES_PER_BLOCK * (unit_bytes / 64u + 1u);
     default:              return 0u;
     }
 }
@@ -77,13 +79,14 @@ uint32_t orc_fault_site_bits(uint32_t kernel, uint32_t unit_bytes, uint32_t K, u
 uint32_t orc_out_bytes_per_unit(uint32_t kernel) {
     switch (kernel) {
     case ORC_K_CRC16: return 2; case ORC_K_SHA256: return 32; case ORC_K_AES128: return 16;
-    case ORC_K_MM_U32: case ORC_K_GEMM_TF32: return 4; default: return 0;
+    case ORC_K_MM_U32: case ORC_K_GEMM_TF32: return 4; case ORC_K_CHSTONE_SHA: return 20; default: return 0;
     }
 }
 
 /* One vote per output element OF THE C TYPE THE REFERENCE STORES:
  * u16 crc (crc16.c:30), u8 digest byte (sha256_common_tmr.c:169-178),
- * u8 state byte (TI_aes_128.c:226-229), mm_t element (mm_common_tmr.c:16). */
+ * u8 state byte (TI_aes_128.c:226-229), mm_t element (mm_common_tmr.c:16),
+ * LONG sha_info_digest word (chstone/sha/sha.h:38, compared in sha_driver.c:59). */
 uint32_t orc_out_bytes(uint32_t kernel, uint32_t unit_bytes) {
     return kernel == ORC_K_QSORT ? unit_bytes : orc_out_bytes_per_unit(kernel);
 }
@@ -91,7 +94,7 @@ uint32_t orc_out_bytes(uint32_t kernel, uint32_t unit_bytes) {
 uint32_t orc_votes_per_unit(uint32_t kernel) {
     switch (kernel) {
     case ORC_K_CRC16: return 1; case ORC_K_SHA256: return 32; case ORC_K_AES128: return 16;
-    case ORC_K_MM_U32: case ORC_K_GEMM_TF32: return 1; default: return 0;
+    case ORC_K_MM_U32: case ORC_K_GEMM_TF32: return 1; case ORC_K_CHSTONE_SHA: return 5; default: return 0;
     }
 }
 
@@ -212,6 +215,59 @@ void orc_sha256(const uint8_t* data, uint32_t len, uint8_t digest[32], const orc
     sha_compress(st, buf, blk++, f);                        /* :164 */
     for (int w = 0; w < 8; ++w)                             /* :169-178 big-endian digest bytes */
         for (int i = 0; i < 4; ++i) digest[4 * w + i] = (uint8_t)(st[w] >> (24 - 8 * i));
+}
+
+/* ------------------------------------------------------------------ */
+/* 8f-4: CHStone sha  tests/chstone/sha/sha.c                            */
+/* The CHStone variant: no rotate in the W expansion (USE_MODIFIED_SHA is */
+/* not defined, :101), LITTLE-endian word load (its own memcpy, :71-90),  */
+/* and a final block indexed in WORDS by a BYTE count (:167-168).         */
+/* A unit is one stream of `len` bytes, len a multiple of 64 below 2^29:  */
+/* sha_init; sha_update over whole 64-byte blocks (:149-154; the trailing */
+/* memcpy :155 copies nothing); sha_final with count == 0, i.e.           */
+/* data[0] = 0x80 (:168), data[1..13] = 0 (its own memset, :174 -> :55-69 */
+/* zeroes (56-1)/4 = 13 words after skipping 1), data[14] = hi = 0,       */
+/* data[15] = lo = 8*len (:176-177).  sha_stream (:182-193) over chunks   */
+/* in_i[j] that are multiples of 64 is the same thing on the concatenation*/
+/* ------------------------------------------------------------------ */
+static inline uint32_t rotl32(uint32_t v, unsigned n) { return (v << n) | (v >> (32u - n)); }
+
+static void chs_transform(uint32_t dig[5], const uint32_t data[16], uint32_t blk, const orc_fault* f) {
+    uint32_t W[80], v[5];
+    int has = f && f->active && (f->site / CHS_SITES_PER_BLOCK) == blk;
+    uint32_t s = has ? f->site % CHS_SITES_PER_BLOCK : 0xFFFFFFFFu;
+    uint32_t mask = has ? (1u << f->bit) : 0u;
+    for (int i = 0; i < 16; ++i) W[i] = data[i];                               /* :97-99 */
+    if (s < 16u) W[s] ^= mask;
+    for (int i = 16; i < 80; ++i) W[i] = W[i - 3] ^ W[i - 8] ^ W[i - 14] ^ W[i - 16];   /* :100-102 */
+    for (int i = 0; i < 5; ++i) v[i] = dig[i];                                 /* :103-107 */
+    for (uint32_t t = 0; t < 80; ++t) {                                        /* :109-120, FUNC :47-53 */
+        if (s >= 16u && s < 416u && (s - 16u) / 5u == t) v[(s - 16u) % 5u] ^= mask;
+        uint32_t A = v[0], B = v[1], C = v[2], D = v[3], E = v[4], fn, k;
+        if (t < 20)      { fn = (B & C) | (~B & D);          k = 0x5a827999u; }   /* f1 :30 */
+        else if (t < 40) { fn = B ^ C ^ D;                   k = 0x6ed9eba1u; }   /* f2 :31 */
+        else if (t < 60) { fn = (B & C) | (B & D) | (C & D); k = 0x8f1bbcdcu; }   /* f3 :32 */
+        else             { fn = B ^ C ^ D;                   k = 0xca62c1d6u; }   /* f4 :33 */
+        uint32_t temp = rotl32(A, 5) + fn + E + W[t] + k;
+        v[4] = D; v[3] = C; v[2] = rotl32(B, 30); v[1] = A; v[0] = temp;
+    }
+    for (int i = 0; i < 5; ++i) dig[i] += v[i];                                /* :122-126 */
+    if (s >= 416u && s < 421u) dig[s - 416u] ^= mask;
+}
+
+void orc_chstone_sha(const uint8_t* data, uint32_t len, uint32_t digest[5], const orc_fault* f) {
+    uint32_t dig[5] = { 0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u, 0xc3d2e1f0u };   /* :132-136 */
+    uint32_t w[16], blk = 0;
+    for (uint32_t off = 0; off + 64u <= len; off += 64u) {                     /* :149-154 */
+        for (int i = 0; i < 16; ++i)                                           /* :78-89 little-endian pack */
+            w[i] = (uint32_t)data[off + 4 * i] | ((uint32_t)data[off + 4 * i + 1] << 8) |
+                   ((uint32_t)data[off + 4 * i + 2] << 16) | ((uint32_t)data[off + 4 * i + 3] << 24);
+        chs_transform(dig, w, blk++, f);
+    }
+    memset(w, 0, sizeof w);
+    w[0] = 0x80u; w[14] = 0u; w[15] = len << 3;                                /* :168, :174, :176-177 */
+    chs_transform(dig, w, blk, f);                                             /* :178 */
+    for (int i = 0; i < 5; ++i) digest[i] = dig[i];
 }
 
 /* ------------------------------------------------------------------ */
@@ -464,12 +520,18 @@ static void run_replica(const orc_desc* d, uint64_t local, const orc_fault* f, u
                                      (uint32_t)(local / d->N), (uint32_t)(local % d->N), f);
         memcpy(out, &v, 4);
     } break;
+    case ORC_K_CHSTONE_SHA: {
+        uint32_t dg[5];
+        orc_chstone_sha((const uint8_t*)d->in + local * d->unit_bytes, d->unit_bytes, dg, f);
+        memcpy(out, dg, 20);
+    } break;
     default: break;
     }
 }
 
 int orc_run_range(const orc_desc* d, uint64_t u0, uint64_t u1, orc_stats* st) {
-    if (!d || d->num_clones < 1 || d->num_clones > 3 || d->kernel > ORC_K_QSORT) return -1;
+    if (!d || d->num_clones < 1 || d->num_clones > 3 || d->kernel > ORC_K_CHSTONE_SHA) return -1;
+    if (d->kernel == ORC_K_CHSTONE_SHA && (d->unit_bytes < 64u || (d->unit_bytes & 63u) || d->unit_bytes >= (1u << 29))) return -1;
     if (d->kernel == ORC_K_QSORT) {
         const uint32_t L = d->unit_bytes / 4u, nc = d->num_clones;
         if (L < 1 || L > 1024 || (d->unit_bytes & 3u)) return -1;

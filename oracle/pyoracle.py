@@ -14,7 +14,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-K_CRC16, K_SHA256, K_AES128, K_MM_U32, K_GEMM_TF32, K_QSORT = range(6)
+K_CRC16, K_SHA256, K_AES128, K_MM_U32, K_GEMM_TF32, K_QSORT, K_CHSTONE_SHA = range(7)
 F_COUNT_ERRORS, F_COUNT_SYNCS, F_MAJORITY = 1, 2, 0x100
 PLAN_NONE, PLAN_BERNOULLI, PLAN_TABLE = 0, 1, 2
 AES_DECRYPT, AES_KEY_PER_UNIT = 1, 2
@@ -79,6 +79,7 @@ def lib():
         L.orc_crc16.restype = C.c_uint16
         L.orc_sha256.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(OrcFault)]
         L.orc_aes128.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OrcFault)]
+        L.orc_chstone_sha.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(OrcFault)]
         L.orc_run.argtypes = [C.POINTER(OrcDesc), C.POINTER(OrcStats)]
         L.orc_run_mt.argtypes = [C.POINTER(OrcDesc), C.c_int, C.POINTER(OrcStats)]
         _lib = L
@@ -176,6 +177,27 @@ def sha256(data: bytes) -> bytes:
     out = np.zeros(32, dtype=np.uint8)
     lib().orc_sha256(buf.ctypes.data, len(data), out.ctypes.data, None)
     return out.tobytes()
+
+
+def chstone_sha(data: bytes) -> list:
+    """sha_info_digest[5] of tests/chstone/sha for one stream (len(data) % 64 == 0)."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    out = np.zeros(5, dtype=np.uint32)
+    lib().orc_chstone_sha(buf.ctypes.data, len(data), out.ctypes.data, None)
+    return [int(x) for x in out]
+
+
+def chstone_site_of_input_bit(byte: int, bit: int):
+    """(site, bit) of the fault plan that flips `bit` of input byte `byte` as the replica loads it (little-endian W[])."""
+    return 421 * (byte // 64) + (byte % 64) // 4, 8 * (byte % 4) + bit
+
+
+def chstone_indata() -> np.ndarray:
+    """The benchmark's own 2 x 8192-byte input, read out of oracle/_ref/libref_chsha.so (compiled reference data)."""
+    r = ref("chsha")
+    r.ref_chsha_indata.restype = C.c_void_p
+    n = int(r.ref_chsha_len())
+    return np.frombuffer((C.c_uint8 * n).from_address(r.ref_chsha_indata()), dtype=np.uint8).copy()
 
 
 def aes128(state: bytes, key: bytes, direction: int):

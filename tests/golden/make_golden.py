@@ -15,6 +15,9 @@ Contents
   aes     : the 568 NIST AESAVS records of tests/aes/ECB*.h (80 bytes each: key|key2|cipher|plain|input),
             and what aes_enc_dec() leaves in state[] and key[] for each direction
   mm      : mm_tmr.c 9x9 uint32 operands, results_matrix, xor_golden; matrixMultiply.c int operands/results
+  chsha   : tests/chstone/sha: the golden outData of sha_driver.c (the 16 KiB indata itself is NOT copied: only its
+            SHA-256, the GPU test reads the bytes from oracle/_ref/libref_chsha.so), reference digests of Philox
+            streams of several lengths, and TMR/DWC runs with input flips
   xmr     : TMR/DWC runs of the reference functions with a single-bit flip in ONE replica's private
             copy of its input (the only fault sites reachable without editing reference sources)
 """
@@ -201,6 +204,47 @@ def main():
     xmr.update({"crc_msgs": hexs(msgs.tobytes()), "crc_faults": plan,
                 "crc_run_tmr": {"out": [int(x) for x in out], "stats": st.as_dict()}})
     g["xmr"] = xmr
+
+    # ---------------------------------------------------------------- chstone sha (appended last: the rng stream above is unchanged)
+    import hashlib
+    rh = po.ref("chsha")
+    rh.ref_chsha_indata.restype = C.c_void_p
+    rh.ref_chsha_golden.restype = C.POINTER(C.c_uint32)
+    rh.ref_chsha.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    klen = int(rh.ref_chsha_len())
+    indata = np.frombuffer((C.c_uint8 * klen).from_address(rh.ref_chsha_indata()), dtype=np.uint8).copy()
+    dg = np.zeros(5, dtype=np.uint32)
+    rh.ref_chsha(indata.ctypes.data, klen, dg.ctypes.data)
+    assert [int(x) for x in dg] == [int(rh.ref_chsha_golden()[i]) for i in range(5)]      # sha_driver.c:45-46 outData
+    ch = {"kat_len": klen, "kat_input_sha256": hashlib.sha256(indata.tobytes()).hexdigest(),
+          "kat_digest": [int(x) for x in dg], "philox": []}
+    for seed, ln in [(1, 64), (2, 128), (3, 192), (4, 1024), (5, 4096), (6, 16384), (7, 65536)]:
+        d = po.fill_philox(ln // 4, 0, seed).view(np.uint8)
+        rh.ref_chsha(d.ctypes.data, ln, dg.ctypes.data)
+        ch["philox"].append({"seed": seed, "len": ln, "digest": [int(x) for x in dg]})
+    n, ln = 12, 192
+    msgs = po.fill_philox(n * ln // 4, 0, 77).view(np.uint8)
+    faults = (po.RefFault * n)()
+    plan = []
+    for u in range(n):
+        if u % 4 == 3:
+            faults[u] = po.RefFault(0, -1, 0)
+            plan.append(None)
+        else:
+            r_, by, bi = int(rng.integers(0, 3)), int(rng.integers(0, ln)), int(rng.integers(0, 8))
+            faults[u] = po.RefFault(r_, by, bi)
+            plan.append([r_, by, bi])
+    rh.ref_chsha_xmr.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                 C.c_void_p, C.POINTER(po.RefStats)]
+    ch.update({"xmr_seed": 77, "xmr_n": n, "xmr_len": ln, "xmr_faults": plan, "xmr_runs": {}})
+    for nc in (3, 2):
+        fl = (po.RefFault * n)(*[po.RefFault(f.replica, f.byte if f.replica < nc else -1, f.bit) for f in faults])
+        out = np.zeros(5 * n, dtype=np.uint32)
+        st = po.RefStats()
+        st.first_fault_unit = po.NO_FAULT_UNIT
+        rh.ref_chsha_xmr(msgs.ctypes.data, out.ctypes.data, n, ln, nc, 1, 1, fl, C.byref(st))
+        ch["xmr_runs"][str(nc)] = {"out": [int(x) for x in out], "stats": st.as_dict()}
+    g["chsha"] = ch
 
     path = os.path.join(ROOT, "tests", "golden", "coast_golden.json")
     with open(path, "w") as f:

@@ -23,6 +23,7 @@ CASES = [
      r"C:0 E:0 F:0 T:0us", 0),                                                                      # sha256_tmr.c:30
     ("mm_common", "mm_tmr", ["SRCFILES={ref}/mm_common/mm_tmr.c", "TARGET=mm_tmr", "OPT_PASSES=-TMR -countErrors"],
      "coast_xmr_matrix_multiply", r"Error\?: 0", 0),                                                # mm_tmr.c:38
+    ("chstone/sha", "sha_driver", [], "coast_xmr_sha_stream", r"RESULT: PASS", 0),                  # unittest/cfg/full.yml:5-6
 ]
 
 

@@ -87,7 +87,7 @@ def test_campaigns_reproduce_the_table_shape(rt, oracle, tmp_path):
     # quicksort is the workload where most flips are MASKED (a compare operand flip rarely changes the branch): like the
     # published table, unmitigated still sorts correctly most of the time; TMR never fails; DWC flags a superset of the SDCs
     assert q3.errors == 0 and q1.errors < 1000 and q1.success > 1000 and q2.errors <= 2 and q2.detected >= q1.errors * 0.5
-    for wl in ("sha256", "aes", "mm"):
+    for wl in ("sha256", "aes", "mm", "chsha"):
         t, _ = cp.run_campaign(rt, wl, "-TMR -countErrors", 2000, seed=5)
         assert t.errors == 0
         d, _ = cp.run_campaign(rt, wl, "-DWC", 2000, seed=5)

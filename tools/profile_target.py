@@ -14,12 +14,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--kernel", choices=["sha256", "aes", "crc16", "mm", "gemm", "qsort"], default="sha256")
+    ap.add_argument("--kernel", choices=["sha256", "aes", "crc16", "mm", "gemm", "qsort", "chsha"], default="sha256")
     ap.add_argument("--nc", type=int, default=3)
     ap.add_argument("--log2n", type=int, default=20)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--inject", type=float, default=0.0)
     ap.add_argument("--side", type=int, default=1024)
+    ap.add_argument("--stream-bytes", type=int, default=16384, help="chsha: bytes per stream (the benchmark's is 2 x 8192)")
     ap.add_argument("--flags", type=lambda x: int(x, 0), default=0, help="extra COAST_F_* bits, e.g. 0x8 = -i, 0x10 = -s")
     ap.add_argument("--time", action="store_true", help="print CUDA-event ms per launch (outside any profiler)")
     a = ap.parse_args()
@@ -44,6 +45,12 @@ def main():
         out = torch.empty(n * 16, dtype=torch.uint8, device="cuda")
         d = rt.make_desc(cb.K_AES128, a.nc, d_in, out, n, flags=flags, key=bytes(16), plan=plan)
         alg = n * 32
+    elif a.kernel == "chsha":
+        ub = a.stream_bytes
+        d_in = torch.empty(n * ub, dtype=torch.uint8, device="cuda"); rt.fill_philox(d_in, 6)
+        out = torch.empty(n * 20, dtype=torch.uint8, device="cuda")
+        d = rt.make_desc(cb.K_CHSTONE_SHA, a.nc, d_in, out, n, flags=flags, unit_bytes=ub, plan=plan)
+        alg = n * (ub + 20)
     elif a.kernel == "qsort":
         L = 580
         d_in = torch.empty(n * L, dtype=torch.int32, device="cuda"); rt.fill_philox(d_in, 9)
