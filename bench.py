@@ -402,10 +402,43 @@ def run_ours(args):
     pcie_h2d = copy_gbs(ins[1 % nsets].view(torch.uint8)[: h_in.numel() * h_in.element_size()], h_in.view(torch.uint8))
     pcie_d2h = copy_gbs(h_out.view(torch.uint8), outs[0].view(torch.uint8)[: h_out.numel() * h_out.element_size()])
 
-    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+    # SURVEY.md 8e "measured separately": the OPTIONAL data-path collectives a caller may add around the sharded launch --
+    # all-gather of the voted outputs; for the matmul also the one distribution step (B from rank 0).  Never part of
+    # `value`: the path itself exchanges only the 5 counters.  Device-timed, max over ranks.
+    coll_ms = [0.0, 0.0]
+    coll_note = None
+    if dist is not None and world > 1:
+        def time_coll(fn, reps=3):
+            fn(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier(); a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); b.synchronize()
+            return a.elapsed_time(b) / reps
+        try:
+            mine = outs[0].view(torch.uint8)
+            per = torch.tensor([mine.numel()], dtype=torch.int64, device=dev)
+            lo_hi = torch.stack([per, -per]).flatten()
+            dist.all_reduce(lo_hi, op=dist.ReduceOp.MIN)
+            equal = int(lo_hi[0]) == -int(lo_hi[1])                       # all_gather_into_tensor needs equal shards
+            if equal and world * mine.numel() <= (2 << 30):
+                gathered = torch.empty(world * mine.numel(), dtype=torch.uint8, device=dev)
+                coll_ms[0] = time_coll(lambda: dist.all_gather_into_tensor(gathered, mine))
+                assert torch.equal(gathered[rank * mine.numel():(rank + 1) * mine.numel()], mine)
+                del gathered
+            else:
+                coll_note = "all-gather skipped: unequal shards or more than 2 GiB of outputs"
+            if is_gemm:
+                Bt = auxs[0]
+                coll_ms[1] = time_coll(lambda: dist.broadcast(Bt, src=0))
+        except Exception as exc:                                          # optional measurement: never lose the bench line
+            coll_note = f"collective timing failed: {exc!r}"[:200]
+
+    t = torch.tensor([ms, e2e_s, coll_ms[0], coll_ms[1]], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)           # max over ranks
-    ms, e2e_s = float(t[0]), float(t[1])
+    ms, e2e_s, coll_ms = float(t[0]), float(t[1]), [float(t[2]), float(t[3])]
     if rank == 0:
         ms_per_step = ms / args.steps
         value = total_out_bytes / (ms_per_step * 1e-3) / 1e6
@@ -449,6 +482,12 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "stats_last_sync": st.as_dict(),
         }
+        if world > 1:
+            line["collectives"] = {"in_value": "all-reduce of the 5 counters per step (inside the timed region)",
+                                   "allgather_outputs_ms": round(coll_ms[0], 4) if coll_ms[0] else None,
+                                   "allgather_bytes": world * outs[0].numel() * outs[0].element_size() if coll_ms[0] else None,
+                                   "broadcast_B_ms": round(coll_ms[1], 4) if coll_ms[1] else None,
+                                   "note": coll_note or "measured separately, not part of value (SURVEY.md 8e)"}
         if world == 1 and not args.no_cpu_baseline and args.workload == "sha256":
             line["cpu_baseline"] = cpu_baseline_block()
         print(json.dumps(line), flush=True)
