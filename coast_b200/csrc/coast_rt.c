@@ -54,6 +54,11 @@ __attribute__((weak)) void FAULT_DETECTED_DWC(void) { /* synchronization.cpp:125
                        CUstream, void**, void**))                                                            \
     X(cuMemAlloc_v2, (CUdeviceptr*, size_t))                                                                 \
     X(cuMemFree_v2, (CUdeviceptr))                                                                           \
+    X(cuMemPoolCreate, (CUmemoryPool*, const CUmemPoolProps*))                                               \
+    X(cuMemPoolDestroy, (CUmemoryPool))                                                                      \
+    X(cuMemPoolSetAttribute, (CUmemoryPool, CUmemPool_attribute, void*))                                     \
+    X(cuMemAllocFromPoolAsync, (CUdeviceptr*, size_t, CUmemoryPool, CUstream))                               \
+    X(cuMemFreeAsync, (CUdeviceptr, CUstream))                                                               \
     X(cuMemcpyHtoDAsync_v2, (CUdeviceptr, const void*, size_t, CUstream))                                    \
     X(cuMemcpyDtoHAsync_v2, (void*, CUdeviceptr, size_t, CUstream))                                          \
     X(cuMemcpyDtoDAsync_v2, (CUdeviceptr, CUdeviceptr, size_t, CUstream))                                    \
@@ -90,6 +95,8 @@ static struct {
     uint32_t def_nc, def_flags; int def_set;
     /* coast_run_host scratch: 3 slots */
     CUstream hs[3]; CUdeviceptr h_in[3], h_out[3], h_aux[3]; size_t h_in_cap[3], h_out_cap[3], h_aux_cap[3];
+    /* stream-ordered scratch (the replicas' private arrays of xmr_qsort.cuh): any number of streams may launch at once */
+    CUmemoryPool pool;
     /* limb planes of the tensor-core exact matmul (xmr_mm_tc.cuh) */
     CUdeviceptr mm_planes; size_t mm_planes_cap;
 } G;
@@ -191,6 +198,14 @@ int coast_init(int device) {
     r = p_cuModuleLoadData(&G.mod, coast_kernels_cubin);
     if (r != CUDA_SUCCESS) { p_cuDevicePrimaryCtxRelease_v2(G.dev); return drv_fail(r, "cuModuleLoadData(sm_100a cubin)"); }
     DRV(p_cuMemAlloc_v2(&G.counters, XMR_CTR_COUNT * sizeof(uint64_t)));
+    {
+        CUmemPoolProps pp; memset(&pp, 0, sizeof pp);
+        pp.allocType = CU_MEM_ALLOCATION_TYPE_PINNED;
+        pp.location.type = CU_MEM_LOCATION_TYPE_DEVICE; pp.location.id = (int)G.dev;
+        DRV(p_cuMemPoolCreate(&G.pool, &pp));
+        cuuint64_t keep = ~(cuuint64_t)0;                  /* keep freed scratch cached in the pool between launches */
+        DRV(p_cuMemPoolSetAttribute(G.pool, CU_MEMPOOL_ATTR_RELEASE_THRESHOLD, &keep));
+    }
     DRV(p_cuMemHostAlloc((void**)&G.h_counters, XMR_CTR_COUNT * sizeof(uint64_t), 0));
     G.device = device;
     G.inited = 1;
@@ -214,6 +229,7 @@ int coast_shutdown(void) {
     if (G.mm_planes) p_cuMemFree_v2(G.mm_planes);
     G.mm_planes = 0; G.mm_planes_cap = 0;
     p_cuMemFree_v2(G.counters);
+    if (G.pool) { p_cuMemPoolDestroy(G.pool); G.pool = NULL; }
     p_cuMemFreeHost(G.h_counters);
     p_cuModuleUnload(G.mod);
     p_cuDevicePrimaryCtxRelease_v2(G.dev);
@@ -440,7 +456,7 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
     a.n_sites = coast_fault_sites(d->kernel, d->unit_bytes, d->K);
 
     char name[64];
-    unsigned smem = 0; int tma = 0; int block = XMR_CTA_THREADS; int mm_tiled = 0;
+    unsigned smem = 0; int tma = 0; int block = XMR_CTA_THREADS; int mm_tiled = 0; int qs_scratch = 0;
     unsigned tile_rows = 0, row_bytes = 0; CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_NONE;
     const int aligned16 = (((uintptr_t)d->d_in) & 15u) == 0;
     switch (d->kernel) {
@@ -508,7 +524,7 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
     case COAST_K_QSORT:
         if (d->unit_bytes < 4 || (d->unit_bytes & 3u) || d->unit_bytes > 4096u)
             return fail(COAST_ERR_BAD_ARG, "quicksort arrays are 1..1024 int32 (unit_bytes = 4*L, got %u)", d->unit_bytes);
-        block = 128;
+        block = 128; qs_scratch = 1;
         snprintf(name, sizeof name, "xmr_qsort_nc%u_inj%d", nc, inj);
         break;
     case COAST_K_CHSTONE_SHA:
@@ -548,13 +564,24 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
         uint64_t warps = (d->n_units + upw - 1) / upw;
         uint64_t wpc = (uint64_t)block / 32u;
         uint64_t ctas = (warps + wpc - 1) / wpc;
-        uint64_t cap = (uint64_t)G.sm_count * (unsigned)occ * 4u;
+        /* quicksort: one resident wave (persistent warps), because every warp owns a scratch slot */
+        uint64_t cap = (uint64_t)G.sm_count * (unsigned)occ * (qs_scratch ? 1u : 4u);
         grid = (unsigned)(ctas < cap ? ctas : cap);
+    }
+    CUdeviceptr scratch = 0;
+    if (qs_scratch) {
+        /* private copy of every replica's array, lane-major and CONTIGUOUS per lane (a scan walks one cache line per 32
+         * elements; thread-local memory would put consecutive elements of a lane 128 bytes apart) */
+        size_t bytes = (size_t)grid * (size_t)(block / 32) * 32u * (size_t)d->unit_bytes;
+        DRV(p_cuMemAllocFromPoolAsync(&scratch, bytes ? bytes : 4, G.pool, (CUstream)stream));
+        a.aux = (const void*)scratch;
     }
     if (d->flags & COAST_F_VERBOSE)
         fprintf(stderr, "coast_rt: %s grid=%u block=%d smem=%u units=%llu\n", name, grid, block, smem,
                 (unsigned long long)d->n_units);
-    DRV(p_cuLaunchKernel(fn, grid, 1, 1, (unsigned)block, 1, 1, smem, (CUstream)stream, params, NULL));
+    CUresult lr = p_cuLaunchKernel(fn, grid, 1, 1, (unsigned)block, 1, 1, smem, (CUstream)stream, params, NULL);
+    if (scratch) p_cuMemFreeAsync(scratch, (CUstream)stream);           /* stream-ordered: released after the kernel */
+    if (lr != CUDA_SUCCESS) return drv_fail(lr, "cuLaunchKernel");
     return COAST_OK;
 }
 

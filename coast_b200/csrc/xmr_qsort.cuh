@@ -4,7 +4,10 @@
 // loops (populateSyncPoints synchronization.cpp:146-155, syncTerminator :741-1113, the same select voter :934-938):
 // the NC replica lanes of a unit run in lockstep, every data-dependent condition (`A[i] < pivot`, `A[j] > pivot`) is voted
 // with sub-warp shuffles over the unit's lane group and ALL replicas follow the voted branch; each replica swaps inside
-// its own private copy of the array (memory replication, local memory).  SoR exit: one vote per stored element.
+// its own private copy of the array (memory replication).  The copies live in a library-owned, stream-ordered scratch
+// buffer (a.aux), lane-major and contiguous per lane: the i++ / j-- scans of :126-127 then walk one 128-byte line per 32
+// elements and hit in L1, where thread-local memory (32-way interleaved) put every element of a lane in a different line
+// (r01: 17.8 ms for 65 536 x 580 ints under TMR, DRAM-latency bound).  SoR exit: one vote per stored element.
 // Unit = one array of L = unit_bytes/4 ints (L <= 1024; the reference sorts 580).  Recursion = explicit stack, left first.
 // Fault sites: s < 32L: the value loaded for the s-th executed data comparison; 32L <= s < 33L: element s-32L of the
 // replica's private copy before sorting.  The CPU checker under oracle/ uses the identical enumeration, guards and order.
@@ -44,7 +47,7 @@ __device__ __forceinline__ void qsort_body(const xmr_args& a) {
     const unsigned long long n_wtiles = (a.n_units + UPW - 1) / UPW;
     const uint32_t L = a.unit_bytes >> 2;
     Tally tally(a);
-    int32_t A[QS_MAX];
+    int32_t* const A = static_cast<int32_t*>(const_cast<void*>(a.aux)) + (gwarp * 32ull + (unsigned)lane) * L;   // this lane's slot
     uint32_t stack[QS_MAX];                                     // (off << 16) | len, len <= 1024 needs 11 bits
     for (unsigned long long wt = gwarp; wt < n_wtiles; wt += nwarps) {
         const unsigned long long local = wt * UPW + u;
