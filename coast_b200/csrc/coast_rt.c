@@ -525,7 +525,10 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
         if (d->unit_bytes < 4 || (d->unit_bytes & 3u) || d->unit_bytes > 4096u)
             return fail(COAST_ERR_BAD_ARG, "quicksort arrays are 1..1024 int32 (unit_bytes = 4*L, got %u)", d->unit_bytes);
         block = 128; qs_scratch = 1;
-        snprintf(name, sizeof name, "xmr_qsort_nc%u_inj%d", nc, inj);
+        {   /* two schedulings of the same algorithm (xmr_qsort.cuh): per-unit state machine (default) or nested loops */
+            const char* path = getenv("COAST_QSORT_PATH");
+            snprintf(name, sizeof name, "%s_nc%u_inj%d", path && !strcmp(path, "nested") ? "xmr_qsortn" : "xmr_qsort", nc, inj);
+        }
         break;
     case COAST_K_CHSTONE_SHA:
         if (d->unit_bytes < 64u || (d->unit_bytes & 63u) || d->unit_bytes >= (1u << 29))
