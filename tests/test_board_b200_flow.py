@@ -7,32 +7,19 @@ every output of compiling reference sources goes) and must print what the refere
 import os
 import re
 import subprocess
+import sys
 
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = "/root/reference/tests"
-OUT = os.path.join(ROOT, "oracle", "_ref", "b200")
-
-# test dir, TARGET, extra make vars, runtime entry the pass must have wired in, expected stdout regex, expected exit code
-CASES = [
-    ("crc16", "crc16", [], "coast_xmr_crc16", r"result: 5ba3", 0),                                  # crc16.c:42
-    ("aes", "aes", [], "coast_xmr_aes_enc_dec", r"Number of errors: 0", 0),                         # aes.c:114 (568 NIST KATs)
-    ("matrixMultiply", "matrixMultiply", [], "coast_xmr_matrix_multiply", r"Number of errors: 0", 0),   # unittest/cfg/full.yml:2-3
-    ("sha256_common", "sha256_tmr", ["SRCFILES={ref}/sha256_common/sha256_tmr.c"], "coast_xmr_sha256_hash",
-     r"C:0 E:0 F:0 T:0us", 0),                                                                      # sha256_tmr.c:30
-    ("mm_common", "mm_tmr", ["SRCFILES={ref}/mm_common/mm_tmr.c", "TARGET=mm_tmr", "OPT_PASSES=-TMR -countErrors"],
-     "coast_xmr_matrix_multiply", r"Error\?: 0", 0),                                                # mm_tmr.c:38
-    ("chstone/sha", "sha_driver", [], "coast_xmr_sha_stream", r"RESULT: PASS", 0),                  # unittest/cfg/full.yml:5-6
-]
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from build_reference_tests import CASES, OUT, REF, make_cmd  # noqa: E402  (the list the driver's build() uses too)
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout absent (GPU box)")
 @pytest.mark.parametrize("tdir,target,extra,entry,_re,_rc", CASES)
 def test_unchanged_reference_tests_build_against_the_runtime(built_lib, tdir, target, extra, entry, _re, _rc):
-    cmd = ["make", "-s", "-C", os.path.join(REF, tdir), f"LEVEL={ROOT}/include", "BOARD=b200", "-B"] + \
-          [e.format(ref=REF) for e in extra] + ["exe"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    res = subprocess.run(make_cmd(tdir, extra, rebuild=True), capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     exe = os.path.join(OUT, target, target + ".out")
     assert os.path.exists(exe)
@@ -105,7 +92,7 @@ def test_every_sweep_entry_parses_without_an_ignored_token(built_lib):
         nc, fl = C.c_uint32(), C.c_uint32()
         code = ("import ctypes as C,sys; l=C.CDLL(sys.argv[1]); n=C.c_uint32(); f=C.c_uint32(); "
                 "sys.exit(l.coast_parse_opt_passes(sys.argv[2].encode(), C.byref(n), C.byref(f)) * 0 + n.value)")
-        res = subprocess.run([os.sys.executable, "-c", code, built_lib, passes], capture_output=True, text=True)
+        res = subprocess.run([sys.executable, "-c", code, built_lib, passes], capture_output=True, text=True)
         assert "ignored" not in res.stderr and "not emulated" not in res.stderr, (passes, res.stderr)
         assert res.returncode == (3 if "-TMR" in passes else 2 if "-DWC" in passes else 1), passes
         assert lib.coast_parse_opt_passes(passes.encode(), C.byref(nc), C.byref(fl)) == 0
