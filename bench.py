@@ -96,6 +96,16 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+# one name per workload, shared by both arms so that `config.workload` is identical in the two JSON lines the driver compares
+WORKLOAD_NAMES = {
+    "sha256": "sha256 TMR, 2^20 x 64-byte messages per GPU (BASELINE configs[1])",
+    "sha256_2p30": "batched sha256 TMR, 2^30 x 64-byte messages sharded over the GPUs (BASELINE configs[4])",
+    "aes": "aes-128 ECB encrypt DWC, 2^24 x 16-byte blocks, Bernoulli(2^-10) single-bit flips (BASELINE configs[2])",
+    "crc16": "crc16 TMR, 2^20 x 64-byte messages (SURVEY.md 8d config 1 timing shape)",
+    "gemm": "matmul TMR 4096x4096x4096 fp32 on tcgen05 kind::tf32, three TMEM accumulator replicas + voter (BASELINE configs[3])",
+}
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own sha256_hash() under the restated TMR wrapper (oracle/_ref), or the port
 # ------------------------------------------------------------------------------------------------
@@ -194,7 +204,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t * 1e3, 3), "higher_is_better": True,
         "scaling": "strong" if wl == "gemm" else "weak", "vs_baseline": None,
         "dtype": "f32" if wl == "gemm" else ("u8" if wl == "aes" else "u32"), "data": "synthetic",
-        "config": {"workload": wl, "units_per_step": n, "protection": {"aes": "-DWC + injector", }.get(wl, "-TMR -countErrors -countSyncs"),
+        "config": {"workload": WORKLOAD_NAMES[wl], "units_per_step": n, "protection": {"aes": "-DWC + injector", }.get(wl, "-TMR -countErrors -countSyncs"),
                    "note": "reference C sources compiled in place (oracle/_ref) + restated xMR wrapper for sha256; oracle port for the "
                            "other workloads; the real opt -TMR binary needs LLVM 7 (absent). A step is a bounded sample of the GPU arm's batch."},
         "cpu_baseline": {"value": round(val, 3), "unit": "MB/s", "cores": threads, "kind": kind,
@@ -214,20 +224,20 @@ def workload_table(cb):
     F = cb.F_COUNT_ERRORS | cb.F_COUNT_SYNCS
     return {
         "sha256": dict(kernel=cb.K_SHA256, nc=3, flags=F, n=1 << 20, unit_bytes=64, in_b=64, out_b=32, alg_b=96, plan=None,
-                       name="sha256 TMR, 2^20 x 64-byte messages per GPU (BASELINE configs[1])", kname="xmr_sha256_b64_seg_nc3_inj0",
+                       name=WORKLOAD_NAMES["sha256"], kname="xmr_sha256_b64_seg_nc3_inj0",
                        protection="-TMR -countErrors -countSyncs", bound="hbm", sets=4),
         "sha256_2p30": dict(kernel=cb.K_SHA256, nc=3, flags=F, n=1 << 30, unit_bytes=64, in_b=64, out_b=32, alg_b=96, plan=None, strong=True,
-                            name="batched sha256 TMR, 2^30 x 64-byte messages sharded over the GPUs (BASELINE configs[4])",
+                            name=WORKLOAD_NAMES["sha256_2p30"],
                             kname="xmr_sha256_b64_seg_nc3_inj0", protection="-TMR -countErrors -countSyncs", bound="hbm", sets=1),
         "aes": dict(kernel=cb.K_AES128, nc=2, flags=0, n=1 << 24, unit_bytes=0, in_b=16, out_b=16, alg_b=32,
                     plan=dict(seed=33, p=2.0 ** -10), key=bytes(16),
-                    name="aes-128 ECB encrypt DWC, 2^24 x 16-byte blocks, Bernoulli(2^-10) single-bit flips (BASELINE configs[2])",
+                    name=WORKLOAD_NAMES["aes"],
                     kname="xmr_aes128_enc_nc2_inj1", protection="-DWC + on-device injector", bound="hbm", sets=2),
         "crc16": dict(kernel=cb.K_CRC16, nc=3, flags=F, n=1 << 20, unit_bytes=64, in_b=64, out_b=2, alg_b=66, plan=None,
-                      name="crc16 TMR, 2^20 x 64-byte messages (SURVEY.md 8d config 1 timing shape)", kname="xmr_crc16_b64_nc3_inj0",
+                      name=WORKLOAD_NAMES["crc16"], kname="xmr_crc16_b64_nc3_inj0",
                       protection="-TMR -countErrors -countSyncs", bound="hbm", sets=4),
         "gemm": dict(kernel=cb.K_GEMM_TF32, nc=3, flags=F, side=4096, plan=None,
-                     name="matmul TMR 4096x4096x4096 fp32 on tcgen05 kind::tf32, three TMEM accumulator replicas + voter (BASELINE configs[3])",
+                     name=WORKLOAD_NAMES["gemm"],
                      kname="xmr_gemm_tf32_nc3_inj0", protection="-TMR -countErrors -countSyncs", bound="tensor", sets=2),
     }
 
