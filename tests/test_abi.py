@@ -40,6 +40,26 @@ def test_sm100a_cubin_is_embedded(built_lib):
     assert cubin[:4] == b"\x7fELF" and cubin in blob
 
 
+def test_every_kernel_the_host_code_can_name_is_in_the_cubin(built_lib):
+    """coast_rt.c builds kernel names with snprintf; a typo would only show up as a launch failure on a GPU box"""
+    import itertools
+    import re
+    import subprocess
+    src = open(os.path.join(ROOT, "coast_b200", "csrc", "coast_rt.c")).read()
+    fmts = set(re.findall(r'"(xmr_[A-Za-z0-9_%]+)"', src)) - {"xmr_qsort", "xmr_qsortn"}      # the two prefixes of one "%s_nc%u_inj%d"
+    fmts |= {"xmr_qsort_nc%u_inj%d", "xmr_qsortn_nc%u_inj%d"}
+    names = set()
+    for f in fmts:
+        opts = [["tc", "tct"] if tok == "%s" else ["1", "2", "3"] if tok == "%u" else ["0", "1"] for tok in re.findall(r"%[sud]", f)]
+        for combo in itertools.product(*opts):
+            it = iter(combo)
+            names.add(re.sub(r"%[sud]", lambda m: next(it), f))
+    sass = subprocess.run(["cuobjdump", "-elf", os.path.join(ROOT, "coast_b200", "csrc", "coast_kernels.cubin")],
+                          capture_output=True, text=True).stdout
+    have = set(re.findall(r"\.text\.(xmr_\w+)", sass))
+    assert len(names) > 80 and not (names - have), sorted(names - have)
+
+
 @pytest.mark.parametrize("s,nc,fl", [
     ("-TMR -reportErrors", 3, 0x40),                       # tests/crc16/Makefile:3
     ("-TMR -verbose -countErrors", 3, 0x21),               # tests/sha256_common/Makefile:3
