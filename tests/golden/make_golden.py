@@ -18,6 +18,8 @@ Contents
   chsha   : tests/chstone/sha: the golden outData of sha_driver.c (the 16 KiB indata itself is NOT copied: only its
             SHA-256, the GPU test reads the bytes from oracle/_ref/libref_chsha.so), reference digests of Philox
             streams of several lengths, and TMR/DWC runs with input flips
+  qsort   : tests/quicksort: the benchmark's own 580-int input (srand(0)) with the SHA-256 of what quick_sort() makes of it,
+            and reference outputs for random arrays of several lengths (duplicates, extremes)
   xmr     : TMR/DWC runs of the reference functions with a single-bit flip in ONE replica's private
             copy of its input (the only fault sites reachable without editing reference sources)
 """
@@ -245,6 +247,26 @@ def main():
         rh.ref_chsha_xmr(msgs.ctypes.data, out.ctypes.data, n, ln, nc, 1, 1, fl, C.byref(st))
         ch["xmr_runs"][str(nc)] = {"out": [int(x) for x in out], "stats": st.as_dict()}
     g["chsha"] = ch
+
+    # ---------------------------------------------------------------- quicksort (tests/quicksort/quicksort.c), appended last
+    rq = po.ref("qsort")
+    rq.ref_qsort_init.restype = C.POINTER(C.c_int)
+    L = int(rq.ref_qsort_elements())
+    assert rq.ref_qsort_selfcheck(0) == 0
+    p_ = rq.ref_qsort_init(0)                               # the benchmark's own input: srand(0), 580 x rand()  (:93-115)
+    inp = np.array([p_[i] for i in range(L)], dtype=np.int32)
+    srt = inp.copy()
+    rq.ref_quick_sort(srt.ctypes.data, L)
+    qs = {"elements": L, "seed0_input": [int(v) for v in inp], "seed0_sorted_sha256": hashlib.sha256(srt.tobytes()).hexdigest(),
+          "random": []}
+    for ln in (1, 2, 3, 17, 100, 580, 1024):
+        a_ = rng.integers(-2 ** 31, 2 ** 31 - 1, ln, dtype=np.int64).astype(np.int32)
+        if ln == 100:
+            a_ = (a_ % 7).astype(np.int32)                  # many duplicates
+        b_ = a_.copy()
+        rq.ref_quick_sort(b_.ctypes.data, ln)
+        qs["random"].append({"input": [int(v) for v in a_], "sorted": [int(v) for v in b_]})
+    g["qsort"] = qs
 
     path = os.path.join(ROOT, "tests", "golden", "coast_golden.json")
     with open(path, "w") as f:

@@ -532,3 +532,17 @@ def test_dwc_default_handler_aborts_like_the_reference(built_lib):
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
     assert res.returncode == -6, (res.returncode, res.stdout, res.stderr)          # SIGABRT
     assert "before sync" in res.stdout and "NOT REACHED" not in res.stdout and "FAULT_DETECTED_DWC" in res.stderr
+
+
+def test_quicksort_reference_golden_vectors_on_device(rt, oracle, golden):
+    """the benchmark's own 580-int input and the reference outputs of tests/golden (quicksort.c compiled in place)"""
+    g = golden["qsort"]
+    inp = np.array(g["seed0_input"], dtype=np.int32)
+    for nc in (1, 2, 3):
+        out, st = both(rt, oracle, oracle.K_QSORT, nc, inp, 1, unit_bytes=4 * len(inp), flags=1)
+        assert hashlib.sha256(out.tobytes()).hexdigest() == g["seed0_sorted_sha256"]
+        assert st["errors_corrected"] == 0 and st["dwc_detected"] == 0
+    for rec in g["random"]:
+        a = np.array(rec["input"], dtype=np.int32)
+        out, _ = both(rt, oracle, oracle.K_QSORT, 3, a, 1, unit_bytes=4 * len(a))
+        assert np.frombuffer(out.tobytes(), dtype=np.int32).tolist() == rec["sorted"]

@@ -83,6 +83,21 @@ def main():
         n += 1
     rows.append(("matrix_multiply() (mm_common_tmr.c)", f"random {side}x{side} uint32 operands", n))
 
+    # quicksort: random arrays of random lengths (duplicates included)
+    rq = po.ref("qsort")
+    n = 0
+    for _ in range(3000):
+        ln = int(rng.integers(1, 1025))
+        a = rng.integers(-2 ** 31, 2 ** 31 - 1, ln, dtype=np.int64).astype(np.int32)
+        if n % 3 == 0:
+            a = (a % 11).astype(np.int32)
+        b = a.copy()
+        rq.ref_quick_sort(b.ctypes.data, ln)
+        out, _ = po.run(po.K_QSORT, 3, a, 1, unit_bytes=4 * ln)
+        assert out.tobytes() == b.tobytes(), ln
+        n += 1
+    rows.append(("quick_sort() (quicksort.c)", "random arrays of 1..1024 ints, a third with many duplicates, under the TMR wrapper", n))
+
     dt = time.time() - t0
     lines = ["# Extended oracle pin (r01) -- `python tools/oracle_pin_extended.py`", "",
              "Randomized differential run of `oracle/coast_oracle.c` against the reference's own functions compiled in place",
