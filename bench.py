@@ -189,7 +189,7 @@ def run_reference(args):
     cal_n = {"gemm": 4096 * 2, "aes": 1 << 16}.get(wl, 1 << 14)
     t_cal, kind, ob = cpu_xmr(wl, cal_n, threads)
     rate = cal_n / max(t_cal, 1e-6)
-    total_budget = 90.0                                   # whole --steps/--warmup run stays within a few minutes
+    total_budget = args.ref_budget_s                      # whole --steps/--warmup run stays within a few minutes
     full = {"sha256": N_UNITS, "sha256_2p30": N_UNITS, "crc16": 1 << 20, "aes": 1 << 24, "gemm": 4096 * 4096}[wl]
     n = int(max(cal_n, min(full, rate * total_budget / max(1, args.steps + args.warmup))))
     n = (n // 4096) * 4096 if wl == "gemm" else 1 << (n.bit_length() - 1)
@@ -518,6 +518,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=90.0, help="--impl reference: CPU seconds the whole run may take")
     ap.add_argument("--threads", type=int, default=0, help="--impl reference: host threads (default: all; config 1 is 1 thread)")
     ap.add_argument("--workload", choices=["sha256", "sha256_2p30", "aes", "crc16", "gemm"], default="sha256",
                     help="default sha256 = BASELINE configs[1], the headline line; the others are extra lines")

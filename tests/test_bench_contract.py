@@ -1,0 +1,36 @@
+"""The JSON line of `bench.py --impl reference` (the arm that runs on host cores, so it can be checked without a GPU)
+carries every key of the driver's contract; under torchrun only rank 0 prints."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+        "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"}
+
+
+def _run(extra, env=None):
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3",
+           "--ref-budget-s", "2"] + extra
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+
+
+def test_reference_arm_line_has_the_contract_keys():
+    res = _run(["--threads", "2"])
+    assert res.returncode == 0, res.stderr
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert KEYS <= set(d), KEYS - set(d)
+    assert d["impl"] == "reference" and d["unit"] == "MB/s" and d["higher_is_better"] is True and d["warmup"] >= 3
+    assert d["metric"].startswith("protected-kernel throughput (MB/s voted output)") and d["value"] > 0
+    assert d["config"]["workload"].startswith("sha256 TMR, 2^20 x 64-byte messages")
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] == 2 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_print_nothing():
+    res = _run([], env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert res.returncode == 0 and not [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
