@@ -159,6 +159,17 @@ def cpu_xmr(workload: str, n_units: int, threads: int, repeats: int = 1):
     po.build()
     if workload == "crc16":
         inp = po.fill_philox(n_units * 16, 0, 2).view(np.uint8)
+        if po.ref_available():                              # the reference's own crc16() under the restated TMR wrapper
+            import ctypes as C
+            lib = po.ref("crc16")
+            lib.ref_crc16_xmr_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                             C.c_int, C.POINTER(po.RefStats)]
+            out = np.zeros(n_units, dtype=np.uint16)
+            t0 = time.perf_counter()
+            for _ in range(repeats):
+                st = po.RefStats()
+                lib.ref_crc16_xmr_mt(inp.ctypes.data, out.ctypes.data, n_units, 64, 3, 1, 1, threads, C.byref(st))
+            return (time.perf_counter() - t0) / repeats, "reference", 2
         kw = dict(kernel=po.K_CRC16, nc=3, flags=3, unit_bytes=64)
         ob = 2
     elif workload == "aes":
