@@ -174,6 +174,28 @@ def cpu_xmr(workload: str, n_units: int, threads: int, repeats: int = 1):
         ob = 2
     elif workload == "aes":
         inp = po.fill_philox(n_units * 4, 0, 2).view(np.uint8)
+        if po.ref_available():
+            # the reference's own aes_enc_dec() under the restated DWC wrapper.  Its flips can only go into a replica's private
+            # copy of the INPUT (mid-round sites need edited sources): Bernoulli(2^-10) per block, as in the GPU arm's plan.
+            import ctypes as C
+            lib = po.ref("aes")
+            lib.ref_aes_xmr_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int,
+                                           C.c_int, C.c_void_p, C.c_int, C.POINTER(po.RefStats)]
+            rng = np.random.default_rng(33)
+            hit = rng.random(n_units) < 2.0 ** -10
+            faults = np.zeros((n_units, 3), dtype=np.int32)           # ref_fault {replica, byte, bit}
+            faults[:, 1] = -1
+            k = int(hit.sum())
+            faults[hit] = np.stack([rng.integers(0, 2, k), rng.integers(0, 16, k), rng.integers(0, 8, k)], axis=1)
+            key = np.zeros(16, dtype=np.uint8)
+            out = np.zeros(n_units * 16, dtype=np.uint8)
+            t0 = time.perf_counter()
+            for _ in range(repeats):
+                st = po.RefStats()
+                lib.ref_aes_xmr_mt(inp.ctypes.data, out.ctypes.data, n_units, key.ctypes.data, 0, 0, 2, 0, 0, faults.ctypes.data,
+                                   threads, C.byref(st))
+                assert st.dwc_detected == st.injected == k      # detect-rate parity holds on the CPU arm too
+            return (time.perf_counter() - t0) / repeats, "reference", 16
         kw = dict(kernel=po.K_AES128, nc=2, flags=0, key=bytes(16), plan=po.make_plan(po.PLAN_BERNOULLI, seed=33, p=2.0 ** -10))
         ob = 16
     else:  # gemm: a row-block sample of the 4096^3 problem (n_units = rows * 4096)
@@ -216,8 +238,9 @@ def run_reference(args):
         "scaling": "strong" if wl == "gemm" else "weak", "vs_baseline": None,
         "dtype": "f32" if wl == "gemm" else ("u8" if wl == "aes" else "u32"), "data": "synthetic",
         "config": {"workload": WORKLOAD_NAMES[wl], "units_per_step": n, "protection": {"aes": "-DWC + injector", }.get(wl, "-TMR -countErrors -countSyncs"),
-                   "note": "reference C sources compiled in place (oracle/_ref) + restated xMR wrapper for sha256; oracle port for the "
-                           "other workloads; the real opt -TMR binary needs LLVM 7 (absent). A step is a bounded sample of the GPU arm's batch."},
+                   "note": "reference C sources compiled in place (oracle/_ref) + restated xMR wrapper (sha256, crc16, aes; aes flips go "
+                           "into a replica's input copy); oracle port for the fp32 matmul; the real opt -TMR binary needs LLVM 7 "
+                           "(absent). A step is a bounded sample of the GPU arm's batch."},
         "cpu_baseline": {"value": round(val, 3), "unit": "MB/s", "cores": threads, "kind": kind,
                          "sample": f"{n} units per step, {threads} pthreads"},
         "e2e": {"value": round(val, 3), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
