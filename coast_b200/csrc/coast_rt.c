@@ -684,7 +684,7 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int call_
     { const char* e = getenv("COAST_HOST_CHUNK_BYTES"); if (e && atoll(e) > 0) max_chunk_bytes = (uint64_t)atoll(e); }   /* tuning knob */
     const uint64_t min_chunk = ((1ull << 20) / ib) > 1024ull ? ((1ull << 20) / ib) : 1024ull;
     const uint64_t max_chunk = (max_chunk_bytes / ib) > min_chunk ? (max_chunk_bytes / ib) : min_chunk;
-    const uint64_t chunk = max_chunk;                          /* slot buffers are sized for the largest chunk */
+    const uint64_t chunk = max_chunk < d->n_units ? max_chunk : d->n_units;   /* slot buffers: the largest chunk this call can make */
     uint64_t ramp = min_chunk;
     uint64_t done = 0; int slot = 0;
     while (done < d->n_units) {

@@ -1,0 +1,70 @@
+"""Child process of tests/test_host_logic.py: drives libcoast_rt.so against the mock driver (tests/mock_cuda/mock_cuda.c).
+Usage: python child.py <scenario-json>.  Prints one JSON object."""
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from coast_b200 import runtime as R  # noqa: E402  (structs + argtypes only; torch is never imported here)
+
+
+def main():
+    sc = json.loads(sys.argv[1])
+    L = R.load_library()
+    L.coast_malloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    L.coast_free.argtypes = [C.c_void_p]
+    res = {"init": L.coast_init(0)}
+    if res["init"]:
+        res["error"] = L.coast_last_error().decode()
+        print(json.dumps(res))
+        return
+
+    def dmalloc(n):
+        p = C.c_void_p()
+        rc = L.coast_malloc(C.byref(p), n)
+        assert rc == 0, L.coast_last_error()
+        return p.value
+
+    out = []
+    for op in sc["ops"]:
+        kind = op["op"]
+        d = R.LaunchDesc()
+        d.kernel, d.num_clones, d.flags, d.mode = op.get("kernel", 0), op.get("nc", 3), op.get("flags", 0), op.get("mode", 0)
+        d.n_units, d.unit_base, d.unit_bytes = op.get("n", 0), op.get("unit_base", 0), op.get("unit_bytes", 0)
+        d.M, d.N, d.K = op.get("M", 0), op.get("N", 0), op.get("K", 0)
+        plan = None
+        if op.get("p"):
+            plan = R._Plan(); plan.mode = 1; plan.seed_lo = 7; plan.threshold = int(op["p"] * 2 ** 32)
+            d.plan = C.pointer(plan)
+        if kind == "launch":
+            bufs = [dmalloc(max(op["in_bytes"], 16)), dmalloc(max(op["out_bytes"], 16))]
+            d.d_in, d.d_out = bufs[0] + op.get("misalign", 0), bufs[1]
+            if op.get("aux_bytes"):
+                bufs.append(dmalloc(op["aux_bytes"]))
+                d.d_aux = bufs[2]
+            rc = L.coast_launch(C.byref(d), None)
+            st = R._Stats()
+            rc2 = L.coast_sync_noabort(None, C.byref(st)) if rc == 0 else 0
+            for b in bufs:
+                L.coast_free(b)
+            out.append({"rc": rc, "sync_rc": rc2, "err": L.coast_last_error().decode() if rc else ""})
+        elif kind == "run_host":
+            h_in = (C.c_uint8 * max(op["in_bytes"], 1))()
+            h_out = (C.c_uint8 * max(op["out_bytes"], 1))()
+            for i in range(0, op["in_bytes"], 4099):
+                h_in[i] = (i * 7 + 1) & 0xFF
+            d.d_in, d.d_out = C.addressof(h_in), C.addressof(h_out)
+            st = R._Stats()
+            rc = L.coast_run_host_noabort(C.byref(d), C.byref(st))
+            out.append({"rc": rc, "err": L.coast_last_error().decode() if rc else "", "host_in": C.addressof(h_in),
+                        "host_out": C.addressof(h_out), "first_fault_unit": st.first_fault_unit})
+        elif kind == "shutdown":
+            out.append({"rc": L.coast_shutdown()})
+    res["ops"] = out
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

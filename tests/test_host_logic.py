@@ -1,0 +1,208 @@
+"""Host logic of libcoast_rt.so (coast_b200/csrc/coast_rt.c) on a GPU-less box, against a MOCK driver
+(tests/mock_cuda/mock_cuda.c, test infrastructure: it runs no workload, it records and bounds-checks driver calls):
+launch geometry and shared memory within sm_100 limits, tensor maps inside the caller's buffers, the argument block every
+kernel receives, the chunk schedule of coast_run_host() (every byte copied exactly once, per-chunk unit_base), scratch and
+staging memory released, loud failures for bad arguments and for a non-sm_100 device."""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+K_CRC16, K_SHA256, K_AES128, K_MM_U32, K_GEMM_TF32, K_QSORT, K_CHSTONE_SHA = range(7)
+
+
+class XmrArgs(C.Structure):                     # coast_b200/csrc/xmr_args.h
+    _fields_ = [("inp", C.c_uint64), ("out", C.c_uint64), ("aux", C.c_uint64), ("n_units", C.c_uint64), ("unit_base", C.c_uint64),
+                ("counters", C.c_uint64), ("plan_table", C.c_uint64), ("status", C.c_uint64),
+                ("unit_bytes", C.c_uint32), ("flags", C.c_uint32), ("mode", C.c_uint32), ("M", C.c_uint32), ("N", C.c_uint32),
+                ("K", C.c_uint32), ("plan_mode", C.c_uint32), ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32),
+                ("threshold", C.c_uint32), ("n_sites", C.c_uint32), ("n_tiles", C.c_uint32), ("key", C.c_uint8 * 16)]
+
+
+@pytest.fixture(scope="session")
+def mock_dir(tmp_path_factory, built_lib):
+    d = tmp_path_factory.mktemp("mockcuda")
+    subprocess.run(["gcc", "-O1", "-shared", "-fPIC", "-Wall", "-I/usr/local/cuda/include", "-o", str(d / "libcuda.so.1"),
+                    os.path.join(ROOT, "tests", "mock_cuda", "mock_cuda.c")], check=True)
+    return d
+
+
+def run_child(mock_dir, tmp_path, ops, env_extra=None):
+    log = tmp_path / "mock.log"
+    env = dict(os.environ, LD_LIBRARY_PATH=f"{mock_dir}:" + os.environ.get("LD_LIBRARY_PATH", ""), MOCK_CUDA_LOG=str(log))
+    env.update(env_extra or {})
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock_cuda", "child.py"), json.dumps({"ops": ops})],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    events = [json.loads(ln) for ln in open(log)] if log.exists() else []
+    return json.loads(res.stdout.strip().splitlines()[-1]), events
+
+
+def args_of(ev):
+    assert sizeof_args() == 128
+    return XmrArgs.from_buffer_copy(bytes.fromhex(ev["arg0"]))
+
+
+def sizeof_args():
+    return C.sizeof(XmrArgs)
+
+
+def test_argument_block_mirror_matches_the_header():
+    src = open(os.path.join(ROOT, "coast_b200", "csrc", "xmr_args.h")).read()
+    assert sizeof_args() == 128 and "unsigned char key[16];" in src and src.index("n_tiles") < src.index("key[16]")
+
+
+@pytest.mark.parametrize("kernel,nc,n,ub,in_b,out_b,want", [
+    (K_SHA256, 3, 100000, 64, 6400000, 3200000, ("xmr_sha256_b64_seg_nc3_inj0", 384, 128)),
+    (K_SHA256, 2, 100000, 64, 6400000, 3200000, ("xmr_sha256_b64_nc2_inj0", 256, 128)),
+    (K_SHA256, 3, 1000, 100, 100000, 32000, ("xmr_sha256_gen_nc3_inj0", 256, None)),
+    (K_CRC16, 3, 100000, 64, 6400000, 200000, ("xmr_crc16_b64_nc3_inj0", 1024, 320)),
+    (K_CRC16, 1, 100000, 64, 6400000, 200000, ("xmr_crc16_b64_nc1_inj0", 768, 768)),
+    (K_CRC16, 3, 5, 13, 65, 10, ("xmr_crc16_gen_nc3_inj0", 256, None)),
+    (K_AES128, 2, 1 << 20, 0, 16 << 20, 16 << 20, ("xmr_aes128_enc_nc2_inj0", 512, 1024)),
+    (K_QSORT, 3, 5000, 2320, 5000 * 2320, 5000 * 2320, ("xmr_qsort_nc3_inj0", 128, None)),
+    (K_CHSTONE_SHA, 3, 300, 16384, 300 * 16384, 300 * 20, ("xmr_chsha_nc3_inj0", 256, None)),
+])
+def test_launch_geometry_and_argument_block(mock_dir, tmp_path, kernel, nc, n, ub, in_b, out_b, want):
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="launch", kernel=kernel, nc=nc, n=n, unit_bytes=ub, in_bytes=in_b, out_bytes=out_b,
+                                                  flags=3), dict(op="shutdown")])
+    assert res["init"] == 0 and res["ops"][0]["rc"] == 0, res
+    assert not [e for e in ev if e["op"] == "error"], ev
+    launches = [e for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
+    assert len(launches) == 1
+    la = launches[0]
+    name, block, tile_rows = want
+    assert la["name"] == name and la["block"] == block and la["smem"] <= 232448 and 1 <= la["grid"] <= 148 * 32 * 4
+    a = args_of(la)
+    assert a.n_units == n and a.unit_base == 0 and a.unit_bytes == ub and a.flags == 3 and a.plan_mode == 0
+    if tile_rows:                                           # TMA-tiled kernels: one tensor map over exactly the caller's rows
+        assert a.n_tiles == -(-n // tile_rows) and la["grid"] <= 148 * 8
+        tm = [e for e in ev if e["op"] == "tmap"]
+        assert len(tm) == 1 and tm[0]["dim1"] == n and tm[0]["box1"] <= 256 and tile_rows % tm[0]["box1"] == 0
+        assert tm[0]["box_bytes"] * (tile_rows // tm[0]["box1"]) * 2 + 64 <= la["smem"]     # two ring stages fit
+    if kernel == K_QSORT:                                   # per-unit scratch from the pool, released after the launch
+        big = [e for e in ev if e["op"] == "alloc" and e["bytes"] >= la["grid"] * 4 * 32 * ub]
+        assert big and a.aux != 0
+    assert ev[-1] == {"op": "exit", "live_allocations": 0}
+
+
+def test_injector_variant_and_plan_fields(mock_dir, tmp_path):
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="launch", kernel=K_AES128, nc=2, n=4096, in_bytes=65536, out_bytes=65536, p=2 ** -10)])
+    la = [e for e in ev if e["op"] == "launch" and "_nc" in e["name"]][0]
+    a = args_of(la)
+    assert la["name"] == "xmr_aes128_enc_nc2_inj1" and a.plan_mode == 1 and a.threshold == 1 << 22 and a.n_sites == 176
+
+
+@pytest.mark.parametrize("kernel,ub,ob,n", [(K_SHA256, 64, 32, 1), (K_SHA256, 64, 32, 1000), (K_SHA256, 64, 32, (1 << 20) + 123),
+                                            (K_CRC16, 13, 2, 7), (K_AES128, 16, 16, 300001), (K_CHSTONE_SHA, 16384, 20, 3)])
+def test_run_host_chunk_schedule_copies_every_byte_once(mock_dir, tmp_path, kernel, ub, ob, n):
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="run_host", kernel=kernel, nc=3 if kernel != K_AES128 else 2, n=n, unit_bytes=ub if kernel != K_AES128 else 0,
+                                                  in_bytes=n * ub, out_bytes=n * ob, unit_base=1000), dict(op="shutdown")])
+    r = res["ops"][0]
+    assert r["rc"] == 0, r
+    assert not [e for e in ev if e["op"] == "error"], [e for e in ev if e["op"] == "error"]
+    h2d = sorted((e["host"] - r["host_in"], e["bytes"]) for e in ev if e["op"] == "h2d")
+    d2h = sorted((e["host"] - r["host_out"], e["bytes"]) for e in ev if e["op"] == "d2h" and 0 <= e["host"] - r["host_out"] < n * ob)
+    for spans, total in ((h2d, n * ub), (d2h, n * ob)):
+        pos = 0
+        for off, nb in spans:
+            assert off == pos, (spans[:5], total)          # contiguous, no gap, no overlap
+            pos += nb
+        assert pos == total
+    launches = [e for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
+    done = 0
+    for la in launches:                                     # every chunk is keyed by its GLOBAL unit index
+        a = args_of(la)
+        assert a.unit_base == 1000 + done
+        done += a.n_units
+    assert done == n and len({la["stream"] for la in launches}) <= 3
+    assert ev[-1] == {"op": "exit", "live_allocations": 0}
+
+
+@pytest.mark.parametrize("op,needle", [
+    (dict(op="launch", kernel=K_CRC16, nc=3, n=10, unit_bytes=0, in_bytes=64, out_bytes=64), "crc16 length"),
+    (dict(op="launch", kernel=K_CRC16, nc=4, n=10, unit_bytes=8, in_bytes=80, out_bytes=64), "num_clones"),
+    (dict(op="launch", kernel=9, nc=3, n=10, unit_bytes=8, in_bytes=80, out_bytes=64), "unknown kernel"),
+    (dict(op="launch", kernel=K_CHSTONE_SHA, nc=3, n=2, unit_bytes=100, in_bytes=200, out_bytes=40), "64-byte blocks"),
+    (dict(op="launch", kernel=K_QSORT, nc=3, n=2, unit_bytes=4100, in_bytes=8200, out_bytes=8200), "quicksort arrays"),
+    (dict(op="launch", kernel=K_MM_U32, nc=3, n=81, M=9, N=9, K=9, in_bytes=324, out_bytes=324), "MM needs"),
+    (dict(op="launch", kernel=K_AES128, nc=2, n=4, in_bytes=80, out_bytes=64, misalign=4), "16-byte aligned"),
+])
+def test_bad_arguments_fail_loudly(mock_dir, tmp_path, op, needle):
+    res, ev = run_child(mock_dir, tmp_path, [op])
+    r = res["ops"][0]
+    assert r["rc"] != 0 and needle in r["err"], r
+    assert not [e for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
+
+
+def test_unaligned_sha_input_takes_the_general_kernel(mock_dir, tmp_path):
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="launch", kernel=K_SHA256, nc=3, n=100, unit_bytes=64, in_bytes=6500, out_bytes=3200, misalign=4)])
+    assert res["ops"][0]["rc"] == 0
+    assert [e["name"] for e in ev if e["op"] == "launch" and "_nc" in e["name"]] == ["xmr_sha256_gen_nc3_inj0"]
+    assert not [e for e in ev if e["op"] == "tmap"]
+
+
+def test_a_device_that_is_not_sm100_is_refused(mock_dir, tmp_path):
+    res, ev = run_child(mock_dir, tmp_path, [], env_extra={"MOCK_CUDA_CC_MAJOR": "9"})
+    assert res["init"] != 0 and "sm_100a code only" in res["error"]
+
+
+@pytest.mark.parametrize("M,N,K,nc,env,want", [
+    (256, 128, 256, 3, {}, ["xmr_mm_split_a", "xmr_mm_split_bt", "xmr_mm_u32_tct_nc3_inj0"]),       # TMR: A limb planes staged in TMEM
+    (256, 128, 256, 2, {}, ["xmr_mm_split_a", "xmr_mm_split_bt", "xmr_mm_u32_tc_nc2_inj0"]),
+    (256, 128, 256, 3, {"COAST_MM_PATH": "tiled"}, ["xmr_mm_u32_tiled_nc3_inj0"]),
+    (64, 128, 48, 3, {}, ["xmr_mm_u32_tiled_nc3_inj0"]),                                              # not 128/64/128-aligned
+    (9, 9, 9, 3, {}, ["xmr_mm_u32_nc3_inj0"]),                                                        # the reference's own size
+])
+def test_exact_matmul_path_selection_and_tensor_maps(mock_dir, tmp_path, M, N, K, nc, env, want):
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="launch", kernel=K_MM_U32, nc=nc, n=M * N, M=M, N=N, K=K, in_bytes=M * K * 4,
+                                                  aux_bytes=K * N * 4, out_bytes=M * N * 4, flags=3), dict(op="shutdown")], env_extra=env)
+    assert res["ops"][0]["rc"] == 0, res
+    assert not [e for e in ev if e["op"] == "error"], [e for e in ev if e["op"] == "error"]
+    names = [e["name"] for e in ev if e["op"] == "launch" and e["name"] not in ("xmr_counters_reset",)]
+    assert names == want
+    if "split" in want[0]:
+        tm = [e for e in ev if e["op"] == "tmap"]
+        assert len(tm) == 2 and all(t["elem"] == 1 and t["rank"] == 3 and t["box0"] == 128 for t in tm)   # u8 limb planes, 128-byte k rows
+    la = [e for e in ev if e["op"] == "launch" and "_nc" in e["name"]][0]
+    assert la["smem"] <= 232448 and la["grid"] <= max(148, (M // 64) * (N // 128))
+    assert ev[-1] == {"op": "exit", "live_allocations": 0}
+
+
+def test_tf32_gemm_launch(mock_dir, tmp_path):
+    s = 512
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="launch", kernel=K_GEMM_TF32, nc=3, n=s * s, M=s, N=s, K=s, in_bytes=s * s * 4,
+                                                  aux_bytes=s * s * 4, out_bytes=s * s * 4, flags=3)])
+    assert res["ops"][0]["rc"] == 0 and not [e for e in ev if e["op"] == "error"]
+    la = [e for e in ev if e["op"] == "launch" and "_nc" in e["name"]][0]
+    assert la["name"] == "xmr_gemm_tf32_nc3_inj0" and la["block"] == 256 and la["grid"] == 16 and la["smem"] <= 232448
+    tm = [e for e in ev if e["op"] == "tmap"]
+    assert [t["rank"] for t in tm] == [2, 3] and tm[1]["swizzle"] != tm[0]["swizzle"]      # B: the 32-byte-atom swizzle of the MN-major operand
+    bad, _ = run_child(mock_dir, tmp_path, [dict(op="launch", kernel=K_GEMM_TF32, nc=3, n=100 * 128, M=100, N=128, K=64, in_bytes=100 * 64 * 4,
+                                                  aux_bytes=64 * 128 * 4, out_bytes=100 * 128 * 4)])
+    assert bad["ops"][0]["rc"] != 0 and "multiples of 128" in bad["ops"][0]["err"]
+
+
+def test_quicksort_through_the_host_call_uses_one_scratch_slot_per_chunk(mock_dir, tmp_path):
+    n, L = 3000, 580
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="run_host", kernel=K_QSORT, nc=3, n=n, unit_bytes=4 * L, in_bytes=n * 4 * L,
+                                                  out_bytes=n * 4 * L), dict(op="shutdown")])
+    assert res["ops"][0]["rc"] == 0 and not [e for e in ev if e["op"] == "error"]
+    launches = [e for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
+    assert sum(args_of(la).n_units for la in launches) == n and all(args_of(la).aux for la in launches)
+    assert ev[-1] == {"op": "exit", "live_allocations": 0}
+
+
+def test_host_call_staging_is_bounded_by_the_call_not_by_the_largest_chunk(mock_dir, tmp_path):
+    """one 64 MiB CHStone stream, and a 1-unit crc16 call: the staging slots must not be sized for 1024 units"""
+    big = 64 << 20
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="run_host", kernel=K_CHSTONE_SHA, nc=3, n=1, unit_bytes=big, in_bytes=big, out_bytes=20),
+                                             dict(op="run_host", kernel=K_CRC16, nc=3, n=1, unit_bytes=13, in_bytes=13, out_bytes=2),
+                                             dict(op="shutdown")])
+    assert [r["rc"] for r in res["ops"]] == [0, 0, 0], res
+    assert max(e["bytes"] for e in ev if e["op"] == "alloc") <= big + 4096
+    assert ev[-1] == {"op": "exit", "live_allocations": 0}
