@@ -673,7 +673,9 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int call_
         return sync_impl(G.hs[0], out, call_handler);
     }
     const uint64_t ib = in_bytes_per_unit(d);
-    if (!ib || !ob) return fail(COAST_ERR_UNSUPPORTED, "coast_run_host: kernel %u", d->kernel);
+    /* a zero-length SHA-256 message (sha256_hash(len = 0) hashes one padded block) has nothing to stage */
+    if (!ob || (!ib && d->kernel != COAST_K_SHA256)) return fail(COAST_ERR_UNSUPPORTED, "coast_run_host: kernel %u", d->kernel);
+    const uint64_t ibs = ib ? ib : 1;                          /* divisor of the chunk schedule */
     const int per_unit_key = d->kernel == COAST_K_AES128 && (d->mode & COAST_AES_KEY_PER_UNIT);
     /* each chunk is its own launch (own tensor map); the fault plan is keyed by the global unit index so
      * chunking never changes results */
@@ -682,8 +684,8 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int call_
      * down.  So chunks ramp 1,2,4,8,16,16,... MiB and shrink again towards the end (each at most half of what remains). */
     uint64_t max_chunk_bytes = 16ull << 20;
     { const char* e = getenv("COAST_HOST_CHUNK_BYTES"); if (e && atoll(e) > 0) max_chunk_bytes = (uint64_t)atoll(e); }   /* tuning knob */
-    const uint64_t min_chunk = ((1ull << 20) / ib) > 1024ull ? ((1ull << 20) / ib) : 1024ull;
-    const uint64_t max_chunk = (max_chunk_bytes / ib) > min_chunk ? (max_chunk_bytes / ib) : min_chunk;
+    const uint64_t min_chunk = ((1ull << 20) / ibs) > 1024ull ? ((1ull << 20) / ibs) : 1024ull;
+    const uint64_t max_chunk = (max_chunk_bytes / ibs) > min_chunk ? (max_chunk_bytes / ibs) : min_chunk;
     const uint64_t chunk = max_chunk < d->n_units ? max_chunk : d->n_units;   /* slot buffers: the largest chunk this call can make */
     uint64_t ramp = min_chunk;
     uint64_t done = 0; int slot = 0;
@@ -694,9 +696,9 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int call_
         if (n < min_chunk) n = min_chunk;
         if (n > left) n = left;
         ramp *= 2;
-        rc = slot_reserve(&G.h_in[slot], &G.h_in_cap[slot], (size_t)(chunk * ib)); if (rc) return rc;
+        rc = slot_reserve(&G.h_in[slot], &G.h_in_cap[slot], (size_t)(chunk * ib) > 16 ? (size_t)(chunk * ib) : 16); if (rc) return rc;
         rc = slot_reserve(&G.h_out[slot], &G.h_out_cap[slot], (size_t)(chunk * ob)); if (rc) return rc;
-        DRV(p_cuMemcpyHtoDAsync_v2(G.h_in[slot], (const uint8_t*)d->d_in + done * ib, (size_t)(n * ib), G.hs[slot]));
+        if (ib) DRV(p_cuMemcpyHtoDAsync_v2(G.h_in[slot], (const uint8_t*)d->d_in + done * ib, (size_t)(n * ib), G.hs[slot]));
         coast_launch_desc c = *d;
         c.d_in = (void*)G.h_in[slot]; c.d_out = (void*)G.h_out[slot];
         c.n_units = n; c.unit_base = d->unit_base + done;

@@ -60,6 +60,34 @@ def main():
             rc = L.coast_run_host_noabort(C.byref(d), C.byref(st))
             out.append({"rc": rc, "err": L.coast_last_error().decode() if rc else "", "host_in": C.addressof(h_in),
                         "host_out": C.addressof(h_out), "first_fault_unit": st.first_fault_unit})
+        elif kind == "run_host_aux":                        # AES with per-unit keys (+ write-back), or a matmul: three host buffers
+            h_in = (C.c_uint8 * op["in_bytes"])()
+            h_aux = (C.c_uint8 * op["aux_bytes"])()
+            h_out = (C.c_uint8 * op["out_bytes"])()
+            d.d_in, d.d_aux, d.d_out = C.addressof(h_in), C.addressof(h_aux), C.addressof(h_out)
+            st = R._Stats()
+            rc = L.coast_run_host_noabort(C.byref(d), C.byref(st))
+            out.append({"rc": rc, "err": L.coast_last_error().decode() if rc else "", "host_in": C.addressof(h_in),
+                        "host_aux": C.addressof(h_aux), "host_out": C.addressof(h_out)})
+        elif kind == "entries":                             # the reference-facing entry points (what the make flow binds)
+            L.coast_set_opt_passes(op.get("passes", "-TMR -countErrors").encode())
+            msg = b"Automated TMR"
+            crc = L.coast_xmr_crc16(msg, len(msg))
+            L.coast_xmr_sha256_hash.argtypes = [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p]
+            cd, bl, stt, data, dig = (C.c_uint8 * 64)(), (C.c_uint32 * 2)(), (C.c_uint32 * 8)(), (C.c_uint8 * 10)(), (C.c_uint8 * 32)()
+            L.coast_xmr_sha256_hash(cd, bl, stt, data, 10, dig)
+            L.coast_xmr_sha256_hash(cd, bl, stt, data, 0, dig)          # empty message: still one padded block
+            state, key = (C.c_uint8 * 16)(), (C.c_uint8 * 16)()
+            L.coast_xmr_aes_enc_dec.argtypes = [C.c_void_p, C.c_void_p, C.c_ubyte]
+            L.coast_xmr_aes_enc_dec(state, key, 0)
+            L.coast_xmr_aes_enc_dec(state, key, 1)
+            f, s2, r = (C.c_uint32 * 81)(), (C.c_uint32 * 81)(), (C.c_uint32 * 81)()
+            L.coast_xmr_matrix_multiply_u32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+            L.coast_xmr_matrix_multiply_u32(f, s2, r, 9)
+            indata, in_i, dg = (C.c_uint8 * 16384)(), (C.c_int * 2)(8192, 8192), (C.c_uint32 * 5)()
+            L.coast_xmr_chstone_sha_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+            L.coast_xmr_chstone_sha_stream(indata, in_i, 2, 8192, dg)
+            out.append({"rc": 0, "crc": crc, "tmr_error_cnt": C.c_uint32.in_dll(L, "TMR_ERROR_CNT").value})
         elif kind == "shutdown":
             out.append({"rc": L.coast_shutdown()})
     res["ops"] = out

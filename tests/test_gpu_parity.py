@@ -546,3 +546,14 @@ def test_quicksort_reference_golden_vectors_on_device(rt, oracle, golden):
         a = np.array(rec["input"], dtype=np.int32)
         out, _ = both(rt, oracle, oracle.K_QSORT, 3, a, 1, unit_bytes=4 * len(a))
         assert np.frombuffer(out.tobytes(), dtype=np.int32).tolist() == rec["sorted"]
+
+
+def test_empty_message_through_the_reference_entry_point(rt):
+    """sha256_hash(len = 0) (sha256_common_tmr.c:101-180 hashes one padded block): the host call has nothing to stage"""
+    import ctypes as C
+    L = rt.L
+    assert L.coast_set_opt_passes(b"-TMR -countErrors") == 0
+    digest = C.create_string_buffer(32)
+    cd, bl, stt, msg = C.create_string_buffer(64), (C.c_uint32 * 2)(), (C.c_uint32 * 8)(), C.create_string_buffer(4)
+    L.coast_xmr_sha256_hash(cd, bl, stt, msg, 0, digest)
+    assert digest.raw == hashlib.sha256(b"").digest()

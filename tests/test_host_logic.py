@@ -206,3 +206,44 @@ def test_host_call_staging_is_bounded_by_the_call_not_by_the_largest_chunk(mock_
     assert [r["rc"] for r in res["ops"]] == [0, 0, 0], res
     assert max(e["bytes"] for e in ev if e["op"] == "alloc") <= big + 4096
     assert ev[-1] == {"op": "exit", "live_allocations": 0}
+
+
+def test_reference_entry_points_drive_the_host_call(mock_dir, tmp_path):
+    """crc16 / sha256_hash (10 bytes and empty) / aes_enc_dec both directions / matrix_multiply 9x9 / sha_stream: one protected
+    launch each with the mode of OPT_PASSES, buffers staged and released"""
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="entries", passes="-TMR -countErrors"), dict(op="shutdown")])
+    assert res["ops"][0]["rc"] == 0 and not [e for e in ev if e["op"] == "error"], [e for e in ev if e["op"] == "error"]
+    names = [e["name"] for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
+    assert names == ["xmr_crc16_gen_nc3_inj0", "xmr_sha256_gen_nc3_inj0", "xmr_sha256_gen_nc3_inj0", "xmr_aes128_gen_nc3_inj0",
+                     "xmr_aes128_gen_nc3_inj0", "xmr_mm_u32_nc3_inj0", "xmr_chsha_nc3_inj0"]
+    args = [args_of(e) for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
+    assert [a.unit_bytes for a in args[:3]] == [13, 10, 0] and all(a.n_units == 1 for a in args[:5]) and args[5].n_units == 81
+    assert args[3].mode == 2 | 4 and args[4].mode == 1 | 2 | 4          # per-unit key + write-back (+ decrypt): key[] is mutated in place
+    assert args[6].unit_bytes == 16384 and all(a.flags & 1 for a in args)
+    assert ev[-1] == {"op": "exit", "live_allocations": 0}
+
+
+def test_aes_per_unit_keys_with_write_back_through_the_host_call(mock_dir, tmp_path):
+    n = 200000
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="run_host_aux", kernel=K_AES128, nc=2, n=n, mode=2 | 4, in_bytes=16 * n, aux_bytes=16 * n,
+                                                  out_bytes=16 * n), dict(op="shutdown")])
+    r = res["ops"][0]
+    assert r["rc"] == 0 and not [e for e in ev if e["op"] == "error"]
+    for key, direction in (("host_in", "h2d"), ("host_aux", "h2d"), ("host_out", "d2h"), ("host_aux", "d2h")):
+        spans = sorted((e["host"] - r[key], e["bytes"]) for e in ev if e["op"] == direction and 0 <= e["host"] - r[key] < 16 * n)
+        pos = 0
+        for off, nb in spans:
+            assert off == pos
+            pos += nb
+        assert pos == 16 * n, (key, direction)
+    assert ev[-1] == {"op": "exit", "live_allocations": 0}
+
+
+def test_matmul_through_the_host_call_is_one_shot(mock_dir, tmp_path):
+    M = N = K = 128
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="run_host_aux", kernel=K_MM_U32, nc=3, n=M * N, M=M, N=N, K=K, in_bytes=M * K * 4,
+                                                  aux_bytes=K * N * 4, out_bytes=M * N * 4), dict(op="shutdown")])
+    assert res["ops"][0]["rc"] == 0 and not [e for e in ev if e["op"] == "error"]
+    assert [e["bytes"] for e in ev if e["op"] == "h2d"] == [M * K * 4, K * N * 4]
+    assert [e["bytes"] for e in ev if e["op"] == "d2h" and e["bytes"] > 64] == [M * N * 4]
+    assert ev[-1] == {"op": "exit", "live_allocations": 0}
