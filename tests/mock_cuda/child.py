@@ -15,7 +15,11 @@ def main():
     L = R.load_library()
     L.coast_malloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     L.coast_free.argtypes = [C.c_void_p]
-    res = {"init": L.coast_init(0)}
+    pre = None
+    if sc.get("before_init"):                               # compute calls before coast_init must fail loudly, not crash
+        d0 = R.LaunchDesc(); d0.kernel = 1; d0.num_clones = 3; d0.n_units = 1; d0.unit_bytes = 64
+        pre = {"launch": L.coast_launch(C.byref(d0), None), "err": L.coast_last_error().decode()}
+    res = {"init": L.coast_init(0), "before_init": pre}
     if res["init"]:
         res["error"] = L.coast_last_error().decode()
         print(json.dumps(res))
@@ -88,6 +92,27 @@ def main():
             L.coast_xmr_chstone_sha_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
             L.coast_xmr_chstone_sha_stream(indata, in_i, 2, 8192, dg)
             out.append({"rc": 0, "crc": crc, "tmr_error_cnt": C.c_uint32.in_dll(L, "TMR_ERROR_CNT").value})
+        elif kind == "misc":
+            r = {}
+            r["reinit_same"] = L.coast_init(0)
+            r["reinit_other"] = L.coast_init(1)
+            buf = dmalloc(4096)
+            r["fill0"] = L.coast_fill_philox(buf, 0, 0, 1, None)
+            r["fill"] = L.coast_fill_philox(buf, 1024, 5, 1, None)
+            r["snapshot"] = L.coast_stats_snapshot(None, buf)
+            st = R._Stats()
+            d.kernel, d.num_clones, d.n_units, d.unit_bytes = 1, 3, 0, 64
+            h = (C.c_uint8 * 64)()
+            d.d_in, d.d_out = C.addressof(h), C.addressof(h)
+            r["run_host_empty"] = L.coast_run_host_noabort(C.byref(d), C.byref(st))
+            r["stats"] = [st.errors_corrected, st.dwc_detected, st.syncs, st.injected, st.first_fault_unit]
+            tp = R._Plan(); tp.mode = 2
+            d.n_units = 4; d.plan = C.pointer(tp)
+            r["run_host_table"] = L.coast_run_host_noabort(C.byref(d), C.byref(st)); r["run_host_table_err"] = L.coast_last_error().decode()
+            d.d_in, d.d_out = buf, buf
+            r["launch_table_without_table"] = L.coast_launch(C.byref(d), None); r["launch_table_err"] = L.coast_last_error().decode()
+            L.coast_free(buf)
+            out.append(r)
         elif kind == "shutdown":
             out.append({"rc": L.coast_shutdown()})
     res["ops"] = out

@@ -247,3 +247,41 @@ def test_matmul_through_the_host_call_is_one_shot(mock_dir, tmp_path):
     assert [e["bytes"] for e in ev if e["op"] == "h2d"] == [M * K * 4, K * N * 4]
     assert [e["bytes"] for e in ev if e["op"] == "d2h" and e["bytes"] > 64] == [M * N * 4]
     assert ev[-1] == {"op": "exit", "live_allocations": 0}
+
+
+def test_lifecycle_and_small_api_calls(mock_dir, tmp_path):
+    log = tmp_path / "mock.log"
+    env = dict(os.environ, LD_LIBRARY_PATH=f"{mock_dir}:" + os.environ.get("LD_LIBRARY_PATH", ""), MOCK_CUDA_LOG=str(log))
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock_cuda", "child.py"),
+                          json.dumps({"before_init": True, "ops": [dict(op="misc"), dict(op="shutdown")]})],
+                         capture_output=True, text=True, env=env, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    assert out["before_init"]["launch"] != 0 and "coast_init" in out["before_init"]["err"]
+    r = out["ops"][0]
+    assert r["reinit_same"] == 0 and r["reinit_other"] != 0
+    assert r["fill0"] == 0 and r["fill"] == 0 and r["snapshot"] == 0
+    assert r["run_host_empty"] == 0 and r["stats"] == [0, 0, 0, 0, 2 ** 64 - 1]
+    assert r["run_host_table"] != 0 and "TABLE" in r["run_host_table_err"]
+    assert r["launch_table_without_table"] != 0 and "d_table" in r["launch_table_err"]
+    ev = [json.loads(ln) for ln in open(log)]
+    assert not [e for e in ev if e["op"] == "error"] and ev[-1] == {"op": "exit", "live_allocations": 0}
+
+
+@pytest.mark.parametrize("flags,mode,nc,want", [
+    (3 | 0x8, 0, 3, "xmr_sha256_b64_nc3_inj0"),             # -i: replicas on adjacent lanes
+    (3 | 0x10, 0, 3, "xmr_sha256_b64_seg_nc3_inj0"),        # -s (also the default)
+    (3, 0, 1, "xmr_sha256_b64_nc1_inj0"),
+])
+def test_sha_layout_flags_select_the_kernel(mock_dir, tmp_path, flags, mode, nc, want):
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="launch", kernel=K_SHA256, nc=nc, n=5000, unit_bytes=64, in_bytes=320000, out_bytes=160000,
+                                                  flags=flags)])
+    assert [e["name"] for e in ev if e["op"] == "launch" and "_nc" in e["name"]] == [want]
+
+
+def test_aes_decrypt_and_per_unit_keys_use_the_general_kernel(mock_dir, tmp_path):
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="launch", kernel=K_AES128, nc=2, n=1000, mode=1, in_bytes=16000, out_bytes=16000),
+                                             dict(op="launch", kernel=K_AES128, nc=2, n=1000, mode=2, in_bytes=16000, out_bytes=16000, aux_bytes=16000),
+                                             dict(op="launch", kernel=K_AES128, nc=2, n=1000, mode=2, in_bytes=16000, out_bytes=16000)])
+    assert [r["rc"] == 0 for r in res["ops"]] == [True, True, False] and "per-unit keys need d_aux" in res["ops"][2]["err"]
+    assert [e["name"] for e in ev if e["op"] == "launch" and "_nc" in e["name"]] == ["xmr_aes128_gen_nc2_inj0"] * 2
