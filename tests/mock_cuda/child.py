@@ -113,6 +113,21 @@ def main():
             r["launch_table_without_table"] = L.coast_launch(C.byref(d), None); r["launch_table_err"] = L.coast_last_error().decode()
             L.coast_free(buf)
             out.append(r)
+        elif kind == "sync_fold":                           # counters -> the reference's run-time symbols
+            buf = dmalloc(1 << 16)
+            d.kernel, d.num_clones, d.n_units, d.unit_bytes, d.flags = 1, op.get("nc", 3), 100, 64, 3
+            d.d_in, d.d_out = buf, buf
+            r = {"launch": L.coast_launch(C.byref(d), None)}
+            st = R._Stats()
+            r["sync"] = (L.coast_sync if op.get("abort") else L.coast_sync_noabort)(None, C.byref(st))
+            r["stats"] = [st.errors_corrected, st.dwc_detected, st.syncs, st.injected, st.first_fault_unit]
+            r["TMR_ERROR_CNT"] = C.c_uint32.in_dll(L, "TMR_ERROR_CNT").value
+            r["SYNC_COUNT"] = C.c_uint64.in_dll(L, "__SYNC_COUNT").value
+            st2 = R._Stats()
+            L.coast_sync_noabort(None, C.byref(st2))        # counters were reset by the first sync
+            r["second"] = [st2.errors_corrected, st2.dwc_detected, st2.syncs, st2.injected, st2.first_fault_unit]
+            L.coast_free(buf)
+            out.append(r)
         elif kind == "shutdown":
             out.append({"rc": L.coast_shutdown()})
     res["ops"] = out

@@ -123,6 +123,15 @@ CUresult cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, uns
         for (int i = 0; i < (is_args ? 128 : 8); ++i) fprintf(logf, "%02x", p[i]);
         fprintf(logf, "\"}\n"); fflush(logf);
     }
+    const char* tally = getenv("MOCK_CUDA_TALLY");                        /* "errors,dwc,syncs,injected,first": what a kernel would have counted */
+    if (tally && strncmp(fn->name, "xmr_", 4) == 0 && strstr(fn->name, "_nc")) {
+        unsigned long long v[5] = { 0, 0, 0, 0, ~0ull };
+        sscanf(tally, "%llu,%llu,%llu,%llu,%llu", &v[0], &v[1], &v[2], &v[3], &v[4]);
+        unsigned long long* c = *(unsigned long long**)((const unsigned char*)params[0] + 40);   /* xmr_args.counters */
+        if (find_alloc((uintptr_t)c, 5 * 8) < 0) return bad("counters pointer in the argument block");
+        for (int i = 0; i < 4; ++i) c[i] += v[i];
+        if (v[4] < c[4]) c[4] = v[4];
+    }
     if (!strcmp(fn->name, "xmr_counters_reset")) {                         /* the one kernel whose effect the host relies on */
         unsigned long long* c = *(unsigned long long**)params[0];
         if (find_alloc((uintptr_t)c, 5 * 8) < 0) return bad("counters pointer");

@@ -285,3 +285,25 @@ def test_aes_decrypt_and_per_unit_keys_use_the_general_kernel(mock_dir, tmp_path
                                              dict(op="launch", kernel=K_AES128, nc=2, n=1000, mode=2, in_bytes=16000, out_bytes=16000)])
     assert [r["rc"] == 0 for r in res["ops"]] == [True, True, False] and "per-unit keys need d_aux" in res["ops"][2]["err"]
     assert [e["name"] for e in ev if e["op"] == "launch" and "_nc" in e["name"]] == ["xmr_aes128_gen_nc2_inj0"] * 2
+
+
+def test_sync_folds_counters_into_the_reference_symbols(mock_dir, tmp_path):
+    """coast_sync(): device counters -> coast_stats, TMR_ERROR_CNT (an i32 in the reference: wraps, synchronization.cpp:1428-1431),
+    __SYNC_COUNT (i64), and the counters start from zero again"""
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="sync_fold"), dict(op="sync_fold"), dict(op="shutdown")],
+                        env_extra={"MOCK_CUDA_TALLY": f"{2 ** 32 + 5},0,3200,7,41"})
+    a, b = res["ops"][0], res["ops"][1]
+    assert a["launch"] == 0 and a["sync"] == 0 and a["stats"] == [2 ** 32 + 5, 0, 3200, 7, 41]
+    assert a["TMR_ERROR_CNT"] == 5 and a["SYNC_COUNT"] == 3200 and a["second"] == [0, 0, 0, 0, 2 ** 64 - 1]
+    assert b["TMR_ERROR_CNT"] == 10 and b["SYNC_COUNT"] == 6400         # the symbols accumulate over the program, like the pass's globals
+
+
+def test_dwc_detection_calls_the_handler_which_aborts_by_default(mock_dir, tmp_path):
+    """FAULT_DETECTED_DWC() (synchronization.cpp:1251-1266: default = abort()) is called by coast_sync, not by coast_sync_noabort"""
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="sync_fold", nc=2)], env_extra={"MOCK_CUDA_TALLY": "0,3,0,3,17"})
+    assert res["ops"][0]["stats"][:2] == [0, 3] and res["ops"][0]["stats"][4] == 17
+    log = tmp_path / "mock2.log"
+    env = dict(os.environ, LD_LIBRARY_PATH=f"{mock_dir}:" + os.environ.get("LD_LIBRARY_PATH", ""), MOCK_CUDA_LOG=str(log), MOCK_CUDA_TALLY="0,3,0,3,17")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock_cuda", "child.py"), json.dumps({"ops": [dict(op="sync_fold", nc=2, abort=True)]})],
+                       capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == -6 and "FAULT_DETECTED_DWC" in r.stderr          # SIGABRT, as the reference's protected binary
