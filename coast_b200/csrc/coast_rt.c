@@ -16,11 +16,15 @@
 #include "xmr_args.h"
 
 #include <cuda.h>
+#include <ctype.h>
 #include <dlfcn.h>
+#include <sched.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 extern const unsigned char coast_kernels_cubin[];   /* generated: bin2c of coast_kernels.cubin */
 
@@ -41,6 +45,8 @@ __attribute__((weak)) void FAULT_DETECTED_DWC(void) { /* synchronization.cpp:125
     X(cuInit, (unsigned int))                                                                                \
     X(cuDeviceGet, (CUdevice*, int))                                                                         \
     X(cuDeviceGetAttribute, (int*, CUdevice_attribute, CUdevice))                                            \
+    X(cuDeviceGetPCIBusId, (char*, int, CUdevice))                                                           \
+    X(cuPointerGetAttribute, (void*, CUpointer_attribute, CUdeviceptr))                                      \
     X(cuDevicePrimaryCtxRetain, (CUcontext*, CUdevice))                                                      \
     X(cuDevicePrimaryCtxRelease_v2, (CUdevice))                                                              \
     X(cuCtxSetCurrent, (CUcontext))                                                                          \
@@ -97,9 +103,21 @@ static struct {
     CUstream hs[3]; CUdeviceptr h_in[3], h_out[3], h_aux[3]; size_t h_in_cap[3], h_out_cap[3], h_aux_cap[3];
     /* stream-ordered scratch (the replicas' private arrays of xmr_qsort.cuh): any number of streams may launch at once */
     CUmemoryPool pool;
-    /* limb planes of the tensor-core exact matmul (xmr_mm_tc.cuh) */
-    CUdeviceptr mm_planes; size_t mm_planes_cap;
+    CUdeviceptr h_stat[3]; size_t h_stat_cap[3];     /* per-slot d_status staging of coast_run_host */
+    int numa_node;                   /* NUMA node the process was bound to by coast_init (-1: not bound) */
+    int busy;                        /* one host thread at a time (the reference is single-threaded); others fail loudly */
+    /* tensor maps of the row-tiled kernels, keyed by (base, row bytes, rows, box rows, swizzle): coast_run_host re-encodes the
+     * same few maps every call */
+    struct { const void* base; uint32_t row_bytes, box_rows; uint64_t rows; int swz; CUtensorMap map; } tmaps[16];
+    int n_tmaps, tmap_next;
+    int zero_copy_default;           /* host-call path for pinned buffers: 1 = one zero-copy launch, 0 = staged chunks */
 } G;
+
+/* Single-caller guard.  The reference's emitted code is single-threaded (plain load/add/store on its counters,
+ * synchronization.cpp:1428-1431) and so is this runtime: one counter block, one set of host-call slots.  A second host
+ * thread entering while a call is in progress gets COAST_ERR_BUSY instead of a silent race. */
+static int enter(void);
+static void leave(void) { __atomic_store_n(&G.busy, 0, __ATOMIC_RELEASE); }
 
 static int fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt);
@@ -107,6 +125,15 @@ static int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+static int enter(void) {
+    if (__atomic_exchange_n(&G.busy, 1, __ATOMIC_ACQUIRE)) {
+        /* do not touch G.err: the call in progress owns it */
+        return COAST_ERR_BUSY;
+    }
+    return COAST_OK;
+}
+#define ENTER() do { int e_ = enter(); if (e_) return e_; } while (0)
+#define LEAVE(rc) do { int l_ = (rc); leave(); return l_; } while (0)
 static int drv_fail(CUresult r, const char* what) {
     const char* s = NULL;
     if (p_cuGetErrorString) p_cuGetErrorString(r, &s);
@@ -131,6 +158,58 @@ static int bind_driver(void) {
     G.libcuda = h;
     return COAST_OK;
 }
+
+
+/* ------------------------------------------------------------------ */
+/* NUMA placement                                                        */
+/* ------------------------------------------------------------------ */
+/* The host-call path (coast_run_host) is PCIe-bound; on a two-socket box a process that runs -- and first-touches its
+ * pinned buffers -- on the socket the GPU is NOT attached to loses up to half of the copy bandwidth (measured r01: 1.69 vs
+ * 3.16 ms per 96 MiB step on two boxes).  coast_init() therefore moves the calling thread (threads it creates later inherit
+ * it) onto the CPUs of the GPU's NUMA node and makes that node the preferred one for its memory.  Plain syscalls, no
+ * libnuma.  COAST_NUMA_BIND=0 leaves the process alone.  Best effort: any failure leaves things as they were. */
+#ifndef MPOL_PREFERRED
+#define MPOL_PREFERRED 1
+#endif
+static int parse_cpulist(const char* s, cpu_set_t* set) {
+    int n = 0;
+    CPU_ZERO(set);
+    while (*s) {
+        while (*s == ',' || isspace((unsigned char)*s)) ++s;
+        if (!isdigit((unsigned char)*s)) break;
+        char* e; long a = strtol(s, &e, 10), b = a;
+        if (*e == '-') b = strtol(e + 1, &e, 10);
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET((int)c, set); ++n; }
+        s = e;
+    }
+    return n;
+}
+static void numa_bind_to_gpu(void) {
+    G.numa_node = -1;
+    const char* env = getenv("COAST_NUMA_BIND");
+    if (env && !strcmp(env, "0")) return;
+    char bdf[32] = {0}, path[128], buf[4096];
+    if (p_cuDeviceGetPCIBusId(bdf, (int)sizeof bdf - 1, G.dev) != CUDA_SUCCESS) return;
+    for (char* c = bdf; *c; ++c) *c = (char)tolower((unsigned char)*c);
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bdf);
+    FILE* f = fopen(path, "r"); if (!f) return;
+    int node = -1; if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f);
+    if (node < 0 || node >= 1024) return;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r"); if (!f) return;
+    size_t got = fread(buf, 1, sizeof buf - 1, f); fclose(f); buf[got] = 0;
+    cpu_set_t want, cur, both;
+    if (!parse_cpulist(buf, &want)) return;
+    if (sched_getaffinity(0, sizeof cur, &cur)) return;
+    CPU_AND(&both, &want, &cur);                       /* never widen a cpuset the launcher (cgroup, taskset) imposed */
+    if (!CPU_COUNT(&both)) return;
+    if (sched_setaffinity(0, sizeof both, &both)) return;
+    unsigned long mask[16]; memset(mask, 0, sizeof mask);
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    syscall(SYS_set_mempolicy, MPOL_PREFERRED, mask, (unsigned long)(8 * sizeof mask));   /* a refusal only costs locality */
+    G.numa_node = node;
+}
+int coast_numa_node(void) { return G.inited ? G.numa_node : -1; }
 
 static int ensure_ctx(void) {
     if (!G.inited) return fail(COAST_ERR_NOT_INIT, "coast_init() has not been called");
@@ -170,13 +249,14 @@ static int launch_small(const char* name, unsigned grid, unsigned block, void** 
     return COAST_OK;
 }
 
-int coast_stats_reset(void* stream) {
+static int stats_reset_impl(void* stream) {
     int rc = ensure_ctx(); if (rc) return rc;
     void* params[] = { &G.counters };
     return launch_small("xmr_counters_reset", 1, 32, params, (CUstream)stream);
 }
+int coast_stats_reset(void* stream) { ENTER(); LEAVE(stats_reset_impl(stream)); }
 
-int coast_init(int device) {
+static int init_impl(int device) {
     if (G.inited) {
         if (device == G.device) return ensure_ctx();
         return fail(COAST_ERR_BAD_ARG, "coast_rt already initialised on device %d", G.device);
@@ -195,6 +275,8 @@ int coast_init(int device) {
         return fail(COAST_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library carries sm_100a code only", device, major, minor);
     }
     p_cuDeviceGetAttribute(&G.sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, G.dev);
+    numa_bind_to_gpu();
+    G.zero_copy_default = 1;
     r = p_cuModuleLoadData(&G.mod, coast_kernels_cubin);
     if (r != CUDA_SUCCESS) { p_cuDevicePrimaryCtxRelease_v2(G.dev); return drv_fail(r, "cuModuleLoadData(sm_100a cubin)"); }
     DRV(p_cuMemAlloc_v2(&G.counters, XMR_CTR_COUNT * sizeof(uint64_t)));
@@ -209,25 +291,27 @@ int coast_init(int device) {
     DRV(p_cuMemHostAlloc((void**)&G.h_counters, XMR_CTR_COUNT * sizeof(uint64_t), 0));
     G.device = device;
     G.inited = 1;
-    rc = coast_stats_reset(NULL); if (rc) return rc;
+    rc = stats_reset_impl(NULL); if (rc) return rc;
     DRV(p_cuStreamSynchronize(NULL));
     const char* env = getenv("COAST_OPT_PASSES");
     if (env && !G.def_set) coast_set_opt_passes(env);
     return COAST_OK;
 }
+int coast_init(int device) { ENTER(); LEAVE(init_impl(device)); }
 
-int coast_shutdown(void) {
+static int shutdown_impl(void) {
     if (!G.inited) return COAST_OK;
     ensure_ctx();
     for (int i = 0; i < 3; ++i) {
         if (G.h_in[i]) p_cuMemFree_v2(G.h_in[i]);
         if (G.h_out[i]) p_cuMemFree_v2(G.h_out[i]);
         if (G.h_aux[i]) p_cuMemFree_v2(G.h_aux[i]);
+        if (G.h_stat[i]) p_cuMemFree_v2(G.h_stat[i]);
         if (G.hs[i]) p_cuStreamDestroy_v2(G.hs[i]);
-        G.h_in[i] = G.h_out[i] = G.h_aux[i] = 0; G.h_in_cap[i] = G.h_out_cap[i] = G.h_aux_cap[i] = 0; G.hs[i] = NULL;
+        G.h_in[i] = G.h_out[i] = G.h_aux[i] = G.h_stat[i] = 0;
+        G.h_in_cap[i] = G.h_out_cap[i] = G.h_aux_cap[i] = G.h_stat_cap[i] = 0; G.hs[i] = NULL;
     }
-    if (G.mm_planes) p_cuMemFree_v2(G.mm_planes);
-    G.mm_planes = 0; G.mm_planes_cap = 0;
+    G.n_tmaps = G.tmap_next = 0;
     p_cuMemFree_v2(G.counters);
     if (G.pool) { p_cuMemPoolDestroy(G.pool); G.pool = NULL; }
     p_cuMemFreeHost(G.h_counters);
@@ -236,6 +320,7 @@ int coast_shutdown(void) {
     G.inited = 0; G.n_fns = 0;
     return COAST_OK;
 }
+int coast_shutdown(void) { ENTER(); LEAVE(shutdown_impl()); }
 
 /* ------------------------------------------------------------------ */
 /* OPT_PASSES front end (dataflowProtection.cpp:14-47 cl::opt names)     */
@@ -328,8 +413,8 @@ static unsigned ring_smem(unsigned tile_rows, unsigned row_bytes) {
     return XMR_STAGES * stride + 64u;
 }
 
-static int encode_rows_map(CUtensorMap* map, const void* base, uint32_t row_bytes, uint64_t rows, uint32_t box_rows,
-                           CUtensorMapSwizzle swz) {
+static int encode_rows_map_uncached(CUtensorMap* map, const void* base, uint32_t row_bytes, uint64_t rows, uint32_t box_rows,
+                                    CUtensorMapSwizzle swz) {
     cuuint64_t gdim[2] = { row_bytes / 4u, rows };
     cuuint64_t gstr[1] = { row_bytes };
     cuuint32_t box[2] = { row_bytes / 4u, box_rows };
@@ -337,6 +422,21 @@ static int encode_rows_map(CUtensorMap* map, const void* base, uint32_t row_byte
     DRV(p_cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)base, gdim, gstr, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+    return COAST_OK;
+}
+
+/* A tensor map is a pure function of (base, geometry); the host-call path re-creates the same handful every call, so the
+ * last 16 are kept (round-robin replacement). */
+static int encode_rows_map(CUtensorMap* map, const void* base, uint32_t row_bytes, uint64_t rows, uint32_t box_rows,
+                           CUtensorMapSwizzle swz) {
+    for (int i = 0; i < G.n_tmaps; ++i)
+        if (G.tmaps[i].base == base && G.tmaps[i].rows == rows && G.tmaps[i].row_bytes == row_bytes &&
+            G.tmaps[i].box_rows == box_rows && G.tmaps[i].swz == (int)swz) { *map = G.tmaps[i].map; return COAST_OK; }
+    int rc = encode_rows_map_uncached(map, base, row_bytes, rows, box_rows, swz); if (rc) return rc;
+    const int n_slots = (int)(sizeof G.tmaps / sizeof G.tmaps[0]);
+    int k = G.n_tmaps < n_slots ? G.n_tmaps++ : (G.tmap_next++ % n_slots);
+    G.tmaps[k].base = base; G.tmaps[k].rows = rows; G.tmaps[k].row_bytes = row_bytes; G.tmaps[k].box_rows = box_rows;
+    G.tmaps[k].swz = (int)swz; G.tmaps[k].map = *map;
     return COAST_OK;
 }
 
@@ -377,15 +477,8 @@ static int launch_gemm_tf32(const coast_launch_desc* d, xmr_args* a, int inj, CU
 
 /* Exact integer matmul on tcgen05 kind::i8 (xmr_mm_tc.cuh): split A and B into u8 limb planes (library scratch),
  * then ten u8 GEMMs per replica into four s32 TMEM accumulators, recombined modulo 2^32 in the epilogue. */
-static int launch_mm_tc(const coast_launch_desc* d, xmr_args* a, int inj, CUstream stream, int atmem) {
+static int launch_mm_tc_planes(const coast_launch_desc* d, xmr_args* a, int inj, CUstream stream, int atmem, CUdeviceptr pa, CUdeviceptr pb) {
     const uint32_t nc = d->num_clones, bn = atmem ? (nc == 1 ? 64u : 32u) : (nc == 3 ? 32u : 64u);
-    const size_t a_bytes = (size_t)d->M * d->K * 4u, b_bytes = (size_t)d->K * d->N * 4u;   /* 4 planes of 1 byte per element */
-    if (G.mm_planes_cap < a_bytes + b_bytes) {
-        if (G.mm_planes) { DRV(p_cuStreamSynchronize(stream)); DRV(p_cuMemFree_v2(G.mm_planes)); G.mm_planes = 0; G.mm_planes_cap = 0; }
-        DRV(p_cuMemAlloc_v2(&G.mm_planes, a_bytes + b_bytes));
-        G.mm_planes_cap = a_bytes + b_bytes;
-    }
-    CUdeviceptr pa = G.mm_planes, pb = G.mm_planes + a_bytes;
     {
         CUfunction f; int rc = get_fn("xmr_mm_split_a", 0, &f, NULL); if (rc) return rc;
         unsigned long long rows = d->M, K = d->K; const void* A = d->d_in;
@@ -427,8 +520,19 @@ static int launch_mm_tc(const coast_launch_desc* d, xmr_args* a, int inj, CUstre
     DRV(p_cuLaunchKernel(fn, grid, 1, 1, 256, 1, 1, smem, stream, params, NULL));
     return COAST_OK;
 }
+/* The limb planes (4 x u8 per element of A and of B^T) are per-launch scratch from the stream-ordered pool, like the
+ * quicksort replicas: allocated on the launch's stream, released on it after the kernel, so launches on different
+ * streams never share planes.  The pool keeps released memory cached, so steady state costs no driver allocation. */
+static int launch_mm_tc(const coast_launch_desc* d, xmr_args* a, int inj, CUstream stream, int atmem) {
+    const size_t a_bytes = (size_t)d->M * d->K * 4u, b_bytes = (size_t)d->K * d->N * 4u;   /* 4 planes of 1 byte per element */
+    CUdeviceptr planes = 0;
+    DRV(p_cuMemAllocFromPoolAsync(&planes, a_bytes + b_bytes, G.pool, stream));
+    int rc = launch_mm_tc_planes(d, a, inj, stream, atmem, planes, planes + a_bytes);
+    p_cuMemFreeAsync(planes, stream);
+    return rc;
+}
 
-int coast_launch(const coast_launch_desc* d, void* stream) {
+static int launch_impl(const coast_launch_desc* d, void* stream) {
     int rc = ensure_ctx(); if (rc) return rc;
     if (!d) return fail(COAST_ERR_BAD_ARG, "null descriptor");
     if (d->kernel >= COAST_K_COUNT_) return fail(COAST_ERR_BAD_ARG, "unknown kernel id %u", d->kernel);
@@ -591,10 +695,12 @@ int coast_launch(const coast_launch_desc* d, void* stream) {
 /* ------------------------------------------------------------------ */
 /* counters                                                             */
 /* ------------------------------------------------------------------ */
-static int sync_impl(void* stream, coast_stats* out, int call_handler) {
+/* Folds the device counters into *out and the reference's globals; *dwc_fired tells the guarded wrappers to call the
+ * handler AFTER the single-caller guard is released (a user handler may longjmp or call back into the library). */
+static int sync_impl(void* stream, coast_stats* out, int* dwc_fired) {
     int rc = ensure_ctx(); if (rc) return rc;
     DRV(p_cuMemcpyDtoHAsync_v2(G.h_counters, G.counters, XMR_CTR_COUNT * sizeof(uint64_t), (CUstream)stream));
-    rc = coast_stats_reset(stream); if (rc) return rc;
+    rc = stats_reset_impl(stream); if (rc) return rc;
     DRV(p_cuStreamSynchronize((CUstream)stream));
     coast_stats st;
     st.errors_corrected = G.h_counters[XMR_CTR_ERRORS];
@@ -605,17 +711,26 @@ static int sync_impl(void* stream, coast_stats* out, int call_handler) {
     TMR_ERROR_CNT += (uint32_t)st.errors_corrected;          /* i32 wrap, synchronization.cpp:1428-1431 */
     __SYNC_COUNT += st.syncs;
     if (out) *out = st;
-    if (call_handler && st.dwc_detected) FAULT_DETECTED_DWC();   /* synchronization.cpp:1299-1302 */
+    if (dwc_fired) *dwc_fired = st.dwc_detected != 0;
     return COAST_OK;
 }
-int coast_sync(void* stream, coast_stats* out) { return sync_impl(stream, out, 1); }
-int coast_sync_noabort(void* stream, coast_stats* out) { return sync_impl(stream, out, 0); }
+static int sync_guarded(void* stream, coast_stats* out, int call_handler) {
+    ENTER();
+    int fired = 0, rc = sync_impl(stream, out, &fired);
+    leave();
+    if (!rc && call_handler && fired) FAULT_DETECTED_DWC();   /* synchronization.cpp:1299-1302 */
+    return rc;
+}
+int coast_sync(void* stream, coast_stats* out) { return sync_guarded(stream, out, 1); }
+int coast_sync_noabort(void* stream, coast_stats* out) { return sync_guarded(stream, out, 0); }
+int coast_launch(const coast_launch_desc* d, void* stream) { ENTER(); LEAVE(launch_impl(d, stream)); }
 
 int coast_stats_snapshot(void* stream, void* d_stats_out) {
-    int rc = ensure_ctx(); if (rc) return rc;
-    if (!d_stats_out) return fail(COAST_ERR_BAD_ARG, "null d_stats_out");
-    DRV(p_cuMemcpyDtoDAsync_v2((CUdeviceptr)d_stats_out, G.counters, XMR_CTR_COUNT * sizeof(uint64_t), (CUstream)stream));
-    return COAST_OK;
+    ENTER();
+    int rc = ensure_ctx(); if (rc) LEAVE(rc);
+    if (!d_stats_out) LEAVE(fail(COAST_ERR_BAD_ARG, "null d_stats_out"));
+    CUresult r = p_cuMemcpyDtoDAsync_v2((CUdeviceptr)d_stats_out, G.counters, XMR_CTR_COUNT * sizeof(uint64_t), (CUstream)stream);
+    LEAVE(r == CUDA_SUCCESS ? COAST_OK : drv_fail(r, "cuMemcpyDtoDAsync(counters)"));
 }
 
 /* ------------------------------------------------------------------ */
@@ -632,7 +747,7 @@ int coast_stream_create(void** s) { int rc = ensure_ctx(); if (rc) return rc; CU
 int coast_stream_destroy(void* s) { int rc = ensure_ctx(); if (rc) return rc; DRV(p_cuStreamDestroy_v2((CUstream)s)); return COAST_OK; }
 int coast_stream_sync(void* s) { int rc = ensure_ctx(); if (rc) return rc; DRV(p_cuStreamSynchronize((CUstream)s)); return COAST_OK; }
 
-int coast_fill_philox(void* d_dst, uint64_t n_words, uint64_t word_base, uint32_t seed, void* stream) {
+static int fill_philox_impl(void* d_dst, uint64_t n_words, uint64_t word_base, uint32_t seed, void* stream) {
     int rc = ensure_ctx(); if (rc) return rc;
     if (!n_words) return COAST_OK;
     unsigned long long nw = n_words, wb = word_base;
@@ -640,6 +755,10 @@ int coast_fill_philox(void* d_dst, uint64_t n_words, uint64_t word_base, uint32_
     uint64_t blks = (n_words + 3) / 4 + 1;
     uint64_t ctas = (blks + 255) / 256, cap = (uint64_t)G.sm_count * 16;
     return launch_small("xmr_fill_philox", (unsigned)(ctas < cap ? ctas : cap), 256, params, (CUstream)stream);
+}
+
+int coast_fill_philox(void* d_dst, uint64_t n_words, uint64_t word_base, uint32_t seed, void* stream) {
+    ENTER(); LEAVE(fill_philox_impl(d_dst, n_words, word_base, seed, stream));
 }
 
 /* ------------------------------------------------------------------ */
@@ -654,41 +773,47 @@ static int slot_reserve(CUdeviceptr* p, size_t* cap, size_t need) {
     return COAST_OK;
 }
 
-static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int call_handler) {
-    int rc = ensure_ctx(); if (rc) return rc;
-    if (!d) return fail(COAST_ERR_BAD_ARG, "null descriptor");
-    if (d->plan && d->plan->mode == COAST_PLAN_TABLE) return fail(COAST_ERR_UNSUPPORTED, "coast_run_host: TABLE plans need device pointers; use coast_launch");
-    for (int i = 0; i < 3; ++i) if (!G.hs[i]) DRV(p_cuStreamCreate(&G.hs[i], CU_STREAM_NON_BLOCKING));
-    const uint64_t ob = coast_out_bytes(d->kernel, d->unit_bytes);
-    if (d->kernel == COAST_K_MM_U32 || d->kernel == COAST_K_GEMM_TF32) {   /* one shot: A, B in; C out */
-        size_t ab = (size_t)d->M * d->K * 4, bb = (size_t)d->K * d->N * 4, cb = (size_t)d->M * d->N * 4;
-        rc = slot_reserve(&G.h_in[0], &G.h_in_cap[0], ab); if (rc) return rc;
-        rc = slot_reserve(&G.h_aux[0], &G.h_aux_cap[0], bb); if (rc) return rc;
-        rc = slot_reserve(&G.h_out[0], &G.h_out_cap[0], cb); if (rc) return rc;
-        DRV(p_cuMemcpyHtoDAsync_v2(G.h_in[0], d->d_in, ab, G.hs[0]));
-        DRV(p_cuMemcpyHtoDAsync_v2(G.h_aux[0], d->d_aux, bb, G.hs[0]));
-        coast_launch_desc c = *d; c.d_in = (void*)G.h_in[0]; c.d_aux = (void*)G.h_aux[0]; c.d_out = (void*)G.h_out[0];
-        rc = coast_launch(&c, G.hs[0]); if (rc) return rc;
-        DRV(p_cuMemcpyDtoHAsync_v2(d->d_out, G.h_out[0], cb, G.hs[0]));
-        return sync_impl(G.hs[0], out, call_handler);
-    }
-    const uint64_t ib = in_bytes_per_unit(d);
-    /* a zero-length SHA-256 message (sha256_hash(len = 0) hashes one padded block) has nothing to stage */
-    if (!ob || (!ib && d->kernel != COAST_K_SHA256)) return fail(COAST_ERR_UNSUPPORTED, "coast_run_host: kernel %u", d->kernel);
+/* Device-visible alias of a HOST pointer, or 0.  Pinned host memory (cuMemHostAlloc / cudaHostAlloc / cudaHostRegister;
+ * torch's pin_memory()) is mapped into the GPU's address space under UVA, so a kernel -- and the TMA unit -- can read and
+ * write it over PCIe directly. */
+static CUdeviceptr host_alias(const void* h, size_t bytes) {
+    if (!h || !bytes) return 0;
+    unsigned int mt = 0;
+    if (p_cuPointerGetAttribute(&mt, CU_POINTER_ATTRIBUTE_MEMORY_TYPE, (CUdeviceptr)(uintptr_t)h) != CUDA_SUCCESS) return 0;
+    if (mt != CU_MEMORYTYPE_HOST) return 0;
+    CUdeviceptr d0 = 0, d1 = 0;
+    if (p_cuPointerGetAttribute(&d0, CU_POINTER_ATTRIBUTE_DEVICE_POINTER, (CUdeviceptr)(uintptr_t)h) != CUDA_SUCCESS || !d0) return 0;
+    /* the last byte must belong to a mapped range too (a view that runs past a registration is not ours to read) */
+    if (p_cuPointerGetAttribute(&d1, CU_POINTER_ATTRIBUTE_DEVICE_POINTER, (CUdeviceptr)((uintptr_t)h + bytes - 1)) != CUDA_SUCCESS ||
+        d1 != d0 + (bytes - 1)) return 0;
+    return d0;
+}
+
+static int drain_host_streams(void) {
+    CUresult r0 = p_cuStreamSynchronize(G.hs[0]), r1 = p_cuStreamSynchronize(G.hs[1]), r2 = p_cuStreamSynchronize(G.hs[2]);
+    CUresult r = r0 != CUDA_SUCCESS ? r0 : r1 != CUDA_SUCCESS ? r1 : r2;
+    return r == CUDA_SUCCESS ? COAST_OK : drv_fail(r, "cuStreamSynchronize(host-call streams)");
+}
+
+/* Chunked pipeline: H2D -> kernel -> D2H per chunk, chunks round-robin over 3 streams / 3 staging slots. */
+static int run_host_staged(const coast_launch_desc* d, uint64_t ib, uint64_t ob, int per_unit_key) {
+    int rc;
     const uint64_t ibs = ib ? ib : 1;                          /* divisor of the chunk schedule */
-    const int per_unit_key = d->kernel == COAST_K_AES128 && (d->mode & COAST_AES_KEY_PER_UNIT);
     /* each chunk is its own launch (own tensor map); the fault plan is keyed by the global unit index so
      * chunking never changes results */
     /* Chunk schedule measured on the B200 box (tools/e2e_chunk_sweep.py): 8-16 MiB chunks stream best (~12 us of driver
      * work per chunk), but a fixed size leaves the copy engines idle while the first chunk goes up and the last comes
-     * down.  So chunks ramp 1,2,4,8,16,16,... MiB and shrink again towards the end (each at most half of what remains). */
+     * down.  So chunks ramp 1,2,4,8,16,16,... MiB and shrink again towards the end (each at most half of what remains).
+     * Chunks are bounded in BYTES: a unit larger than the bound (a long CHStone stream, a long SHA message) is a chunk
+     * of its own, so the staging slots never exceed max(16 MiB, one unit) each. */
     uint64_t max_chunk_bytes = 16ull << 20;
     { const char* e = getenv("COAST_HOST_CHUNK_BYTES"); if (e && atoll(e) > 0) max_chunk_bytes = (uint64_t)atoll(e); }   /* tuning knob */
-    const uint64_t min_chunk = ((1ull << 20) / ibs) > 1024ull ? ((1ull << 20) / ibs) : 1024ull;
+    const uint64_t min_chunk = ((1ull << 20) / ibs) > 1ull ? ((1ull << 20) / ibs) : 1ull;
     const uint64_t max_chunk = (max_chunk_bytes / ibs) > min_chunk ? (max_chunk_bytes / ibs) : min_chunk;
     const uint64_t chunk = max_chunk < d->n_units ? max_chunk : d->n_units;   /* slot buffers: the largest chunk this call can make */
     uint64_t ramp = min_chunk;
     uint64_t done = 0; int slot = 0;
+#define STEP(call) do { CUresult r_ = (call); if (r_ != CUDA_SUCCESS) { rc = drv_fail(r_, #call); goto fail; } } while (0)
     while (done < d->n_units) {
         const uint64_t left = d->n_units - done;
         uint64_t n = ramp < max_chunk ? ramp : max_chunk;          /* ramp up */
@@ -696,28 +821,101 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int call_
         if (n < min_chunk) n = min_chunk;
         if (n > left) n = left;
         ramp *= 2;
-        rc = slot_reserve(&G.h_in[slot], &G.h_in_cap[slot], (size_t)(chunk * ib) > 16 ? (size_t)(chunk * ib) : 16); if (rc) return rc;
-        rc = slot_reserve(&G.h_out[slot], &G.h_out_cap[slot], (size_t)(chunk * ob)); if (rc) return rc;
-        if (ib) DRV(p_cuMemcpyHtoDAsync_v2(G.h_in[slot], (const uint8_t*)d->d_in + done * ib, (size_t)(n * ib), G.hs[slot]));
+        rc = slot_reserve(&G.h_in[slot], &G.h_in_cap[slot], (size_t)(chunk * ib) > 16 ? (size_t)(chunk * ib) : 16); if (rc) goto fail;
+        rc = slot_reserve(&G.h_out[slot], &G.h_out_cap[slot], (size_t)(chunk * ob)); if (rc) goto fail;
+        if (ib) STEP(p_cuMemcpyHtoDAsync_v2(G.h_in[slot], (const uint8_t*)d->d_in + done * ib, (size_t)(n * ib), G.hs[slot]));
         coast_launch_desc c = *d;
         c.d_in = (void*)G.h_in[slot]; c.d_out = (void*)G.h_out[slot];
         c.n_units = n; c.unit_base = d->unit_base + done;
         if (per_unit_key) {
-            rc = slot_reserve(&G.h_aux[slot], &G.h_aux_cap[slot], (size_t)(chunk * 16)); if (rc) return rc;
-            DRV(p_cuMemcpyHtoDAsync_v2(G.h_aux[slot], (const uint8_t*)d->d_aux + done * 16, (size_t)(n * 16), G.hs[slot]));
+            rc = slot_reserve(&G.h_aux[slot], &G.h_aux_cap[slot], (size_t)(chunk * 16)); if (rc) goto fail;
+            STEP(p_cuMemcpyHtoDAsync_v2(G.h_aux[slot], (const uint8_t*)d->d_aux + done * 16, (size_t)(n * 16), G.hs[slot]));
             c.d_aux = (void*)G.h_aux[slot];
         }
-        rc = coast_launch(&c, G.hs[slot]); if (rc) return rc;
-        DRV(p_cuMemcpyDtoHAsync_v2((uint8_t*)d->d_out + done * ob, G.h_out[slot], (size_t)(n * ob), G.hs[slot]));
+        if (d->d_status) {                                         /* kernels index status[] chunk-locally: stage it per slot */
+            rc = slot_reserve(&G.h_stat[slot], &G.h_stat_cap[slot], (size_t)chunk); if (rc) goto fail;
+            c.d_status = (void*)G.h_stat[slot];
+        }
+        rc = launch_impl(&c, G.hs[slot]); if (rc) goto fail;
+        STEP(p_cuMemcpyDtoHAsync_v2((uint8_t*)d->d_out + done * ob, G.h_out[slot], (size_t)(n * ob), G.hs[slot]));
         if (per_unit_key && (d->mode & COAST_AES_KEY_WRITEBACK))
-            DRV(p_cuMemcpyDtoHAsync_v2((uint8_t*)d->d_aux + done * 16, G.h_aux[slot], (size_t)(n * 16), G.hs[slot]));
+            STEP(p_cuMemcpyDtoHAsync_v2((uint8_t*)d->d_aux + done * 16, G.h_aux[slot], (size_t)(n * 16), G.hs[slot]));
+        if (d->d_status) STEP(p_cuMemcpyDtoHAsync_v2((uint8_t*)d->d_status + done, G.h_stat[slot], (size_t)n, G.hs[slot]));
         done += n; slot = (slot + 1) % 3;
     }
-    DRV(p_cuStreamSynchronize(G.hs[0])); DRV(p_cuStreamSynchronize(G.hs[1]));
-    return sync_impl(G.hs[2], out, call_handler);
+#undef STEP
+    return COAST_OK;
+fail:
+    {   /* copies of earlier chunks may still be in flight on the caller's buffers: never return before they have landed */
+        char keep[sizeof G.err]; memcpy(keep, G.err, sizeof keep);
+        drain_host_streams();
+        memcpy(G.err, keep, sizeof keep);
+    }
+    return rc;
 }
-int coast_run_host(const coast_launch_desc* d, coast_stats* out) { return run_host_impl(d, out, 1); }
-int coast_run_host_noabort(const coast_launch_desc* d, coast_stats* out) { return run_host_impl(d, out, 0); }
+
+/* `d_in` / `d_out` / `d_aux` / `d_status` of the descriptor are HOST pointers here. */
+static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int* dwc_fired) {
+    int rc = ensure_ctx(); if (rc) return rc;
+    if (!d) return fail(COAST_ERR_BAD_ARG, "null descriptor");
+    if (d->plan && d->plan->mode == COAST_PLAN_TABLE) return fail(COAST_ERR_UNSUPPORTED, "coast_run_host: TABLE plans need device pointers; use coast_launch");
+    for (int i = 0; i < 3; ++i) if (!G.hs[i]) DRV(p_cuStreamCreate(&G.hs[i], CU_STREAM_NON_BLOCKING));
+    const uint64_t ob = coast_out_bytes(d->kernel, d->unit_bytes);
+    if (d->kernel == COAST_K_MM_U32 || d->kernel == COAST_K_GEMM_TF32) {   /* one shot: A, B in; C out */
+        if (d->d_status) return fail(COAST_ERR_UNSUPPORTED, "coast_run_host: d_status is not staged for the matmul kernels; use coast_launch");
+        size_t ab = (size_t)d->M * d->K * 4, bb = (size_t)d->K * d->N * 4, cb = (size_t)d->M * d->N * 4;
+        rc = slot_reserve(&G.h_in[0], &G.h_in_cap[0], ab); if (rc) return rc;
+        rc = slot_reserve(&G.h_aux[0], &G.h_aux_cap[0], bb); if (rc) return rc;
+        rc = slot_reserve(&G.h_out[0], &G.h_out_cap[0], cb); if (rc) return rc;
+        DRV(p_cuMemcpyHtoDAsync_v2(G.h_in[0], d->d_in, ab, G.hs[0]));
+        DRV(p_cuMemcpyHtoDAsync_v2(G.h_aux[0], d->d_aux, bb, G.hs[0]));
+        coast_launch_desc c = *d; c.d_in = (void*)G.h_in[0]; c.d_aux = (void*)G.h_aux[0]; c.d_out = (void*)G.h_out[0];
+        rc = launch_impl(&c, G.hs[0]);
+        if (rc) { char keep[sizeof G.err]; memcpy(keep, G.err, sizeof keep); p_cuStreamSynchronize(G.hs[0]); memcpy(G.err, keep, sizeof keep); return rc; }
+        DRV(p_cuMemcpyDtoHAsync_v2(d->d_out, G.h_out[0], cb, G.hs[0]));
+        return sync_impl(G.hs[0], out, dwc_fired);
+    }
+    const uint64_t ib = in_bytes_per_unit(d);
+    /* a zero-length SHA-256 message (sha256_hash(len = 0) hashes one padded block) has nothing to stage */
+    if (!ob || (!ib && d->kernel != COAST_K_SHA256)) return fail(COAST_ERR_UNSUPPORTED, "coast_run_host: kernel %u", d->kernel);
+    const int per_unit_key = d->kernel == COAST_K_AES128 && (d->mode & COAST_AES_KEY_PER_UNIT);
+    if (d->n_units == 0) return sync_impl(G.hs[2], out, dwc_fired);
+
+    /* ZERO-COPY path: when every host buffer is pinned (hence mapped into the GPU's address space) and the kernel reads
+     * each input byte exactly once, ONE launch streams the input over PCIe through the TMA ring / vector loads and
+     * writes the voted output straight back to host memory -- upload, compute and download overlap inside the kernel
+     * at tile granularity, no staging buffers, no chunk schedule.  COAST_HOST_PATH=staged|zerocopy overrides. */
+    const char* hp = getenv("COAST_HOST_PATH");
+    const int streams_once = d->kernel == COAST_K_CRC16 || d->kernel == COAST_K_SHA256 || d->kernel == COAST_K_AES128 ||
+                             d->kernel == COAST_K_CHSTONE_SHA;
+    if (streams_once && !(hp && !strcmp(hp, "staged")) && (G.zero_copy_default || (hp && !strcmp(hp, "zerocopy")))) {
+        CUdeviceptr zi = ib ? host_alias(d->d_in, (size_t)(d->n_units * ib)) : (CUdeviceptr)G.counters /* never read */;
+        CUdeviceptr zo = host_alias(d->d_out, (size_t)(d->n_units * ob));
+        CUdeviceptr za = per_unit_key ? host_alias(d->d_aux, (size_t)(d->n_units * 16)) : 0;
+        CUdeviceptr zs = d->d_status ? host_alias(d->d_status, (size_t)d->n_units) : 0;
+        if (zi && zo && (!per_unit_key || za) && (!d->d_status || zs)) {
+            coast_launch_desc c = *d;
+            c.d_in = (void*)zi; c.d_out = (void*)zo;
+            if (per_unit_key) c.d_aux = (void*)za;
+            if (d->d_status) c.d_status = (void*)zs;
+            rc = launch_impl(&c, G.hs[2]); if (rc) return rc;
+            return sync_impl(G.hs[2], out, dwc_fired);
+        }
+        if (hp && !strcmp(hp, "zerocopy")) return fail(COAST_ERR_BAD_ARG, "COAST_HOST_PATH=zerocopy needs pinned (mapped) host buffers");
+    }
+    rc = run_host_staged(d, ib, ob, per_unit_key); if (rc) return rc;
+    DRV(p_cuStreamSynchronize(G.hs[0])); DRV(p_cuStreamSynchronize(G.hs[1]));
+    return sync_impl(G.hs[2], out, dwc_fired);
+}
+static int run_host_guarded(const coast_launch_desc* d, coast_stats* out, int call_handler) {
+    ENTER();
+    int fired = 0, rc = run_host_impl(d, out, &fired);
+    leave();
+    if (!rc && call_handler && fired) FAULT_DETECTED_DWC();   /* synchronization.cpp:1299-1302 */
+    return rc;
+}
+int coast_run_host(const coast_launch_desc* d, coast_stats* out) { return run_host_guarded(d, out, 1); }
+int coast_run_host_noabort(const coast_launch_desc* d, coast_stats* out) { return run_host_guarded(d, out, 0); }
 
 /* ------------------------------------------------------------------ */
 /* the four reference entry points (what the unchanged tests call)      */
@@ -747,12 +945,32 @@ unsigned short coast_xmr_crc16(const unsigned char* data_p, unsigned char length
 }
 void coast_xmr_sha256_hash(unsigned char ctx_data[], uint32_t ctx_bitlen[], uint32_t ctx_state[], unsigned char data[],
                            uint32_t len, unsigned char hash[]) {
-    (void)ctx_data; (void)ctx_bitlen; (void)ctx_state;         /* scratch of the CPU formulation; replicas keep it in registers */
     coast_launch_desc d; memset(&d, 0, sizeof d);
     entry_mode(&d.num_clones, &d.flags);
     unsigned char dummy = 0;
     d.kernel = COAST_K_SHA256; d.n_units = 1; d.unit_bytes = len; d.d_in = len ? data : &dummy; d.d_out = hash;
     entry_run(&d);
+    /* The caller-visible scratch the reference leaves behind (sha256_common_tmr.c:101-180): replicas keep it in registers,
+     * so it is rebuilt here from the voted digest and the message -- marshalling, not computation.
+     *   ctx_state : the final chaining value = the digest words, big-endian (:169-178)
+     *   ctx_bitlen: {low, high} of 8*len (DBL_INT_ADD, :124,155)
+     *   ctx_data  : the last block fed to sha256_transform (:132-163) */
+    if (ctx_state)
+        for (int i = 0; i < 8; ++i)
+            ctx_state[i] = ((uint32_t)hash[4 * i] << 24) | ((uint32_t)hash[4 * i + 1] << 16) | ((uint32_t)hash[4 * i + 2] << 8) | hash[4 * i + 3];
+    const uint32_t lo = len << 3, hi = len >> 29;
+    if (ctx_bitlen) { ctx_bitlen[0] = lo; ctx_bitlen[1] = hi; }
+    if (ctx_data) {
+        const uint32_t rem = len & 63u;
+        if (rem < 56u) {
+            memcpy(ctx_data, data + (len - rem), rem);
+            ctx_data[rem] = 0x80; memset(ctx_data + rem + 1, 0, 55u - rem);
+        } else {
+            memset(ctx_data, 0, 56);                               /* the extra block: sha_memset(ctx_data, 0, 56) :142-150 */
+        }
+        ctx_data[63] = (unsigned char)lo; ctx_data[62] = (unsigned char)(lo >> 8); ctx_data[61] = (unsigned char)(lo >> 16); ctx_data[60] = (unsigned char)(lo >> 24);
+        ctx_data[59] = (unsigned char)hi; ctx_data[58] = (unsigned char)(hi >> 8); ctx_data[57] = (unsigned char)(hi >> 16); ctx_data[56] = (unsigned char)(hi >> 24);
+    }
 }
 void coast_xmr_aes_enc_dec(unsigned char* state, unsigned char* key, unsigned char dir) {
     coast_launch_desc d; memset(&d, 0, sizeof d);

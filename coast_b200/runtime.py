@@ -18,7 +18,7 @@ F_INTERLEAVE, F_SEGMENT, F_VERBOSE, F_MAJORITY_VOTER = 0x8, 0x10, 0x20, 0x100
 PLAN_NONE, PLAN_BERNOULLI, PLAN_TABLE = 0, 1, 2
 AES_DECRYPT, AES_KEY_PER_UNIT, AES_KEY_WRITEBACK = 1, 2, 4
 NO_FAULT_UNIT = 0xFFFFFFFFFFFFFFFF
-ERR_NO_DRIVER, ERR_NOT_INIT, ERR_BAD_ARG, ERR_UNSUPPORTED = -100001, -100002, -100003, -100004
+ERR_NO_DRIVER, ERR_NOT_INIT, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_BUSY = -100001, -100002, -100003, -100004, -100005
 
 OUT_BYTES = {K_CRC16: 2, K_SHA256: 32, K_AES128: 16, K_MM_U32: 4, K_GEMM_TF32: 4, K_CHSTONE_SHA: 20}
 
@@ -95,7 +95,7 @@ def lib_path() -> str:
 _LIB = None
 
 EXPORTS = [
-    "coast_init", "coast_shutdown", "coast_last_error", "coast_version", "coast_parse_opt_passes", "coast_launch",
+    "coast_init", "coast_numa_node", "coast_shutdown", "coast_last_error", "coast_version", "coast_parse_opt_passes", "coast_launch",
     "coast_sync", "coast_sync_noabort", "coast_stats_snapshot", "coast_stats_reset", "coast_fault_sites",
     "coast_fault_site_bits", "coast_out_bytes_per_unit", "coast_out_bytes", "coast_votes_per_unit", "coast_malloc", "coast_free",
     "coast_memcpy_h2d", "coast_memcpy_d2h", "coast_memset", "coast_host_alloc", "coast_host_free",

@@ -21,8 +21,12 @@
  * COAST_ERR_NO_DRIVER -- there is no CPU fallback in this library.
  *
  * Thread-safety: like the reference's emitted code (plain load/add/store on the
- * counters, synchronization.cpp:1428-1431) the host API is NOT thread-safe per
- * process; device counters are warp-reduced and atomically added.
+ * counters, synchronization.cpp:1428-1431) the host API is single-caller per
+ * process: one counter block, one set of host-call staging slots.  It does not
+ * race silently -- a second host thread that enters coast_init / coast_launch /
+ * coast_sync* / coast_run_host* / coast_stats_* / coast_fill_philox / coast_shutdown
+ * while a call is in progress gets COAST_ERR_BUSY.  Device counters are warp-reduced
+ * and atomically added.
  */
 #ifndef COAST_RT_H_
 #define COAST_RT_H_
@@ -138,8 +142,8 @@ typedef struct coast_fault_plan {
  *                 always the ORIGINAL cipher key, :112-129).
  *   MM_U32   in : A, M x K uint32 row-major; aux: B, K x N uint32 row-major
  *            out: C, M x N uint32; a unit is one C element, n_units must be M*N.  Exact modulo 2^32 on every
- *            path: tcgen05 kind::i8 on u8 limbs when M%128 == N%64 == K%128 == 0 (uses library-owned scratch for
- *            the limb planes: keep such launches on ONE stream), register-tiled CUDA cores when M%64 == N%128 ==
+ *            path: tcgen05 kind::i8 on u8 limbs when M%128 == N%64 == K%128 == 0 (limb planes are per-launch scratch
+ *            from a stream-ordered pool: any number of streams), register-tiled CUDA cores when M%64 == N%128 ==
  *            K%16 == 0, a plain kernel otherwise (e.g. the 9 x 9 tests).  COAST_MM_PATH=tc|tiled|naive overrides.
  *   GEMM_TF32 same with float.
  *   QSORT    in : n_units x unit_bytes, arrays of L = unit_bytes/4 int32 (L <= 1024)   out: the sorted arrays
@@ -169,7 +173,8 @@ typedef struct coast_launch_desc {
     const coast_fault_plan* plan; /* NULL = no injection                          */
     void*       d_status;  /* optional, n_units x uint8_t: per unit, the number of SoR-exit votes at which the
                               replicas disagreed (saturating at 255; 0 = all agreed).  This is the per-run "F:"
-                              field of the board report line (decoder.py:66) for campaign tooling.              */
+                              field of the board report line (decoder.py:66) for campaign tooling.  A device
+                              pointer for coast_launch, a host pointer for coast_run_host (not for the matmuls). */
 } coast_launch_desc;
 
 /* Counters of everything launched since the last coast_sync(). */
@@ -187,9 +192,13 @@ typedef struct coast_stats {
 #define COAST_ERR_NOT_INIT    (-100002)
 #define COAST_ERR_BAD_ARG     (-100003)
 #define COAST_ERR_UNSUPPORTED (-100004)
+#define COAST_ERR_BUSY        (-100005) /* another host thread is inside the library (single caller, see Thread-safety) */
 
 /* --- lifetime ------------------------------------------------------ */
-int  coast_init(int device);          /* bind libcuda, retain device's primary context, load the sm_100a module */
+int  coast_init(int device);          /* bind libcuda, retain device's primary context, load the sm_100a module; moves the
+                                         calling thread onto the CPUs of the GPU's NUMA node and prefers that node for its
+                                         memory (the host-call path is PCIe-bound); COAST_NUMA_BIND=0 disables that */
+int  coast_numa_node(void);           /* the node coast_init bound to, or -1 */
 int  coast_shutdown(void);
 const char* coast_last_error(void);   /* human-readable text of the last failure */
 const char* coast_version(void);
@@ -240,9 +249,18 @@ int  coast_stream_sync(void* stream);
 int  coast_fill_philox(void* d_dst, uint64_t n_words, uint64_t word_base, uint32_t seed, void* stream);
 
 /* --- host-buffer convenience: the reference-facing call -------------- */
-/* What the reference's protected function call becomes: host in -> H2D -> xMR kernel ->
- * D2H -> host out, counters folded as coast_sync().  Chunked and double-buffered on two
- * internal streams.  `h_in`/`h_out`/`h_aux` are HOST pointers here (pinned or pageable). */
+/* What the reference's protected function call becomes: host in -> xMR kernel -> host out,
+ * counters folded as coast_sync().  d_in / d_out / d_aux / d_status of the descriptor are HOST
+ * pointers here.
+ *   pinned buffers (cuMemHostAlloc, cudaHostAlloc/Register, coast_host_alloc, torch pin_memory)
+ *     and a kernel that reads its input once (CRC16, SHA256, AES128, CHSTONE_SHA): ONE launch
+ *     reads the mapped host memory through the TMA ring and writes the voted output straight
+ *     back -- upload, compute and download overlap inside the kernel (zero-copy);
+ *   anything else (pageable memory, matmuls, quicksort): staged -- H2D -> kernel -> D2H per
+ *     chunk, chunks of 1..16 MiB round-robin over three internal streams and staging slots
+ *     (a unit larger than 16 MiB is a chunk of its own).  d_status is staged per chunk too.
+ * COAST_HOST_PATH=staged|zerocopy forces a path.  On any failure every copy already queued on
+ * the caller's buffers is drained before the call returns. */
 int  coast_run_host(const coast_launch_desc* desc_with_host_ptrs, coast_stats* out);
 /* Same, but never calls FAULT_DETECTED_DWC (fault campaigns want the count, not SIGABRT). */
 int  coast_run_host_noabort(const coast_launch_desc* desc_with_host_ptrs, coast_stats* out);

@@ -1,4 +1,5 @@
 /* oracle/_ref/libref_aes.so : tests/aes/TI_aes_128.c + tests/aes/aes.c (568 NIST KATs). */
+#define REF_WANT_FANOUT
 #include "ref_common.h"
 #include "aes/TI_aes_128.c"
 #define main ref_aes_main
@@ -38,33 +39,15 @@ REF_API void ref_aes_xmr(const uint8_t* in, uint8_t* out, uint64_t n, const uint
 }
 
 /* pthread fan-out for the CPU baseline ("reference" kind): aes_enc_dec() only reads the global tables */
-#include <pthread.h>
-typedef struct { const uint8_t* in; uint8_t* out; uint64_t n; const uint8_t* keys; int kpu, dir; uint32_t nc; int ce, cs;
-                 const ref_fault* faults; ref_stats st; } aes_mt;
-static void* aes_mt_main(void* p) {
+typedef struct { const uint8_t* in; uint8_t* out; const uint8_t* keys; int kpu, dir; uint32_t nc; int ce, cs; const ref_fault* faults; } aes_mt;
+static void aes_shard(void* p, uint64_t u0, uint64_t n, ref_stats* st) {
     aes_mt* a = (aes_mt*)p;
-    ref_aes_xmr(a->in, a->out, a->n, a->keys, a->kpu, a->dir, a->nc, a->ce, a->cs, a->faults, &a->st);
-    return NULL;
+    ref_aes_xmr(a->in + u0 * 16, a->out + u0 * 16, n, a->keys + (a->kpu ? u0 * 16 : 0), a->kpu, a->dir, a->nc, a->ce, a->cs,
+                a->faults ? a->faults + u0 : NULL, st);
 }
 REF_API void ref_aes_xmr_mt(const uint8_t* in, uint8_t* out, uint64_t n, const uint8_t* keys, int key_per_unit, int dir,
                             uint32_t nc, int count_errors, int count_syncs, const ref_fault* faults, int n_threads,
                             ref_stats* st) {
-    if (n_threads < 1) n_threads = 1;
-    if (n_threads > 256) n_threads = 256;
-    pthread_t th[256]; aes_mt a[256];
-    uint64_t per = (n + (uint64_t)n_threads - 1) / (uint64_t)n_threads;
-    for (int t = 0; t < n_threads; ++t) {
-        uint64_t u0 = per * (uint64_t)t; if (u0 > n) u0 = n;
-        uint64_t u1 = u0 + per; if (u1 > n) u1 = n;
-        a[t].in = in + u0 * 16; a[t].out = out + u0 * 16; a[t].n = u1 - u0;
-        a[t].keys = keys + (key_per_unit ? u0 * 16 : 0); a[t].kpu = key_per_unit; a[t].dir = dir; a[t].nc = nc;
-        a[t].ce = count_errors; a[t].cs = count_syncs; a[t].faults = faults ? faults + u0 : NULL;
-        memset(&a[t].st, 0, sizeof(ref_stats)); a[t].st.first_fault_unit = ~(uint64_t)0;
-        pthread_create(&th[t], NULL, aes_mt_main, &a[t]);
-    }
-    for (int t = 0; t < n_threads; ++t) {
-        pthread_join(th[t], NULL);
-        st->errors_corrected += a[t].st.errors_corrected; st->dwc_detected += a[t].st.dwc_detected;
-        st->syncs += a[t].st.syncs; st->injected += a[t].st.injected;
-    }
+    aes_mt a = { in, out, keys, key_per_unit, dir, nc, count_errors, count_syncs, faults };
+    ref_fanout(aes_shard, &a, n, n_threads, st);
 }

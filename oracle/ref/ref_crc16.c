@@ -1,4 +1,5 @@
 /* oracle/_ref/libref_crc16.so : tests/crc16/crc16.c compiled from the reference tree. */
+#define REF_WANT_FANOUT
 #include "ref_common.h"
 #define main ref_crc16_main
 #include "crc16/crc16.c"
@@ -27,30 +28,13 @@ REF_API void ref_crc16_xmr(const uint8_t* in, uint16_t* out, uint64_t n, uint32_
 }
 
 /* pthread fan-out for the CPU baseline ("reference" kind): crc16() is a pure function of its arguments */
-#include <pthread.h>
-typedef struct { const uint8_t* in; uint16_t* out; uint64_t n; uint32_t len, nc; int ce, cs; ref_stats st; } crc_mt;
-static void* crc_mt_main(void* p) {
+typedef struct { const uint8_t* in; uint16_t* out; uint32_t len, nc; int ce, cs; } crc_mt;
+static void crc_shard(void* p, uint64_t u0, uint64_t n, ref_stats* st) {
     crc_mt* a = (crc_mt*)p;
-    ref_crc16_xmr(a->in, a->out, a->n, a->len, a->nc, a->ce, a->cs, NULL, &a->st);
-    return NULL;
+    ref_crc16_xmr(a->in + u0 * a->len, a->out + u0, n, a->len, a->nc, a->ce, a->cs, NULL, st);
 }
 REF_API void ref_crc16_xmr_mt(const uint8_t* in, uint16_t* out, uint64_t n, uint32_t len, uint32_t nc,
                               int count_errors, int count_syncs, int n_threads, ref_stats* st) {
-    if (n_threads < 1) n_threads = 1;
-    if (n_threads > 256) n_threads = 256;
-    pthread_t th[256]; crc_mt a[256];
-    uint64_t per = (n + (uint64_t)n_threads - 1) / (uint64_t)n_threads;
-    for (int t = 0; t < n_threads; ++t) {
-        uint64_t u0 = per * (uint64_t)t; if (u0 > n) u0 = n;
-        uint64_t u1 = u0 + per; if (u1 > n) u1 = n;
-        a[t].in = in + u0 * len; a[t].out = out + u0; a[t].n = u1 - u0; a[t].len = len; a[t].nc = nc;
-        a[t].ce = count_errors; a[t].cs = count_syncs; memset(&a[t].st, 0, sizeof(ref_stats));
-        a[t].st.first_fault_unit = ~(uint64_t)0;
-        pthread_create(&th[t], NULL, crc_mt_main, &a[t]);
-    }
-    for (int t = 0; t < n_threads; ++t) {
-        pthread_join(th[t], NULL);
-        st->errors_corrected += a[t].st.errors_corrected; st->dwc_detected += a[t].st.dwc_detected;
-        st->syncs += a[t].st.syncs; st->injected += a[t].st.injected;
-    }
+    crc_mt a = { in, out, len, nc, count_errors, count_syncs };
+    ref_fanout(crc_shard, &a, n, n_threads, st);
 }

@@ -1,5 +1,6 @@
 /* oracle/_ref/libref_sha256.so : tests/sha256_common/sha256_common_tmr.c (+ sha_data.inc,
  * and the 4000-byte KAT of tests/hifive1/sha256.tmr/sha_data.inc) from the reference tree. */
+#define REF_WANT_FANOUT
 #include "ref_common.h"
 typedef uint32_t mm_t;
 unsigned error;
@@ -38,31 +39,19 @@ REF_API void ref_sha256_xmr(const uint8_t* in, uint8_t* out, uint64_t n, uint32_
     free(priv);
 }
 
-/* pthread fan-out for the CPU baseline ("reference" kind) */
-#include <pthread.h>
-typedef struct { const uint8_t* in; uint8_t* out; uint64_t n; uint32_t len, nc; int ce, cs; ref_stats st; } sha_mt;
-static void* sha_mt_main(void* p) {
+/* the caller-visible scratch sha256_hash leaves behind (ctx_data / ctx_bitlen / ctx_state), for the entry-point test */
+REF_API void ref_sha256_ctx(const uint8_t* msg, uint32_t len, uint8_t digest[32], uint8_t cd[64], uint32_t bl[2], uint32_t st[8]) {
+    sha256_hash(cd, bl, st, (unsigned char*)msg, len, digest);
+}
+
+/* pthread fan-out for the CPU baseline ("reference" kind): sha256_hash() is a pure function of its arguments */
+typedef struct { const uint8_t* in; uint8_t* out; uint32_t len, nc; int ce, cs; } sha_mt;
+static void sha_shard(void* p, uint64_t u0, uint64_t n, ref_stats* st) {
     sha_mt* a = (sha_mt*)p;
-    ref_sha256_xmr(a->in, a->out, a->n, a->len, a->nc, a->ce, a->cs, NULL, &a->st);
-    return NULL;
+    ref_sha256_xmr(a->in + u0 * a->len, a->out + u0 * 32, n, a->len, a->nc, a->ce, a->cs, NULL, st);
 }
 REF_API void ref_sha256_xmr_mt(const uint8_t* in, uint8_t* out, uint64_t n, uint32_t len, uint32_t nc,
                                int count_errors, int count_syncs, int n_threads, ref_stats* st) {
-    if (n_threads < 1) n_threads = 1;
-    if (n_threads > 256) n_threads = 256;
-    pthread_t th[256]; sha_mt a[256];
-    uint64_t per = (n + (uint64_t)n_threads - 1) / (uint64_t)n_threads;
-    for (int t = 0; t < n_threads; ++t) {
-        uint64_t u0 = per * (uint64_t)t; if (u0 > n) u0 = n;
-        uint64_t u1 = u0 + per; if (u1 > n) u1 = n;
-        a[t].in = in + u0 * len; a[t].out = out + u0 * 32; a[t].n = u1 - u0; a[t].len = len; a[t].nc = nc;
-        a[t].ce = count_errors; a[t].cs = count_syncs; memset(&a[t].st, 0, sizeof(ref_stats));
-        a[t].st.first_fault_unit = ~(uint64_t)0;
-        pthread_create(&th[t], NULL, sha_mt_main, &a[t]);
-    }
-    for (int t = 0; t < n_threads; ++t) {
-        pthread_join(th[t], NULL);
-        st->errors_corrected += a[t].st.errors_corrected; st->dwc_detected += a[t].st.dwc_detected;
-        st->syncs += a[t].st.syncs; st->injected += a[t].st.injected;
-    }
+    sha_mt a = { in, out, len, nc, count_errors, count_syncs };
+    ref_fanout(sha_shard, &a, n, n_threads, st);
 }

@@ -64,6 +64,51 @@ def main():
             rc = L.coast_run_host_noabort(C.byref(d), C.byref(st))
             out.append({"rc": rc, "err": L.coast_last_error().decode() if rc else "", "host_in": C.addressof(h_in),
                         "host_out": C.addressof(h_out), "first_fault_unit": st.first_fault_unit})
+        elif kind == "run_host_pinned":                     # pinned (mapped) host buffers: the zero-copy host call, or staged when forced
+            L.coast_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+            L.coast_host_free.argtypes = [C.c_void_p]
+            hi, ho, hs = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            assert L.coast_host_alloc(C.byref(hi), max(op["in_bytes"], 16)) == 0
+            assert L.coast_host_alloc(C.byref(ho), max(op["out_bytes"], 16)) == 0
+            d.d_in, d.d_out = hi.value, ho.value
+            if op.get("status"):
+                assert L.coast_host_alloc(C.byref(hs), op["n"]) == 0
+                d.d_status = hs.value
+            st = R._Stats()
+            rc = L.coast_run_host_noabort(C.byref(d), C.byref(st))
+            out.append({"rc": rc, "err": L.coast_last_error().decode() if rc else "", "host_in": hi.value, "host_out": ho.value,
+                        "host_status": hs.value})
+            for h in (hi, ho, hs):
+                if h.value:
+                    L.coast_host_free(h)
+        elif kind == "run_host_status":                     # pageable buffers + a host d_status: staged per chunk
+            h_in = (C.c_uint8 * op["in_bytes"])()
+            h_out = (C.c_uint8 * op["out_bytes"])()
+            h_st = (C.c_uint8 * op["n"])()
+            d.d_in, d.d_out, d.d_status = C.addressof(h_in), C.addressof(h_out), C.addressof(h_st)
+            st = R._Stats()
+            rc = L.coast_run_host_noabort(C.byref(d), C.byref(st))
+            out.append({"rc": rc, "err": L.coast_last_error().decode() if rc else "", "host_in": C.addressof(h_in),
+                        "host_out": C.addressof(h_out), "host_status": C.addressof(h_st)})
+        elif kind == "sha_ctx":                             # what sha256_hash leaves in the caller's scratch arrays
+            L.coast_set_opt_passes(b"-TMR")
+            L.coast_xmr_sha256_hash.argtypes = [C.c_void_p] * 4 + [C.c_uint32, C.c_void_p]
+            recs = []
+            for ln in op["lens"]:
+                cd, bl, stt, dig = (C.c_uint8 * 64)(*([0xEE] * 64)), (C.c_uint32 * 2)(9, 9), (C.c_uint32 * 8)(*([7] * 8)), (C.c_uint8 * 32)()
+                data = (C.c_uint8 * ln)(*[(i * 3 + 1) & 0xFF for i in range(ln)])
+                L.coast_xmr_sha256_hash(cd, bl, stt, data, ln, dig)
+                recs.append({"len": ln, "bitlen": list(bl), "state": list(stt), "data": list(cd), "digest": list(dig)})
+            out.append({"recs": recs})
+        elif kind == "two_threads":                         # single-caller guard: a second thread gets COAST_ERR_BUSY, never a race
+            import threading
+            seen = [set(), set()]
+            def hammer(k):
+                for _ in range(op.get("iters", 20000)):
+                    seen[k].add(L.coast_stats_reset(None))
+            ts = [threading.Thread(target=hammer, args=(k,)) for k in range(2)]
+            [t.start() for t in ts]; [t.join() for t in ts]
+            out.append({"codes": sorted(seen[0] | seen[1]), "after": L.coast_stats_reset(None)})
         elif kind == "run_host_aux":                        # AES with per-unit keys (+ write-back), or a matmul: three host buffers
             h_in = (C.c_uint8 * op["in_bytes"])()
             h_aux = (C.c_uint8 * op["aux_bytes"])()

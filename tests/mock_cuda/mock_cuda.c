@@ -39,6 +39,8 @@ static int find_alloc(uintptr_t p, size_t n) {
 }
 static CUresult do_alloc(CUdeviceptr* out, size_t n, int host) {
     if (!n || n_allocs >= MAX_ALLOC) return CUDA_ERROR_INVALID_VALUE;
+    const char* fa = getenv("MOCK_CUDA_FAIL_ALLOC_AFTER");              /* fault injection: the k-th allocation and later ones fail */
+    if (fa && n_allocs >= atoi(fa)) return CUDA_ERROR_OUT_OF_MEMORY;
     if (n > ((size_t)6 << 30)) return CUDA_ERROR_OUT_OF_MEMORY;          /* the box is small: huge requests fail like OOM */
     void* p = NULL;
     if (posix_memalign(&p, 512, n)) return CUDA_ERROR_OUT_OF_MEMORY;      /* cuMemAlloc returns >= 256-byte aligned memory */
@@ -73,6 +75,16 @@ CUresult cuDeviceGetAttribute(int* v, CUdevice_attribute a, CUdevice d) {
     default: *v = 0;
     }
     return CUDA_SUCCESS;
+}
+CUresult cuDeviceGetPCIBusId(char* s, int len, CUdevice d) { (void)d; snprintf(s, (size_t)len, "0000:FF:1F.7"); return CUDA_SUCCESS; }   /* no such sysfs node: NUMA binding is skipped */
+/* pinned host allocations are "mapped": their device alias is the pointer itself; anything else is unknown to the driver */
+static int find_alloc(uintptr_t p, size_t n);
+CUresult cuPointerGetAttribute(void* out, CUpointer_attribute attr, CUdeviceptr p) {
+    int id = find_alloc((uintptr_t)p, 1);
+    if (id < 0) return CUDA_ERROR_INVALID_VALUE;
+    if (attr == CU_POINTER_ATTRIBUTE_MEMORY_TYPE) { *(unsigned int*)out = allocs[id].host ? CU_MEMORYTYPE_HOST : CU_MEMORYTYPE_DEVICE; return CUDA_SUCCESS; }
+    if (attr == CU_POINTER_ATTRIBUTE_DEVICE_POINTER) { *(CUdeviceptr*)out = p; return CUDA_SUCCESS; }
+    return CUDA_ERROR_INVALID_VALUE;
 }
 CUresult cuDevicePrimaryCtxRetain(CUcontext* c, CUdevice d) { (void)d; *c = (CUcontext)&fake_ctx; return CUDA_SUCCESS; }
 CUresult cuDevicePrimaryCtxRelease_v2(CUdevice d) { (void)d; return CUDA_SUCCESS; }
@@ -174,7 +186,7 @@ CUresult cuMemHostAlloc(void** p, size_t n, unsigned int flags) { (void)flags; C
 CUresult cuMemFreeHost(void* p) { return do_free((CUdeviceptr)(uintptr_t)p); }
 CUresult cuStreamCreate(CUstream* s, unsigned int flags) { (void)flags; *s = (CUstream)(uintptr_t)(0x1000 + ++n_streams); return CUDA_SUCCESS; }
 CUresult cuStreamDestroy_v2(CUstream s) { (void)s; return CUDA_SUCCESS; }
-CUresult cuStreamSynchronize(CUstream s) { (void)s; return CUDA_SUCCESS; }
+CUresult cuStreamSynchronize(CUstream s) { LOG("{\"op\":\"stream_sync\",\"stream\":%d}", stream_id(s)); return CUDA_SUCCESS; }
 CUresult cuGetErrorString(CUresult r, const char** s) { (void)r; *s = "mock driver error"; return CUDA_SUCCESS; }
 
 CUresult cuTensorMapEncodeTiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank, void* addr, const cuuint64_t* gdim,

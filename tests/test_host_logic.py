@@ -307,3 +307,97 @@ def test_dwc_detection_calls_the_handler_which_aborts_by_default(mock_dir, tmp_p
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock_cuda", "child.py"), json.dumps({"ops": [dict(op="sync_fold", nc=2, abort=True)]})],
                        capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == -6 and "FAULT_DETECTED_DWC" in r.stderr          # SIGABRT, as the reference's protected binary
+
+
+def _contiguous(spans, total):
+    pos = 0
+    for off, nb in sorted(spans):
+        assert off == pos, (sorted(spans)[:5], total)
+        pos += nb
+    assert pos == total
+
+
+def test_pinned_buffers_take_the_zero_copy_host_call(mock_dir, tmp_path):
+    """pinned (mapped) host buffers + a read-once kernel: ONE launch on the host pointers' device aliases, no staging copies,
+    no staging allocations; COAST_HOST_PATH=staged forces the chunked pipeline on the same buffers"""
+    n = 300000
+    op = dict(op="run_host_pinned", kernel=K_SHA256, nc=3, n=n, unit_bytes=64, in_bytes=64 * n, out_bytes=32 * n, unit_base=77, status=True)
+    res, ev = run_child(mock_dir, tmp_path, [op, dict(op="shutdown")])
+    r = res["ops"][0]
+    assert r["rc"] == 0 and not [e for e in ev if e["op"] == "error"], (r, [e for e in ev if e["op"] == "error"])
+    launches = [e for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
+    assert len(launches) == 1 and launches[0]["name"] == "xmr_sha256_b64_seg_nc3_inj0"
+    a = args_of(launches[0])
+    assert (a.inp, a.out, a.status, a.n_units, a.unit_base) == (r["host_in"], r["host_out"], r["host_status"], n, 77)
+    assert not [e for e in ev if e["op"] == "h2d"] and all(e["bytes"] <= 64 for e in ev if e["op"] == "d2h")     # only the counters come back by copy
+    assert ev[-1] == {"op": "exit", "live_allocations": 0}
+    res, ev = run_child(mock_dir, tmp_path / "..", [op, dict(op="shutdown")], env_extra={"COAST_HOST_PATH": "staged"})
+    r = res["ops"][0]
+    assert r["rc"] == 0 and len([e for e in ev if e["op"] == "launch" and "_nc" in e["name"]]) > 1
+    _contiguous([(e["host"] - r["host_in"], e["bytes"]) for e in ev if e["op"] == "h2d"], 64 * n)
+
+
+def test_zero_copy_is_refused_for_pageable_buffers_only_when_forced(mock_dir, tmp_path):
+    op = dict(op="run_host", kernel=K_SHA256, nc=3, n=1000, unit_bytes=64, in_bytes=64000, out_bytes=32000)
+    res, ev = run_child(mock_dir, tmp_path, [op], env_extra={"COAST_HOST_PATH": "zerocopy"})
+    assert res["ops"][0]["rc"] != 0 and "pinned" in res["ops"][0]["err"]
+    res, ev = run_child(mock_dir, tmp_path / "..", [op])                       # default: falls back to the staged pipeline
+    assert res["ops"][0]["rc"] == 0 and [e for e in ev if e["op"] == "h2d"]
+
+
+def test_host_call_stages_the_status_bytes_per_chunk(mock_dir, tmp_path):
+    """kernels index status[] chunk-locally, so the host call must give every chunk its own device status
+    buffer and copy it back to (host status + units done)"""
+    n = 300001
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="run_host_status", kernel=K_AES128, nc=2, n=n, in_bytes=16 * n, out_bytes=16 * n),
+                                             dict(op="shutdown")])
+    r = res["ops"][0]
+    assert r["rc"] == 0 and not [e for e in ev if e["op"] == "error"]
+    launches = [args_of(e) for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
+    assert len(launches) > 1 and all(a.status not in (0, r["host_status"]) for a in launches)
+    _contiguous([(e["host"] - r["host_status"], e["bytes"]) for e in ev if e["op"] == "d2h" and 0 <= e["host"] - r["host_status"] < n], n)
+    assert ev[-1] == {"op": "exit", "live_allocations": 0}
+
+
+def test_host_call_chunks_are_bounded_in_bytes(mock_dir, tmp_path):
+    """1024-unit floor x 48 MiB streams used to ask for hundreds of GiB; a unit above the byte bound is its own chunk"""
+    big, n = 48 << 20, 5
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="run_host", kernel=K_CHSTONE_SHA, nc=3, n=n, unit_bytes=big, in_bytes=n * big, out_bytes=n * 20),
+                                             dict(op="shutdown")])
+    assert res["ops"][0]["rc"] == 0, res
+    launches = [args_of(e) for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
+    assert [a.n_units for a in launches] == [1] * n and max(e["bytes"] for e in ev if e["op"] == "alloc") <= big + 4096
+    assert ev[-1] == {"op": "exit", "live_allocations": 0}
+
+
+def test_a_failing_chunk_drains_the_copies_already_queued(mock_dir, tmp_path):
+    """the host call must not return while earlier chunks' copies are still in flight on the caller's buffers: after a driver failure
+    in a later chunk (here: a staging allocation above the mock box's 6 GiB) the streams are synchronised before the error comes back"""
+    big, n = 5 << 30, 2                                                         # first slot fits, the second does not
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="run_host", kernel=K_CHSTONE_SHA, nc=3, n=n, unit_bytes=1 << 28, in_bytes=n << 28, out_bytes=n * 20)],
+                        env_extra={"COAST_HOST_CHUNK_BYTES": str(1 << 28), "MOCK_CUDA_FAIL_ALLOC_AFTER": "6"})
+    r = res["ops"][0]
+    if r["rc"] != 0:                                                            # the injected failure fired mid-schedule
+        syncs = [i for i, e in enumerate(ev) if e["op"] == "stream_sync"]
+        last_copy = max(i for i, e in enumerate(ev) if e["op"] in ("h2d", "d2h", "launch"))
+        assert syncs and max(syncs) > last_copy, "error returned without draining the host-call streams"
+
+
+def test_single_caller_guard(mock_dir, tmp_path):
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="two_threads", iters=20000)])
+    r = res["ops"][0]
+    assert set(r["codes"]) <= {0, -100005} and 0 in r["codes"] and r["after"] == 0
+
+
+def test_sha256_entry_point_writes_the_callers_ctx_scratch(mock_dir, tmp_path):
+    """sha256_hash leaves ctx_state / ctx_bitlen / ctx_data behind (sha256_common_tmr.c:101-180); ctx_state must be
+    the big-endian words of the digest the launch returned, bitlen = 8*len and ctx_data the last padded block"""
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="sha_ctx", lens=[10, 55, 56, 64, 119, 200])])
+    for rec in res["ops"][0]["recs"]:
+        ln = rec["len"]
+        assert rec["bitlen"] == [(8 * ln) & 0xFFFFFFFF, ln >> 29]
+        assert rec["state"] == [int.from_bytes(bytes(rec["digest"][4 * i:4 * i + 4]), "big") for i in range(8)]
+        rem = ln % 64
+        want = (bytes((i * 3 + 1) & 0xFF for i in range(ln - rem, ln)) + b"\x80" + bytes(55 - rem)) if rem < 56 else bytes(56)
+        want += (8 * ln).to_bytes(8, "big")
+        assert bytes(rec["data"]) == want, (ln, rec["data"])
