@@ -111,6 +111,7 @@ static struct {
     struct { const void* base; uint32_t row_bytes, box_rows; uint64_t rows; int swz; CUtensorMap map; } tmaps[16];
     int n_tmaps, tmap_next;
     int zero_copy_default;           /* host-call path for pinned buffers: 1 = one zero-copy launch, 0 = staged chunks */
+    const char* last_host_path;      /* "zerocopy" | "staged" | "one-shot": what the last coast_run_host did */
 } G;
 
 /* Single-caller guard.  The reference's emitted code is single-threaded (plain load/add/store on its counters,
@@ -873,6 +874,7 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int* dwc_
         rc = launch_impl(&c, G.hs[0]);
         if (rc) { char keep[sizeof G.err]; memcpy(keep, G.err, sizeof keep); p_cuStreamSynchronize(G.hs[0]); memcpy(G.err, keep, sizeof keep); return rc; }
         DRV(p_cuMemcpyDtoHAsync_v2(d->d_out, G.h_out[0], cb, G.hs[0]));
+        G.last_host_path = "one-shot";
         return sync_impl(G.hs[0], out, dwc_fired);
     }
     const uint64_t ib = in_bytes_per_unit(d);
@@ -899,11 +901,13 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int* dwc_
             if (per_unit_key) c.d_aux = (void*)za;
             if (d->d_status) c.d_status = (void*)zs;
             rc = launch_impl(&c, G.hs[2]); if (rc) return rc;
+            G.last_host_path = "zerocopy";
             return sync_impl(G.hs[2], out, dwc_fired);
         }
         if (hp && !strcmp(hp, "zerocopy")) return fail(COAST_ERR_BAD_ARG, "COAST_HOST_PATH=zerocopy needs pinned (mapped) host buffers");
     }
     rc = run_host_staged(d, ib, ob, per_unit_key); if (rc) return rc;
+    G.last_host_path = "staged";
     DRV(p_cuStreamSynchronize(G.hs[0])); DRV(p_cuStreamSynchronize(G.hs[1]));
     return sync_impl(G.hs[2], out, dwc_fired);
 }
@@ -914,6 +918,7 @@ static int run_host_guarded(const coast_launch_desc* d, coast_stats* out, int ca
     if (!rc && call_handler && fired) FAULT_DETECTED_DWC();   /* synchronization.cpp:1299-1302 */
     return rc;
 }
+const char* coast_last_host_path(void) { return G.last_host_path ? G.last_host_path : ""; }
 int coast_run_host(const coast_launch_desc* d, coast_stats* out) { return run_host_guarded(d, out, 1); }
 int coast_run_host_noabort(const coast_launch_desc* d, coast_stats* out) { return run_host_guarded(d, out, 0); }
 

@@ -100,7 +100,7 @@ EXPORTS = [
     "coast_fault_site_bits", "coast_out_bytes_per_unit", "coast_out_bytes", "coast_votes_per_unit", "coast_malloc", "coast_free",
     "coast_memcpy_h2d", "coast_memcpy_d2h", "coast_memset", "coast_host_alloc", "coast_host_free",
     "coast_stream_create", "coast_stream_destroy", "coast_stream_sync", "coast_fill_philox", "coast_run_host",
-    "coast_run_host_noabort",
+    "coast_run_host_noabort", "coast_last_host_path",
     "coast_set_opt_passes", "coast_xmr_crc16", "coast_xmr_sha256_hash", "coast_xmr_aes_enc_dec",
     "coast_xmr_matrix_multiply_u32", "coast_xmr_chstone_sha_stream", "TMR_ERROR_CNT", "__SYNC_COUNT", "FAULT_DETECTED_DWC",
 ]
@@ -117,6 +117,7 @@ def load_library():
         L = C.CDLL(path)
         L.coast_last_error.restype = C.c_char_p
         L.coast_version.restype = C.c_char_p
+        L.coast_last_host_path.restype = C.c_char_p
         L.coast_init.argtypes = [C.c_int]
         L.coast_parse_opt_passes.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.coast_set_opt_passes.argtypes = [C.c_char_p]
@@ -219,6 +220,14 @@ class Runtime:
 
     def fault_site_bits(self, kernel, unit_bytes, K, site) -> int:
         return int(self.L.coast_fault_site_bits(kernel, unit_bytes, K, site))
+
+    @property
+    def numa_node(self) -> int:
+        return int(self.L.coast_numa_node())
+
+    @property
+    def last_host_path(self) -> str:
+        return self.L.coast_last_host_path().decode()
 
     @property
     def tmr_error_cnt(self) -> int:

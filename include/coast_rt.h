@@ -262,6 +262,7 @@ int  coast_fill_philox(void* d_dst, uint64_t n_words, uint64_t word_base, uint32
  * COAST_HOST_PATH=staged|zerocopy forces a path.  On any failure every copy already queued on
  * the caller's buffers is drained before the call returns. */
 int  coast_run_host(const coast_launch_desc* desc_with_host_ptrs, coast_stats* out);
+const char* coast_last_host_path(void);   /* "zerocopy", "staged" or "one-shot" (matmuls): what the last host call did */
 /* Same, but never calls FAULT_DETECTED_DWC (fault campaigns want the count, not SIGABRT). */
 int  coast_run_host_noabort(const coast_launch_desc* desc_with_host_ptrs, coast_stats* out);
 

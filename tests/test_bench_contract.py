@@ -34,3 +34,23 @@ def test_reference_arm_line_has_the_contract_keys():
 def test_reference_arm_other_ranks_print_nothing():
     res = _run([], env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert res.returncode == 0 and not [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_both_arms_print_the_same_config_object():
+    """`same_config` was false because the arms' config dicts carried different keys.  config is now a pure
+    function of (workload, GPU count) that both arms call."""
+    sys.path.insert(0, ROOT)
+    import bench
+    res = _run(["--threads", "2", "--gpus", "1"])
+    d = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["config"] == bench.config_for("sha256", 1)
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": config_for(wl, ') == 2          # the reference arm and the GPU arm, nothing hand-written
+    for wl in bench.WORKLOAD_NAMES:
+        assert bench.config_for(wl, 8)["parallelism"] == "shard8" and bench.config_for(wl, 8)["workload"] == bench.WORKLOAD_NAMES[wl]
+
+
+def test_reference_arm_reports_the_median_of_individually_timed_steps():
+    res = _run(["--threads", "2", "--workload", "crc16"])
+    d = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][0])
+    assert "median" in d["cpu_baseline"]["sample"] and "pinned" in d["cpu_baseline"]["sample"] and d["cpu_baseline"]["spread"] >= 1.0

@@ -332,6 +332,70 @@ def test_run_host_matches_device_path(rt, oracle):
     assert ho.numpy().tobytes() == o.tobytes() and st.as_dict() == so
 
 
+@pytest.mark.parametrize("case", ["sha64", "sha100", "sha0", "crc64", "crc13", "aes_enc", "aes_dec_keys", "chsha"])
+def test_host_call_zero_copy_and_staged_agree_with_the_oracle(rt, oracle, case):
+    """coast_run_host(): pinned buffers -> ONE zero-copy launch on the mapped host memory (TMA / vector loads over PCIe, voted
+    output and per-unit status written straight to host memory); pageable buffers -> the staged chunk pipeline.  Same bytes,
+    same counters, same per-unit status as the oracle on both, with injected faults."""
+    import torch
+    import coast_b200 as cb
+    n = 70001
+    kw, okw = {}, {}
+    if case.startswith("sha"):
+        ub = {"sha64": 64, "sha100": 100, "sha0": 0}[case]
+        kernel, nc, ob = cb.K_SHA256, 3, 32
+        inp = msgs(oracle, n, ub, 2) if ub else np.zeros(16, dtype=np.uint8)
+        kw = okw = dict(unit_bytes=ub, flags=3)
+    elif case.startswith("crc"):
+        ub = 64 if case == "crc64" else 13
+        kernel, nc, ob = cb.K_CRC16, 3, 2
+        inp = msgs(oracle, n, ub, 1)
+        kw = okw = dict(unit_bytes=ub, flags=3)
+    elif case == "aes_enc":
+        kernel, nc, ob = cb.K_AES128, 2, 16
+        inp = msgs(oracle, n, 16, 3)
+        kw = okw = dict(key=bytes(range(16)))
+    elif case == "aes_dec_keys":
+        kernel, nc, ob = cb.K_AES128, 3, 16
+        inp = msgs(oracle, n, 16, 3)
+        keys = msgs(oracle, n, 16, 5)
+        kw = dict(mode=cb.AES_DECRYPT | cb.AES_KEY_PER_UNIT, flags=1)
+        okw = dict(mode=cb.AES_DECRYPT | cb.AES_KEY_PER_UNIT, flags=1, aux=keys)
+    else:
+        n = 3001
+        kernel, nc, ob = cb.K_CHSTONE_SHA, 3, 20
+        inp = msgs(oracle, n, 256, 6)
+        kw = okw = dict(unit_bytes=256, flags=3)
+    p = 0.02
+    o_out, o_st = oracle.run(kernel, nc, inp, n, plan=oracle.make_plan(oracle.PLAN_BERNOULLI, seed=21, p=p), unit_base=123, **okw)
+    plan = cb.FaultPlan(mode=cb.PLAN_BERNOULLI, seed=21, p=p)
+    for pinned in (True, False):
+        mk = (lambda a: torch.from_numpy(a.copy()).pin_memory()) if pinned else (lambda a: a.copy())
+        h_in = mk(inp)
+        h_out = mk(np.zeros(n * ob, dtype=np.uint8))
+        h_aux = mk(keys) if case == "aes_dec_keys" else None
+        h_status = mk(np.full(n, 0xEE, dtype=np.uint8))
+        d = rt.make_desc(kernel, nc, h_in.data_ptr() if pinned else h_in.ctypes.data, h_out.data_ptr() if pinned else h_out.ctypes.data, n,
+                         plan=plan, unit_base=123, d_aux=(h_aux.data_ptr() if pinned else h_aux.ctypes.data) if h_aux is not None else None,
+                         d_status=h_status.data_ptr() if pinned else h_status.ctypes.data, **kw)
+        import ctypes as C
+        from coast_b200.runtime import _Stats
+        st = _Stats()
+        rc = rt.L.coast_run_host_noabort(C.byref(d), C.byref(st))
+        assert rc == 0, rt.L.coast_last_error()
+        assert rt.last_host_path == ("zerocopy" if pinned else "staged")
+        got = h_out.numpy() if pinned else h_out
+        assert got.tobytes() == o_out.tobytes(), (case, pinned)
+        assert {k: getattr(st, k) for k in STAT_KEYS} == {k: o_st[k] for k in STAT_KEYS}, (case, pinned)
+        status = h_status.numpy() if pinned else h_status
+        bad_units = int((status != 0).sum())
+        assert int(status.max()) <= 32                              # every byte was written (0xEE poison gone)
+        if nc == 2:
+            assert bad_units == o_st["dwc_detected"]
+        else:
+            assert int(status.astype(np.int64).sum()) == o_st["errors_corrected"]
+
+
 def test_reference_entry_points(rt, oracle, golden):
     """the four functions the unchanged reference tests call (BOARD=b200 flow), under -TMR -countErrors"""
     import ctypes as C
