@@ -277,7 +277,7 @@ static int init_impl(int device) {
     }
     p_cuDeviceGetAttribute(&G.sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, G.dev);
     numa_bind_to_gpu();
-    G.zero_copy_default = 1;
+    G.zero_copy_default = 0;        /* measured r02 (profiles/r02_e2e_zero_copy_experiment.md): SM writes to host memory lose to staged D2H */
     r = p_cuModuleLoadData(&G.mod, coast_kernels_cubin);
     if (r != CUDA_SUCCESS) { p_cuDevicePrimaryCtxRelease_v2(G.dev); return drv_fail(r, "cuModuleLoadData(sm_100a cubin)"); }
     DRV(p_cuMemAlloc_v2(&G.counters, XMR_CTR_COUNT * sizeof(uint64_t)));
@@ -597,13 +597,16 @@ static int launch_impl(const coast_launch_desc* d, void* stream) {
     case COAST_K_AES128:
         if ((d->mode & COAST_AES_KEY_PER_UNIT) && !d->d_aux) return fail(COAST_ERR_BAD_ARG, "per-unit keys need d_aux");
         if (!aligned16 || (((uintptr_t)d->d_out) & 15u)) return fail(COAST_ERR_BAD_ARG, "AES buffers must be 16-byte aligned");
-        if (!(d->mode & (COAST_AES_DECRYPT | COAST_AES_KEY_PER_UNIT)) && d->n_units < 0x7FFFFF00ull) {
-            /* 512-thread CTAs; the shared window [0, 0x30000) holds the ring and the two 64 KiB-aligned T-tables */
+        if ((d->mode & COAST_AES_KEY_PER_UNIT) && (((uintptr_t)d->d_aux) & 15u)) return fail(COAST_ERR_BAD_ARG, "AES per-unit keys must be 16-byte aligned");
+        if (d->n_units >= 0x7FFFFF00ull) return fail(COAST_ERR_UNSUPPORTED, "AES: at most 2^31 - 257 blocks per launch (split the batch)");
+        {
+            /* one table-driven body (xmr_aes128.cuh): enc / dec with one ECB key, enck / deck with per-unit keys.  512-thread CTAs;
+             * the shared window holds the ring, the two 64 KiB-aligned T-tables and, for decrypt, the 32 KiB (InvS, S) table */
+            const int dec = (d->mode & COAST_AES_DECRYPT) != 0, perkey = (d->mode & COAST_AES_KEY_PER_UNIT) != 0;
             tma = 1; block = 512; tile_rows = 16u * upw * (nc == 1 ? 2u : 4u); row_bytes = 16;
-            smem = 0x30000u;
-            snprintf(name, sizeof name, "xmr_aes128_enc_nc%u_inj%d", nc, inj);
-        } else {
-            snprintf(name, sizeof name, "xmr_aes128_gen_nc%u_inj%d", nc, inj);
+            smem = dec ? 0x38000u : 0x30000u;
+            static const char* const stem[4] = { "xmr_aes128_enc", "xmr_aes128_dec", "xmr_aes128_enck", "xmr_aes128_deck" };
+            snprintf(name, sizeof name, "%s_nc%u_inj%d", stem[dec + 2 * perkey], nc, inj);
         }
         break;
     case COAST_K_MM_U32:

@@ -1,44 +1,113 @@
 // xmr_aes128.cuh -- protected AES-128 single-block (tests/aes/TI_aes_128.c:107-231 of byuccl/coast)
 //
 // Unit = one 16-byte block -> 16 bytes.  SoR exit = the 16 u8 state bytes (:224-229): 16 votes.
-// Two kernels, same results:
-//   xmr_aes128_enc  : encrypt, one ECB key (BASELINE config 3).  Column/T-table formulation of the
-//                     same rounds: AddRoundKey-then-SubBytes (:143-146), ShiftRows (:147-166),
-//                     MixColumns (:169-184), forward key schedule (:214-221), last AddRoundKey (:224-229).
-//                     TE0..TE3 are replicated 32x in shared memory (row x = 32 lanes of TE_k[x]) so every lookup
-//                     is bank-conflict free whatever the data and its address is ONE byte-permute; blocks
-//                     arrive through the TMA tile ring.
-//   xmr_aes128_gen  : byte-wise restatement that follows the TI control flow literally; handles
-//                     decrypt (dir=1, :112-129,133-141,187-212) and per-unit keys (the 568 KATs).
-// Fault sites (identical in oracle/): 0..15 = state byte as loaded; 16+16r+i = state[i] at the
-// bottom of main-loop iteration r (:132-223).  A flip there is XOR-linear through the following
-// AddRoundKey, which is why the T-table kernel can apply it after its fused key add.
+// ONE table-driven body, four instantiations per (NC, injector):
+//   enc   : encrypt, one ECB key expanded once per lane (BASELINE config 3)
+//   dec   : decrypt, one key (round keys and their InvMixColumns images expanded once per lane)
+//   enck / deck : per-unit keys from d_aux with the on-the-fly key schedule of the reference
+//           (forward :214-221, to-the-last-round-key :112-129, inverse :133-141), optional write-back of what
+//           aes_enc_dec() leaves in key[] (the last round key after encrypt, the original key after decrypt)
+// Column formulation of the same rounds.  Encrypt: AddRoundKey-then-SubBytes (:143-146), ShiftRows (:147-166),
+// MixColumns (:169-184) = four TE rows XORed.  Decrypt: the reference's iteration is [InvMixColumns (:169-184 with the
+// :172-177 pre-multiply)] -> InvShiftRows (:187-206) -> InvSubBytes ^ key (:208-211); InvMixColumns is linear, so the
+// kernel carries v = InvMixColumns(state) between iterations: v' = TD rows(v) ^ InvMixColumns(round key), and the last
+// iteration ends with plain InvSubBytes ^ rk0.
+// All tables are replicated 32x in shared memory (row x holds one copy per lane) so every lookup is bank-conflict free
+// whatever the data and its address is ONE byte-permute; blocks arrive through the TMA tile ring.
+// Fault sites (identical in oracle/): 0..15 = state byte as loaded; 16+16r+i = state[i] at the bottom of main-loop
+// iteration r (:132-223).  A flip there is XOR-linear through the following AddRoundKey (and, for decrypt, through the
+// following InvMixColumns), which is why the kernel can apply it to its fused values.
+// Injector cost (r02): the Philox decision of a unit is evaluated by ONE of its replica lanes and shuffled to the others,
+// and the per-round hooks sit behind a warp-uniform branch, so a warp none of whose blocks is hit runs the instruction
+// stream of the injector-free kernel.
 #pragma once
 #include "xmr_common.cuh"
 #include "aes_tables.inc"
 
 namespace xmr {
 
-// ---- T-table kernel geometry --------------------------------------------------------------------
+// ---- geometry ----------------------------------------------------------------------------------
 // 512-thread CTAs, one per SM.  Shared-memory WINDOW layout (absolute shared::cta addresses):
 //   [dyn base .. 0x10000)  TMA tile ring (2 stages)
-//   [0x10000 .. 0x20000)   row x (256 B): TE0[x] replicated over 32 lanes | TE1[x] = rotl8  replicated over 32 lanes
-//   [0x20000 .. 0x30000)   row x (256 B): TE2[x] = rotl16 x 32 lanes     | TE3[x] = rotl24 x 32 lanes
-// Row stride 256 B + 64 KiB alignment make the lookup address ONE byte-permute:
+//   [0x10000 .. 0x20000)   row x (256 B): T0[x] replicated over 32 lanes | T1[x] = rotl8  replicated over 32 lanes
+//   [0x20000 .. 0x30000)   row x (256 B): T2[x] = rotl16 x 32 lanes     | T3[x] = rotl24 x 32 lanes
+//   [0x30000 .. 0x38000)   decrypt only, row x (128 B): (InvS[x], S[x], InvS[x], S[x]) replicated over 32 lanes
+// T = TE (encrypt) or TD (decrypt).  Row stride 256 B + 64 KiB alignment make the lookup address ONE byte-permute:
 //   addr = PRMT(t, lanebase) = lanebase.b3 : lanebase.b2 : byte_k(t) : lanebase.b0,  lanebase = table | half | lane*4
-// and bank = lane for every lane whatever the data -> no shared-memory bank conflicts, no rotates, no LEA.
-// (r01 first version: one TE0 copy + PRMT rotates + SHF/LOP3/LEA per lookup = 975 instructions per block; ncu showed
-//  the ALU pipe at 95 %.)
+// and bank = lane for every lane whatever the data -> no shared-memory bank conflicts, no rotates, no LEA.  The 128-byte
+// rows of the third window cost one extra shift: addr = PRMT(t, 2*lanebase) >> 1.
 constexpr int AES_THREADS = 512, AES_WARPS = 16;
-constexpr uint32_t AES_TAB01 = 0x10000u, AES_TAB23 = 0x20000u, AES_WINDOW_END = 0x30000u;
+constexpr uint32_t AES_TAB01 = 0x10000u, AES_TAB23 = 0x20000u, AES_SIS = 0x30000u;
+constexpr uint32_t AES_WINDOW_END_ENC = 0x30000u, AES_WINDOW_END_DEC = 0x38000u;
 template <int NC> struct AesGeom { static constexpr int J = NC == 1 ? 2 : 4; static constexpr int TROWS = AES_WARPS * Lanes<NC>::kUnitsPerWarp * J; };
 
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
 // table row of byte k of t: splice that byte into byte 1 of the lane's base address
-__device__ __forceinline__ uint32_t tab_b0(uint32_t lb, uint32_t t) { return lds32(__byte_perm(t, lb, 0x7604u)); }
-__device__ __forceinline__ uint32_t tab_b1(uint32_t lb, uint32_t t) { return lds32(__byte_perm(t, lb, 0x7614u)); }
-__device__ __forceinline__ uint32_t tab_b2(uint32_t lb, uint32_t t) { return lds32(__byte_perm(t, lb, 0x7624u)); }
-__device__ __forceinline__ uint32_t tab_b3(uint32_t lb, uint32_t t) { return lds32(__byte_perm(t, lb, 0x7634u)); }
+template <int K> __device__ __forceinline__ uint32_t tab(uint32_t lb, uint32_t t) { return lds32(__byte_perm(t, lb, 0x7604u | (K << 4))); }
+// same for the 128-byte-row table: lb2x = 2 * (table | lane*4)
+template <int K> __device__ __forceinline__ uint32_t tab_half(uint32_t lb2x, uint32_t t) { return lds32(__byte_perm(t, lb2x, 0x7604u | (K << 4)) >> 1); }
+
+// ---- GF(2^8) column arithmetic on packed words (row r of the column in byte r) -------------------
+__device__ __forceinline__ uint32_t xtime4(uint32_t w) { return ((w & 0x7F7F7F7Fu) << 1) ^ (((w >> 7) & 0x01010101u) * 0x1Bu); }   // galois_mul2 :88-99, 4 bytes at once
+__device__ __forceinline__ uint32_t mix_column(uint32_t w) {                   // :178-183: out_r = xtime(a_r ^ a_r+1) ^ a_r+1 ^ a_r+2 ^ a_r+3
+    const uint32_t r1 = __byte_perm(w, 0u, 0x0321u), r2 = __byte_perm(w, 0u, 0x1032u), r3 = __byte_perm(w, 0u, 0x2103u);
+    return xtime4(w ^ r1) ^ r1 ^ r2 ^ r3;
+}
+__device__ __forceinline__ uint32_t inv_mix_column(uint32_t w) {               // :172-177 pre-multiply, then the forward mix
+    const uint32_t v = w ^ __byte_perm(w, 0u, 0x1032u);
+    return mix_column(w ^ xtime4(xtime4(v)));
+}
+
+struct AesLaneBases { uint32_t lb0, lb1, lb2, lb3, sis2x; };
+
+// SubWord(RotWord(w)) for the key schedule: bytes (S[w.b1], S[w.b2], S[w.b3], S[w.b0])
+template <bool DEC> __device__ __forceinline__ uint32_t sub_rot_word(const AesLaneBases& L, uint32_t w) {
+    if (DEC) {                                                  // S sits in bytes 1 and 3 of the (InvS, S, InvS, S) rows
+        const uint32_t a = tab_half<1>(L.sis2x, w), b = tab_half<2>(L.sis2x, w), c = tab_half<3>(L.sis2x, w), d = tab_half<0>(L.sis2x, w);
+        return __byte_perm(__byte_perm(a, b, 0x0051u), __byte_perm(c, d, 0x0051u), 0x5410u);
+    }
+    // S-box byte = byte 1 of TE0 = byte 2 of TE1 = byte 0 of TE2 ...
+    return (tab<1>(L.lb2, w) & 0x000000FFu) | (tab<2>(L.lb0, w) & 0x0000FF00u) | (tab<3>(L.lb0, w) & 0x00FF0000u) | (tab<0>(L.lb1, w) & 0xFF000000u);
+}
+// forward key-schedule step (:214-221) and its inverse (:133-141), on the four key columns
+template <bool DEC> __device__ __forceinline__ void key_next(const AesLaneBases& L, uint32_t (&k)[4], int rd) {
+    k[0] ^= sub_rot_word<DEC>(L, k[3]) ^ (uint32_t)XMR_AES_RCON[rd];
+    k[1] ^= k[0]; k[2] ^= k[1]; k[3] ^= k[2];
+}
+template <bool DEC> __device__ __forceinline__ void key_prev(const AesLaneBases& L, uint32_t (&k)[4], int rd) {
+    k[3] ^= k[2]; k[2] ^= k[1]; k[1] ^= k[0];
+    k[0] ^= sub_rot_word<DEC>(L, k[3]) ^ (uint32_t)XMR_AES_RCON[rd];
+}
+
+// one main-loop iteration without its AddRoundKey: encrypt = SubBytes+ShiftRows(+MixColumns), decrypt = InvShiftRows+InvSubBytes(+InvMixColumns)
+template <bool DEC, bool LAST>
+__device__ __forceinline__ void aes_round_cols(const AesLaneBases& L, const uint32_t (&t)[4], uint32_t (&n)[4]) {
+    if (!DEC) {
+        if (!LAST) {                                            // 4 table rows XORed
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                n[c] = tab<0>(L.lb0, t[c]) ^ tab<1>(L.lb1, t[(c + 1) & 3]) ^ tab<2>(L.lb2, t[(c + 2) & 3]) ^ tab<3>(L.lb3, t[(c + 3) & 3]);
+        } else {                                                // round 9: no MixColumns (:168); S[x] sits in byte p of the table picked per position
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                n[c] = (tab<0>(L.lb2, t[c]) & 0x000000FFu) | (tab<1>(L.lb0, t[(c + 1) & 3]) & 0x0000FF00u) |
+                       (tab<2>(L.lb0, t[(c + 2) & 3]) & 0x00FF0000u) | (tab<3>(L.lb1, t[(c + 3) & 3]) & 0xFF000000u);
+        }
+    } else {
+        if (!LAST) {                                            // InvShiftRows: row r of column c comes from column c - r
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                n[c] = tab<0>(L.lb0, t[c]) ^ tab<1>(L.lb1, t[(c + 3) & 3]) ^ tab<2>(L.lb2, t[(c + 2) & 3]) ^ tab<3>(L.lb3, t[(c + 1) & 3]);
+        } else {                                                // last iteration: plain InvSubBytes (byte 0 of the (InvS, S, InvS, S) rows)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t a = tab_half<0>(L.sis2x, t[c]), b = tab_half<1>(L.sis2x, t[(c + 3) & 3]);
+                const uint32_t d = tab_half<2>(L.sis2x, t[(c + 2) & 3]), e = tab_half<3>(L.sis2x, t[(c + 1) & 3]);
+                n[c] = __byte_perm(__byte_perm(a, b, 0x0040u), __byte_perm(d, e, 0x0040u), 0x5410u);
+            }
+        }
+    }
+}
 
 template <int NC>
 __device__ __forceinline__ void aes_vote_store(const uint32_t (&c)[4], uint8_t* out, unsigned long long local,
@@ -53,8 +122,44 @@ __device__ __forceinline__ void aes_vote_store(const uint32_t (&c)[4], uint8_t* 
     }
 }
 
-template <int NC, bool INJECT>
-__device__ __forceinline__ void aes128_enc_body(const xmr_args& a, const CUtensorMap* tmap) {
+// The ten iterations of J blocks.  HOOKS = this warp has at least one block with a mid-round fault: the flip of block j is
+// fbit[j] in column fcol[j] at the bottom of iteration frd[j].  PERKEY: k[j] is the block's running round key.
+template <int J, bool DEC, bool PERKEY, bool HOOKS>
+__device__ __forceinline__ void aes_rounds(const AesLaneBases& L, uint32_t (&s)[J][4], uint32_t (&k)[PERKEY ? J : 1][4], const uint32_t (&rk)[PERKEY ? 4 : 44],
+                                           const uint32_t (&fbit)[J], const int (&frd)[J], const int (&fcol)[J]) {
+#pragma unroll
+    for (int rd = 0; rd < 10; ++rd) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            uint32_t n[4];
+            if (rd < 9) aes_round_cols<DEC, false>(L, s[j], n); else aes_round_cols<DEC, true>(L, s[j], n);
+            if (HOOKS) {                                        // the flip lands on state[] at the bottom of iteration rd
+                uint32_t hit = frd[j] == rd ? fbit[j] : 0u;
+                if (DEC && rd < 9) hit = inv_mix_column(hit);   // the kernel carries InvMixColumns(state) between decrypt iterations
+#pragma unroll
+                for (int c = 0; c < 4; ++c) n[c] ^= fcol[j] == c ? hit : 0u;
+            }
+            if (PERKEY) {
+                if (!DEC) {
+                    key_next<false>(L, k[j], rd);               // :214-221
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) s[j][c] = n[c] ^ k[j][c];
+                } else {
+                    key_prev<true>(L, k[j], 9 - rd);            // :133-141 -> round key 9 - rd
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) s[j][c] = n[c] ^ (rd < 9 ? inv_mix_column(k[j][c]) : k[j][c]);
+                }
+            } else {
+                // encrypt: rk[4(rd+1)..] ; decrypt: rk[] already holds InvMixColumns(round key 9-rd) for rd < 9 and round key 0 last
+#pragma unroll
+                for (int c = 0; c < 4; ++c) s[j][c] = n[c] ^ rk[4 * (rd + 1) + c];
+            }
+        }
+    }
+}
+
+template <int NC, bool INJECT, bool DEC, bool PERKEY>
+__device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap* tmap) {
     constexpr int UPW = Lanes<NC>::kUnitsPerWarp;
     constexpr int J = AesGeom<NC>::J;
     constexpr int TROWS = AesGeom<NC>::TROWS;
@@ -65,37 +170,63 @@ __device__ __forceinline__ void aes128_enc_body(const xmr_args& a, const CUtenso
     Ring ring;
     ring.init(ring_mem, tmap);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {   // build the two 64 KiB tables
+    {   // build the tables
         uint32_t* t01 = reinterpret_cast<uint32_t*>(smem_raw + (AES_TAB01 - win));
         uint32_t* t23 = reinterpret_cast<uint32_t*>(smem_raw + (AES_TAB23 - win));
         for (int i = tid; i < 256 * 64; i += AES_THREADS) {
-            const uint32_t v = XMR_AES_TE0[i >> 6];
+            uint32_t v;
+            if (!DEC) v = XMR_AES_TE0[i >> 6];
+            else {                                              // TD0[x]: InvMixColumns of the column (InvS[x], 0, 0, 0) = (14, 9, 13, 11) . InvS[x]
+                v = inv_mix_column((uint32_t)XMR_AES_RSBOX[i >> 6]);
+            }
             const bool hi = (i & 32) != 0;
-            t01[i] = hi ? __byte_perm(v, 0u, 0x2103u) : v;                               // TE1 = rotl8
-            t23[i] = hi ? __byte_perm(v, 0u, 0x0321u) : __byte_perm(v, 0u, 0x1032u);     // TE3 = rotl24 : TE2 = rotl16
+            t01[i] = hi ? __byte_perm(v, 0u, 0x2103u) : v;                               // T1 = rotl8
+            t23[i] = hi ? __byte_perm(v, 0u, 0x0321u) : __byte_perm(v, 0u, 0x1032u);     // T3 = rotl24 : T2 = rotl16
+        }
+        if (DEC) {
+            uint32_t* sis = reinterpret_cast<uint32_t*>(smem_raw + (AES_SIS - win));
+            for (int i = tid; i < 256 * 32; i += AES_THREADS) {
+                const uint32_t is = XMR_AES_RSBOX[i >> 5], sb = XMR_AES_SBOX[i >> 5];
+                sis[i] = is | (sb << 8) | (is << 16) | (sb << 24);
+            }
         }
     }
     __syncthreads();
-    const uint32_t lb0 = AES_TAB01 + 4u * lane, lb1 = AES_TAB01 + 128u + 4u * lane;
-    const uint32_t lb2 = AES_TAB23 + 4u * lane, lb3 = AES_TAB23 + 128u + 4u * lane;
+    AesLaneBases L;
+    L.lb0 = AES_TAB01 + 4u * lane; L.lb1 = AES_TAB01 + 128u + 4u * lane;
+    L.lb2 = AES_TAB23 + 4u * lane; L.lb3 = AES_TAB23 + 128u + 4u * lane;
+    L.sis2x = 2u * (AES_SIS + 4u * lane);
     const int r = Lanes<NC>::replica(lane);
     const int u = Lanes<NC>::unit(lane);
 
-    // every replica lane expands ITS OWN copy of the key (cloneGlobals: key[] is per-replica memory)
-    uint32_t rk[44];
+    // One-key modes: every replica lane expands ITS OWN copy of the key (cloneGlobals: key[] is per-replica memory).
+    //   encrypt: rk[4i..] = round key i.   decrypt: rk[0..3] = round key 10 (the first AddRoundKey, :127-129),
+    //   rk[4(rd+1)..] = InvMixColumns(round key 9-rd) for rd < 9, rk[40..43] = round key 0.
+    uint32_t rk[PERKEY ? 4 : 44];
+    if (!PERKEY) {
+        uint32_t k[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        rk[i] = (uint32_t)a.key[4 * i] | ((uint32_t)a.key[4 * i + 1] << 8) | ((uint32_t)a.key[4 * i + 2] << 16) | ((uint32_t)a.key[4 * i + 3] << 24);
+        for (int i = 0; i < 4; ++i)
+            k[i] = (uint32_t)a.key[4 * i] | ((uint32_t)a.key[4 * i + 1] << 8) | ((uint32_t)a.key[4 * i + 2] << 16) | ((uint32_t)a.key[4 * i + 3] << 24);
+        if (!DEC) {
 #pragma unroll
-    for (int rd = 0; rd < 10; ++rd) {                          // :214-221; S-box byte = byte 1 of TE0 = byte 2 of TE1 ...
-        const uint32_t w = rk[4 * rd + 3];
-        // SubWord(RotWord(w)): bytes (S[w.b1], S[w.b2], S[w.b3], S[w.b0])
-        const uint32_t sw = (tab_b1(lb2, w) & 0x000000FFu) | (tab_b2(lb0, w) & 0x0000FF00u) |
-                            (tab_b3(lb0, w) & 0x00FF0000u) | (tab_b0(lb1, w) & 0xFF000000u);
-        rk[4 * rd + 4] = rk[4 * rd] ^ sw ^ (uint32_t)XMR_AES_RCON[rd];
-        rk[4 * rd + 5] = rk[4 * rd + 1] ^ rk[4 * rd + 4];
-        rk[4 * rd + 6] = rk[4 * rd + 2] ^ rk[4 * rd + 5];
-        rk[4 * rd + 7] = rk[4 * rd + 3] ^ rk[4 * rd + 6];
+            for (int c = 0; c < 4; ++c) rk[c] = k[c];
+#pragma unroll
+            for (int rd = 0; rd < 10; ++rd) {
+                key_next<false>(L, k, rd);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) rk[4 * (rd + 1) + c] = k[c];
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) rk[40 + c] = k[c];      // round key 0
+#pragma unroll
+            for (int rd = 0; rd < 10; ++rd) {                   // :112-129; round key rd+1 is used by iteration 8-rd (rd < 9), round key 10 first
+                key_next<true>(L, k, rd);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) rk[rd < 9 ? 4 * (9 - rd) + c : c] = rd < 9 ? inv_mix_column(k[c]) : k[c];
+            }
+        }
     }
 
     const uint32_t n_tiles = a.n_tiles;
@@ -117,185 +248,70 @@ __device__ __forceinline__ void aes128_enc_body(const xmr_args& a, const CUtenso
 
         unsigned long long local[J];
         bool valid[J];
-        // fault of block j as branch-free masks: column word fcol[j], shifted bit fbit[j], applied when frd[j] == round
-        // (frd = -1: the replica's input copy, before round 0)
-        uint32_t fbit[J]; int frd[J], fcol[J];
+        uint32_t k[PERKEY ? J : 1][4];
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             local[j] = (unsigned long long)tile * TROWS + (unsigned)((warp * J + j) * UPW + u);
             valid[j] = local[j] < a.n_units;
-            fbit[j] = 0u; frd[j] = -2; fcol[j] = 0;
-            if (INJECT) {
-                Fault f = fault_for_unit(a, NC, valid[j] ? local[j] : 0ull, [](uint32_t) { return 8u; });
-                if (f.active && valid[j]) {
-                    if (Lanes<NC>::voter(lane)) tally.injected++;
-                    if ((int)f.replica == r) {
-                        const uint32_t i = f.site < 16u ? f.site : ((f.site - 16u) & 15u);
-                        frd[j] = f.site < 16u ? -1 : (int)((f.site - 16u) >> 4);
-                        fcol[j] = (int)(i >> 2);
-                        fbit[j] = (1u << f.bit) << (8u * (i & 3u));
-                    }
-                }
-                const uint32_t hit = frd[j] == -1 ? fbit[j] : 0u;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) s[j][c] ^= fcol[j] == c ? hit : 0u;
+            if (PERKEY) {
+                uint4 kq = make_uint4(0u, 0u, 0u, 0u);
+                if (valid[j]) kq = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(a.aux) + local[j] * 16ull));
+                k[j][0] = kq.x; k[j][1] = kq.y; k[j][2] = kq.z; k[j][3] = kq.w;
             }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) s[j][c] ^= rk[c];       // first half of :143-146 (state ^ key)
         }
+        // fault of block j as masks: column word fcol[j], shifted bit fbit[j], applied at the bottom of iteration frd[j]
+        // (frd = -1: the replica's input copy, before the first AddRoundKey; -2: none)
+        uint32_t fbit[J]; int frd[J], fcol[J];
+        bool hooks = false;
 #pragma unroll
-        for (int rd = 0; rd < 10; ++rd) {
+        for (int j = 0; j < J; ++j) { fbit[j] = 0u; frd[j] = -2; fcol[j] = 0; }
+        if (INJECT) {
+            uint32_t packed[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) {                       // the unit's Philox draw: evaluated by replica lane j % NC, shuffled to the others
+                packed[j] = 0u;
+                if (r == j % NC) {
+                    Fault f = fault_for_unit(a, NC, valid[j] ? local[j] : 0ull, [](uint32_t) { return 8u; });
+                    if (f.active && valid[j]) packed[j] = 0x80000000u | (f.replica << 29) | (f.site << 5) | f.bit;
+                }
+            }
+            bool mid = false;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                const uint32_t t0 = s[j][0], t1 = s[j][1], t2 = s[j][2], t3 = s[j][3];
-                uint32_t n[4];
-                if (rd < 9) {                                   // SubBytes + ShiftRows + MixColumns = 4 table rows XORed
-                    n[0] = tab_b0(lb0, t0) ^ tab_b1(lb1, t1) ^ tab_b2(lb2, t2) ^ tab_b3(lb3, t3);
-                    n[1] = tab_b0(lb0, t1) ^ tab_b1(lb1, t2) ^ tab_b2(lb2, t3) ^ tab_b3(lb3, t0);
-                    n[2] = tab_b0(lb0, t2) ^ tab_b1(lb1, t3) ^ tab_b2(lb2, t0) ^ tab_b3(lb3, t1);
-                    n[3] = tab_b0(lb0, t3) ^ tab_b1(lb1, t0) ^ tab_b2(lb2, t1) ^ tab_b3(lb3, t2);
-                } else {                                        // round 9: no MixColumns (:168); S[x] sits in byte p of the table picked per position
-                    n[0] = (tab_b0(lb2, t0) & 0x000000FFu) | (tab_b1(lb0, t1) & 0x0000FF00u) | (tab_b2(lb0, t2) & 0x00FF0000u) | (tab_b3(lb1, t3) & 0xFF000000u);
-                    n[1] = (tab_b0(lb2, t1) & 0x000000FFu) | (tab_b1(lb0, t2) & 0x0000FF00u) | (tab_b2(lb0, t3) & 0x00FF0000u) | (tab_b3(lb1, t0) & 0xFF000000u);
-                    n[2] = (tab_b0(lb2, t2) & 0x000000FFu) | (tab_b1(lb0, t3) & 0x0000FF00u) | (tab_b2(lb0, t0) & 0x00FF0000u) | (tab_b3(lb1, t1) & 0xFF000000u);
-                    n[3] = (tab_b0(lb2, t3) & 0x000000FFu) | (tab_b1(lb0, t0) & 0x0000FF00u) | (tab_b2(lb0, t1) & 0x00FF0000u) | (tab_b3(lb1, t2) & 0xFF000000u);
-                }
-                if (INJECT) {
-                    const uint32_t hit = frd[j] == rd ? fbit[j] : 0u;
+                const uint32_t e = NC == 1 ? packed[j] : __shfl_sync(0xFFFFFFFFu, packed[j], u * NC + j % NC);
+                if (e & 0x80000000u) {
+                    if (Lanes<NC>::voter(lane)) tally.injected++;
+                    if ((int)((e >> 29) & 3u) == r) {
+                        const uint32_t site = (e >> 5) & 0xFFFFFFu, bit = e & 31u;
+                        const uint32_t i = site < 16u ? site : ((site - 16u) & 15u);
+                        frd[j] = site < 16u ? -1 : (int)((site - 16u) >> 4);
+                        fcol[j] = (int)(i >> 2);
+                        fbit[j] = (1u << bit) << (8u * (i & 3u));
+                        if (frd[j] < 0) {                       // the replica's private copy of its input
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) n[c] ^= fcol[j] == c ? hit : 0u;
-                }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) s[j][c] = n[c] ^ rk[4 * (rd + 1) + c];   // next round's / last AddRoundKey
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < J; ++j)
-            aes_vote_store<NC>(s[j], static_cast<uint8_t*>(a.out), local[j], a.unit_base + local[j], valid[j], lane, a.flags, tally);
-    }
-    tally.flush(a.counters);
-}
-
-// ---------------------------------------------------------------------------------------------
-// General path: literal byte-wise control flow of aes_enc_dec(), both directions, optional
-// per-unit keys.  S-boxes live in shared memory (512 B).
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint8_t xtime8(uint8_t v) { return (uint8_t)((v << 1) ^ ((v & 0x80) ? 0x1b : 0)); }   // galois_mul2 :88-99
-
-template <int NC, bool INJECT>
-__device__ __forceinline__ void aes128_gen_body(const xmr_args& a) {
-    __shared__ uint8_t S[256], IS[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) { S[i] = XMR_AES_SBOX[i]; IS[i] = XMR_AES_RSBOX[i]; }
-    __syncthreads();
-    constexpr int UPW = Lanes<NC>::kUnitsPerWarp;
-    const int lane = threadIdx.x & 31;
-    const int r = Lanes<NC>::replica(lane);
-    const unsigned long long gwarp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-    const unsigned long long n_wtiles = (a.n_units + UPW - 1) / UPW;
-    const bool dir = a.mode & 1u, per_unit = a.mode & 2u;
-    Tally tally(a);
-    for (unsigned long long wt = gwarp; wt < n_wtiles; wt += nwarps) {
-        const unsigned long long local = wt * UPW + Lanes<NC>::unit(lane);
-        const bool valid = local < a.n_units;
-        const unsigned long long ld = valid ? local : 0ull;
-        uint8_t s[16], k[16];
-        {
-            uint4 q = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(a.in) + ld * 16ull);
-            uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int i = 0; i < 16; ++i) s[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
-            if (per_unit) {
-                uint4 kq = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(a.aux) + ld * 16ull);
-                uint32_t kw[4] = {kq.x, kq.y, kq.z, kq.w};
-#pragma unroll
-                for (int i = 0; i < 16; ++i) k[i] = (uint8_t)(kw[i >> 2] >> (8 * (i & 3)));
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) k[i] = a.key[i];
-            }
-        }
-        uint32_t fsite = 0xFFFFFFFFu; uint8_t fmask = 0;
-        if (INJECT) {
-            Fault f = fault_for_unit(a, NC, ld, [](uint32_t) { return 8u; });
-            if (f.active && valid) {
-                if (Lanes<NC>::voter(lane)) tally.injected++;
-                if ((int)f.replica == r) { fsite = f.site; fmask = (uint8_t)(1u << f.bit); }
-            }
-            if (fsite < 16u) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) if (fsite == (uint32_t)i) s[i] ^= fmask;
-            }
-        }
-        if (dir) {                                              // :112-129
-            for (int rd = 0; rd < 10; ++rd) {
-                k[0] ^= S[k[13]] ^ XMR_AES_RCON[rd]; k[1] ^= S[k[14]]; k[2] ^= S[k[15]]; k[3] ^= S[k[12]];
-#pragma unroll
-                for (int i = 4; i < 16; ++i) k[i] ^= k[i - 4];
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) s[i] ^= k[i];
-        }
-        for (int rd = 0; rd < 10; ++rd) {                       // :132
-            if (dir) {
-#pragma unroll
-                for (int i = 15; i > 3; --i) k[i] ^= k[i - 4];  // :134-137
-                k[0] ^= S[k[13]] ^ XMR_AES_RCON[9 - rd]; k[1] ^= S[k[14]]; k[2] ^= S[k[15]]; k[3] ^= S[k[12]];   // :138-141
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) s[i] = S[s[i] ^ k[i]];   // :143-146
-                uint8_t t;                                      // :147-166 shift rows
-                t = s[1]; s[1] = s[5]; s[5] = s[9]; s[9] = s[13]; s[13] = t;
-                t = s[2]; s[2] = s[10]; s[10] = t; t = s[6]; s[6] = s[14]; s[14] = t;
-                t = s[15]; s[15] = s[11]; s[11] = s[7]; s[7] = s[3]; s[3] = t;
-            }
-            if ((rd > 0 && dir) || (rd < 9 && !dir)) {          // :168-185
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint8_t* p = s + 4 * c;
-                    if (dir) {                                  // :172-177 inverse pre-multiply
-                        uint8_t b1 = xtime8(xtime8(p[0] ^ p[2])), b2 = xtime8(xtime8(p[1] ^ p[3]));
-                        p[0] ^= b1; p[1] ^= b2; p[2] ^= b1; p[3] ^= b2;
+                            for (int c = 0; c < 4; ++c) s[j][c] ^= fcol[j] == c ? fbit[j] : 0u;
+                        } else mid = true;
                     }
-                    uint8_t all = p[0] ^ p[1] ^ p[2] ^ p[3], first = p[0];
-                    p[0] ^= xtime8(p[0] ^ p[1]) ^ all;
-                    p[1] ^= xtime8(p[1] ^ p[2]) ^ all;
-                    p[2] ^= xtime8(p[2] ^ p[3]) ^ all;
-                    p[3] ^= xtime8(p[3] ^ first) ^ all;
                 }
             }
-            if (dir) {
-                uint8_t t;                                      // :187-206 inverse shift rows
-                t = s[13]; s[13] = s[9]; s[9] = s[5]; s[5] = s[1]; s[1] = t;
-                t = s[10]; s[10] = s[2]; s[2] = t; t = s[14]; s[14] = s[6]; s[6] = t;
-                t = s[3]; s[3] = s[7]; s[7] = s[11]; s[11] = s[15]; s[15] = t;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) s[i] = IS[s[i]] ^ k[i];   // :208-211
-            } else {
-                k[0] ^= S[k[13]] ^ XMR_AES_RCON[rd]; k[1] ^= S[k[14]]; k[2] ^= S[k[15]]; k[3] ^= S[k[12]];   // :214-221
-#pragma unroll
-                for (int i = 4; i < 16; ++i) k[i] ^= k[i - 4];
-            }
-            if (INJECT && fsite >= 16u && (fsite - 16u) >> 4 == (uint32_t)rd) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) if (((fsite - 16u) & 15u) == (uint32_t)i) s[i] ^= fmask;
-            }
+            hooks = __any_sync(0xFFFFFFFFu, mid);               // warp-uniform: a warp without a mid-round hit runs the plain rounds
         }
-        if (!dir) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) s[i] ^= k[i];          // :224-229
+        for (int j = 0; j < J; ++j) {
+            if (PERKEY && DEC) {
+#pragma unroll
+                for (int rd = 0; rd < 10; ++rd) key_next<true>(L, k[j], rd);      // :112-126: run the schedule to the last round key
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s[j][c] ^= PERKEY ? k[j][c] : rk[c];      // first half of :143-146 / :127-129
         }
-        uint32_t c[4];
+        if (INJECT && hooks) aes_rounds<J, DEC, PERKEY, true>(L, s, k, rk, fbit, frd, fcol);
+        else aes_rounds<J, DEC, PERKEY, false>(L, s, k, rk, fbit, frd, fcol);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            c[i] = (uint32_t)s[4 * i] | ((uint32_t)s[4 * i + 1] << 8) | ((uint32_t)s[4 * i + 2] << 16) | ((uint32_t)s[4 * i + 3] << 24);
-        aes_vote_store<NC>(c, static_cast<uint8_t*>(a.out), local, a.unit_base + local, valid, lane, a.flags, tally);
-        if ((a.mode & 4u) && per_unit && valid && Lanes<NC>::voter(lane)) {      // COAST_AES_KEY_WRITEBACK: replica 0's mutated key[]
-            uint32_t kw[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                kw[i] = (uint32_t)k[4 * i] | ((uint32_t)k[4 * i + 1] << 8) | ((uint32_t)k[4 * i + 2] << 16) | ((uint32_t)k[4 * i + 3] << 24);
-            *reinterpret_cast<uint4*>(static_cast<uint8_t*>(const_cast<void*>(a.aux)) + local * 16ull) = make_uint4(kw[0], kw[1], kw[2], kw[3]);
+        for (int j = 0; j < J; ++j) {
+            aes_vote_store<NC>(s[j], static_cast<uint8_t*>(a.out), local[j], a.unit_base + local[j], valid[j], lane, a.flags, tally);
+            if (PERKEY && (a.mode & 4u) && valid[j] && Lanes<NC>::voter(lane))       // COAST_AES_KEY_WRITEBACK: replica 0's mutated key[]
+                *reinterpret_cast<uint4*>(static_cast<uint8_t*>(const_cast<void*>(a.aux)) + local[j] * 16ull) = make_uint4(k[j][0], k[j][1], k[j][2], k[j][3]);
         }
     }
     tally.flush(a.counters);
@@ -303,17 +319,13 @@ __device__ __forceinline__ void aes128_gen_body(const xmr_args& a) {
 
 }  // namespace xmr
 
-#define XMR_AES_ENC_KERNEL(NC, INJ)                                                                      \
+#define XMR_AES_KERNEL(NAME, NC, INJ, DEC, PERKEY)                                                       \
     extern "C" __global__ void __launch_bounds__(xmr::AES_THREADS, 1)                                    \
-    xmr_aes128_enc_nc##NC##_inj##INJ(const __grid_constant__ xmr_args a, const __grid_constant__ CUtensorMap tmap) { \
-        xmr::aes128_enc_body<NC, INJ != 0>(a, &tmap);                                                    \
+    xmr_aes128_##NAME##_nc##NC##_inj##INJ(const __grid_constant__ xmr_args a, const __grid_constant__ CUtensorMap tmap) { \
+        xmr::aes128_body<NC, INJ != 0, DEC, PERKEY>(a, &tmap);                                           \
     }
-#define XMR_AES_GEN_KERNEL(NC, INJ)                                                                      \
-    extern "C" __global__ void __launch_bounds__(XMR_CTA_THREADS)                                        \
-    xmr_aes128_gen_nc##NC##_inj##INJ(const __grid_constant__ xmr_args a) {                               \
-        xmr::aes128_gen_body<NC, INJ != 0>(a);                                                           \
-    }
-XMR_AES_ENC_KERNEL(1, 0) XMR_AES_ENC_KERNEL(2, 0) XMR_AES_ENC_KERNEL(3, 0)
-XMR_AES_ENC_KERNEL(1, 1) XMR_AES_ENC_KERNEL(2, 1) XMR_AES_ENC_KERNEL(3, 1)
-XMR_AES_GEN_KERNEL(1, 0) XMR_AES_GEN_KERNEL(2, 0) XMR_AES_GEN_KERNEL(3, 0)
-XMR_AES_GEN_KERNEL(1, 1) XMR_AES_GEN_KERNEL(2, 1) XMR_AES_GEN_KERNEL(3, 1)
+#define XMR_AES_ALL(NC, INJ) \
+    XMR_AES_KERNEL(enc, NC, INJ, false, false) XMR_AES_KERNEL(dec, NC, INJ, true, false) \
+    XMR_AES_KERNEL(enck, NC, INJ, false, true) XMR_AES_KERNEL(deck, NC, INJ, true, true)
+XMR_AES_ALL(1, 0) XMR_AES_ALL(2, 0) XMR_AES_ALL(3, 0)
+XMR_AES_ALL(1, 1) XMR_AES_ALL(2, 1) XMR_AES_ALL(3, 1)

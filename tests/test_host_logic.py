@@ -214,8 +214,8 @@ def test_reference_entry_points_drive_the_host_call(mock_dir, tmp_path):
     res, ev = run_child(mock_dir, tmp_path, [dict(op="entries", passes="-TMR -countErrors"), dict(op="shutdown")])
     assert res["ops"][0]["rc"] == 0 and not [e for e in ev if e["op"] == "error"], [e for e in ev if e["op"] == "error"]
     names = [e["name"] for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
-    assert names == ["xmr_crc16_gen_nc3_inj0", "xmr_sha256_gen_nc3_inj0", "xmr_sha256_gen_nc3_inj0", "xmr_aes128_gen_nc3_inj0",
-                     "xmr_aes128_gen_nc3_inj0", "xmr_mm_u32_nc3_inj0", "xmr_chsha_nc3_inj0"]
+    assert names == ["xmr_crc16_gen_nc3_inj0", "xmr_sha256_gen_nc3_inj0", "xmr_sha256_gen_nc3_inj0", "xmr_aes128_enck_nc3_inj0",
+                     "xmr_aes128_deck_nc3_inj0", "xmr_mm_u32_nc3_inj0", "xmr_chsha_nc3_inj0"]
     args = [args_of(e) for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
     assert [a.unit_bytes for a in args[:3]] == [13, 10, 0] and all(a.n_units == 1 for a in args[:5]) and args[5].n_units == 81
     assert args[3].mode == 2 | 4 and args[4].mode == 1 | 2 | 4          # per-unit key + write-back (+ decrypt): key[] is mutated in place
@@ -279,12 +279,14 @@ def test_sha_layout_flags_select_the_kernel(mock_dir, tmp_path, flags, mode, nc,
     assert [e["name"] for e in ev if e["op"] == "launch" and "_nc" in e["name"]] == [want]
 
 
-def test_aes_decrypt_and_per_unit_keys_use_the_general_kernel(mock_dir, tmp_path):
+def test_aes_decrypt_and_per_unit_keys_select_the_table_kernels(mock_dir, tmp_path):
     res, ev = run_child(mock_dir, tmp_path, [dict(op="launch", kernel=K_AES128, nc=2, n=1000, mode=1, in_bytes=16000, out_bytes=16000),
                                              dict(op="launch", kernel=K_AES128, nc=2, n=1000, mode=2, in_bytes=16000, out_bytes=16000, aux_bytes=16000),
                                              dict(op="launch", kernel=K_AES128, nc=2, n=1000, mode=2, in_bytes=16000, out_bytes=16000)])
     assert [r["rc"] == 0 for r in res["ops"]] == [True, True, False] and "per-unit keys need d_aux" in res["ops"][2]["err"]
-    assert [e["name"] for e in ev if e["op"] == "launch" and "_nc" in e["name"]] == ["xmr_aes128_gen_nc2_inj0"] * 2
+    la = [e for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
+    assert [e["name"] for e in la] == ["xmr_aes128_dec_nc2_inj0", "xmr_aes128_enck_nc2_inj0"]
+    assert [e["smem"] for e in la] == [0x38000, 0x30000] and all(e["block"] == 512 for e in la)   # decrypt adds the 32 KiB (InvS, S) table
 
 
 def test_sync_folds_counters_into_the_reference_symbols(mock_dir, tmp_path):
