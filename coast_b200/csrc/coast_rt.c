@@ -74,6 +74,10 @@ __attribute__((weak)) void FAULT_DETECTED_DWC(void) { /* synchronization.cpp:125
     X(cuStreamCreate, (CUstream*, unsigned int))                                                             \
     X(cuStreamDestroy_v2, (CUstream))                                                                        \
     X(cuStreamSynchronize, (CUstream))                                                                       \
+    X(cuEventCreate, (CUevent*, unsigned int))                                                               \
+    X(cuEventRecord, (CUevent, CUstream))                                                                    \
+    X(cuEventDestroy_v2, (CUevent))                                                                          \
+    X(cuStreamWaitEvent, (CUstream, CUevent, unsigned int))                                                  \
     X(cuGetErrorString, (CUresult, const char**))                                                            \
     X(cuTensorMapEncodeTiled, (CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,      \
                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, \
@@ -104,14 +108,15 @@ static struct {
     /* stream-ordered scratch (the replicas' private arrays of xmr_qsort.cuh): any number of streams may launch at once */
     CUmemoryPool pool;
     CUdeviceptr h_stat[3]; size_t h_stat_cap[3];     /* per-slot d_status staging of coast_run_host */
+    CUdeviceptr h_b; size_t h_b_cap; CUevent ev_b;   /* matmul host call: the replicated operand B and "B has landed" */
     int numa_node;                   /* NUMA node the process was bound to by coast_init (-1: not bound) */
     int busy;                        /* one host thread at a time (the reference is single-threaded); others fail loudly */
     /* tensor maps of the row-tiled kernels, keyed by (base, row bytes, rows, box rows, swizzle): coast_run_host re-encodes the
      * same few maps every call */
     struct { const void* base; uint32_t row_bytes, box_rows; uint64_t rows; int swz; CUtensorMap map; } tmaps[16];
     int n_tmaps, tmap_next;
-    int zero_copy_default;           /* host-call path for pinned buffers: 1 = one zero-copy launch, 0 = staged chunks */
-    const char* last_host_path;      /* "zerocopy" | "staged" | "one-shot": what the last coast_run_host did */
+    int host_path_default;           /* host-call path for pinned buffers: 0 = staged, 1 = hybrid, 2 = zero-copy */
+    const char* last_host_path;      /* "staged" | "hybrid" | "zerocopy" | "row-blocks" | "one-shot": what the last coast_run_host did */
 } G;
 
 /* Single-caller guard.  The reference's emitted code is single-threaded (plain load/add/store on its counters,
@@ -277,7 +282,7 @@ static int init_impl(int device) {
     }
     p_cuDeviceGetAttribute(&G.sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, G.dev);
     numa_bind_to_gpu();
-    G.zero_copy_default = 0;        /* measured r02 (profiles/r02_e2e_zero_copy_experiment.md): SM writes to host memory lose to staged D2H */
+    G.host_path_default = 0;        /* measured r02 (profiles/r02_e2e_zero_copy_experiment.md) */
     r = p_cuModuleLoadData(&G.mod, coast_kernels_cubin);
     if (r != CUDA_SUCCESS) { p_cuDevicePrimaryCtxRelease_v2(G.dev); return drv_fail(r, "cuModuleLoadData(sm_100a cubin)"); }
     DRV(p_cuMemAlloc_v2(&G.counters, XMR_CTR_COUNT * sizeof(uint64_t)));
@@ -309,6 +314,7 @@ static int shutdown_impl(void) {
         if (G.h_aux[i]) p_cuMemFree_v2(G.h_aux[i]);
         if (G.h_stat[i]) p_cuMemFree_v2(G.h_stat[i]);
         if (G.hs[i]) p_cuStreamDestroy_v2(G.hs[i]);
+        if (i == 0) { if (G.h_b) p_cuMemFree_v2(G.h_b); if (G.ev_b) p_cuEventDestroy_v2(G.ev_b); G.h_b = 0; G.h_b_cap = 0; G.ev_b = NULL; }
         G.h_in[i] = G.h_out[i] = G.h_aux[i] = G.h_stat[i] = 0;
         G.h_in_cap[i] = G.h_out_cap[i] = G.h_aux_cap[i] = G.h_stat_cap[i] = 0; G.hs[i] = NULL;
     }
@@ -666,7 +672,13 @@ static int launch_impl(const coast_launch_desc* d, void* stream) {
         a.n_tiles = (unsigned)n_tiles;
         unsigned loads = (tile_rows + 255u) / 256u;
         while (tile_rows % loads) ++loads;                        /* mirrors TileRing::pick_loads() */
-        rc = encode_rows_map(&map, d->d_in, row_bytes, d->n_units, tile_rows / loads, swz); if (rc) return rc;
+        unsigned pack = 0;                                        /* AES: the same dense bytes as 256- or 64-byte rows when the count allows */
+        if (d->kernel == COAST_K_AES128) {
+            pack = d->n_units % 16u == 0 ? 4u : d->n_units % 4u == 0 ? 2u : 0u;
+            while (pack && (tile_rows / loads) % (1u << pack)) pack -= 2u;
+            a.mode = (a.mode & ~0xF00u) | (pack << 8);
+        }
+        rc = encode_rows_map(&map, d->d_in, row_bytes << pack, d->n_units >> pack, (tile_rows / loads) >> pack, swz); if (rc) return rc;
         uint64_t cap = (uint64_t)G.sm_count * (unsigned)occ;
         grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
     } else if (mm_tiled) {
@@ -800,7 +812,7 @@ static int drain_host_streams(void) {
 }
 
 /* Chunked pipeline: H2D -> kernel -> D2H per chunk, chunks round-robin over 3 streams / 3 staging slots. */
-static int run_host_staged(const coast_launch_desc* d, uint64_t ib, uint64_t ob, int per_unit_key) {
+static int run_host_staged(const coast_launch_desc* d, uint64_t ib, uint64_t ob, int per_unit_key, CUdeviceptr zin) {
     int rc;
     const uint64_t ibs = ib ? ib : 1;                          /* divisor of the chunk schedule */
     /* each chunk is its own launch (own tensor map); the fault plan is keyed by the global unit index so
@@ -825,11 +837,16 @@ static int run_host_staged(const coast_launch_desc* d, uint64_t ib, uint64_t ob,
         if (n < min_chunk) n = min_chunk;
         if (n > left) n = left;
         ramp *= 2;
-        rc = slot_reserve(&G.h_in[slot], &G.h_in_cap[slot], (size_t)(chunk * ib) > 16 ? (size_t)(chunk * ib) : 16); if (rc) goto fail;
         rc = slot_reserve(&G.h_out[slot], &G.h_out_cap[slot], (size_t)(chunk * ob)); if (rc) goto fail;
-        if (ib) STEP(p_cuMemcpyHtoDAsync_v2(G.h_in[slot], (const uint8_t*)d->d_in + done * ib, (size_t)(n * ib), G.hs[slot]));
         coast_launch_desc c = *d;
-        c.d_in = (void*)G.h_in[slot]; c.d_out = (void*)G.h_out[slot];
+        if (zin) {                                                 /* hybrid: the kernel reads this chunk straight from mapped host memory */
+            c.d_in = (void*)(zin + done * ib);
+        } else {
+            rc = slot_reserve(&G.h_in[slot], &G.h_in_cap[slot], (size_t)(chunk * ib) > 16 ? (size_t)(chunk * ib) : 16); if (rc) goto fail;
+            if (ib) STEP(p_cuMemcpyHtoDAsync_v2(G.h_in[slot], (const uint8_t*)d->d_in + done * ib, (size_t)(n * ib), G.hs[slot]));
+            c.d_in = (void*)G.h_in[slot];
+        }
+        c.d_out = (void*)G.h_out[slot];
         c.n_units = n; c.unit_base = d->unit_base + done;
         if (per_unit_key) {
             rc = slot_reserve(&G.h_aux[slot], &G.h_aux_cap[slot], (size_t)(chunk * 16)); if (rc) goto fail;
@@ -858,6 +875,52 @@ fail:
     return rc;
 }
 
+/* Matmul host call.  B (replicated operand) goes up once; C is produced in row blocks: block i's rows of A upload, its
+ * launch and the download of its rows of C run on stream i % 3, so uploads, tensor-core work and downloads of
+ * neighbouring blocks overlap (PCIe is full duplex).  The fault plan is keyed by the global element index
+ * (unit_base + row * N + col), so blocking never changes results.  Small or oddly-shaped problems go in one block. */
+static int run_host_matmul(const coast_launch_desc* d, coast_stats* out, int* dwc_fired) {
+    int rc;
+    const size_t bb = (size_t)d->K * d->N * 4;
+    uint32_t blocks = 1, rows = d->M;
+    { const char* hp = getenv("COAST_HOST_PATH");
+      if (d->M % 128u == 0 && d->M >= 512u && !(hp && !strcmp(hp, "one-shot"))) {
+          blocks = d->M / 128u < 8u ? d->M / 128u : 8u;
+          rows = ((d->M / 128u + blocks - 1u) / blocks) * 128u;
+          blocks = (d->M + rows - 1u) / rows;
+      } }
+    rc = slot_reserve(&G.h_b, &G.h_b_cap, bb); if (rc) return rc;
+    if (!G.ev_b) DRV(p_cuEventCreate(&G.ev_b, CU_EVENT_DISABLE_TIMING));
+    for (int i = 0; i < 3 && (uint32_t)i < blocks; ++i) {
+        rc = slot_reserve(&G.h_in[i], &G.h_in_cap[i], (size_t)rows * d->K * 4); if (rc) return rc;
+        rc = slot_reserve(&G.h_out[i], &G.h_out_cap[i], (size_t)rows * d->N * 4); if (rc) return rc;
+    }
+#define STEP(call) do { CUresult r_ = (call); if (r_ != CUDA_SUCCESS) { rc = drv_fail(r_, #call); goto fail; } } while (0)
+    /* the first block of A leads on stream 0, B follows on stream 1: the first launch needs both, later blocks only their A */
+    for (uint32_t i = 0; i < blocks; ++i) {
+        const int slot = (int)(i % 3u);
+        const uint32_t r0 = i * rows, nr = d->M - r0 < rows ? d->M - r0 : rows;
+        STEP(p_cuMemcpyHtoDAsync_v2(G.h_in[slot], (const uint8_t*)d->d_in + (size_t)r0 * d->K * 4, (size_t)nr * d->K * 4, G.hs[slot]));
+        if (i == 0) {
+            STEP(p_cuMemcpyHtoDAsync_v2(G.h_b, d->d_aux, bb, G.hs[1]));
+            STEP(p_cuEventRecord(G.ev_b, G.hs[1]));
+        }
+        STEP(p_cuStreamWaitEvent(G.hs[slot], G.ev_b, 0));
+        coast_launch_desc c = *d;
+        c.d_in = (void*)G.h_in[slot]; c.d_aux = (void*)G.h_b; c.d_out = (void*)G.h_out[slot];
+        c.M = nr; c.n_units = (uint64_t)nr * d->N; c.unit_base = d->unit_base + (uint64_t)r0 * d->N;
+        rc = launch_impl(&c, G.hs[slot]); if (rc) goto fail;
+        STEP(p_cuMemcpyDtoHAsync_v2((uint8_t*)d->d_out + (size_t)r0 * d->N * 4, G.h_out[slot], (size_t)nr * d->N * 4, G.hs[slot]));
+    }
+#undef STEP
+    G.last_host_path = blocks > 1 ? "row-blocks" : "one-shot";
+    DRV(p_cuStreamSynchronize(G.hs[0])); DRV(p_cuStreamSynchronize(G.hs[1]));
+    return sync_impl(G.hs[2], out, dwc_fired);
+fail:
+    { char keep[sizeof G.err]; memcpy(keep, G.err, sizeof keep); drain_host_streams(); memcpy(G.err, keep, sizeof keep); }
+    return rc;
+}
+
 /* `d_in` / `d_out` / `d_aux` / `d_status` of the descriptor are HOST pointers here. */
 static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int* dwc_fired) {
     int rc = ensure_ctx(); if (rc) return rc;
@@ -865,20 +928,9 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int* dwc_
     if (d->plan && d->plan->mode == COAST_PLAN_TABLE) return fail(COAST_ERR_UNSUPPORTED, "coast_run_host: TABLE plans need device pointers; use coast_launch");
     for (int i = 0; i < 3; ++i) if (!G.hs[i]) DRV(p_cuStreamCreate(&G.hs[i], CU_STREAM_NON_BLOCKING));
     const uint64_t ob = coast_out_bytes(d->kernel, d->unit_bytes);
-    if (d->kernel == COAST_K_MM_U32 || d->kernel == COAST_K_GEMM_TF32) {   /* one shot: A, B in; C out */
+    if (d->kernel == COAST_K_MM_U32 || d->kernel == COAST_K_GEMM_TF32) {
         if (d->d_status) return fail(COAST_ERR_UNSUPPORTED, "coast_run_host: d_status is not staged for the matmul kernels; use coast_launch");
-        size_t ab = (size_t)d->M * d->K * 4, bb = (size_t)d->K * d->N * 4, cb = (size_t)d->M * d->N * 4;
-        rc = slot_reserve(&G.h_in[0], &G.h_in_cap[0], ab); if (rc) return rc;
-        rc = slot_reserve(&G.h_aux[0], &G.h_aux_cap[0], bb); if (rc) return rc;
-        rc = slot_reserve(&G.h_out[0], &G.h_out_cap[0], cb); if (rc) return rc;
-        DRV(p_cuMemcpyHtoDAsync_v2(G.h_in[0], d->d_in, ab, G.hs[0]));
-        DRV(p_cuMemcpyHtoDAsync_v2(G.h_aux[0], d->d_aux, bb, G.hs[0]));
-        coast_launch_desc c = *d; c.d_in = (void*)G.h_in[0]; c.d_aux = (void*)G.h_aux[0]; c.d_out = (void*)G.h_out[0];
-        rc = launch_impl(&c, G.hs[0]);
-        if (rc) { char keep[sizeof G.err]; memcpy(keep, G.err, sizeof keep); p_cuStreamSynchronize(G.hs[0]); memcpy(G.err, keep, sizeof keep); return rc; }
-        DRV(p_cuMemcpyDtoHAsync_v2(d->d_out, G.h_out[0], cb, G.hs[0]));
-        G.last_host_path = "one-shot";
-        return sync_impl(G.hs[0], out, dwc_fired);
+        return run_host_matmul(d, out, dwc_fired);
     }
     const uint64_t ib = in_bytes_per_unit(d);
     /* a zero-length SHA-256 message (sha256_hash(len = 0) hashes one padded block) has nothing to stage */
@@ -886,15 +938,21 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int* dwc_
     const int per_unit_key = d->kernel == COAST_K_AES128 && (d->mode & COAST_AES_KEY_PER_UNIT);
     if (d->n_units == 0) return sync_impl(G.hs[2], out, dwc_fired);
 
-    /* ZERO-COPY path: when every host buffer is pinned (hence mapped into the GPU's address space) and the kernel reads
-     * each input byte exactly once, ONE launch streams the input over PCIe through the TMA ring / vector loads and
-     * writes the voted output straight back to host memory -- upload, compute and download overlap inside the kernel
-     * at tile granularity, no staging buffers, no chunk schedule.  COAST_HOST_PATH=staged|zerocopy overrides. */
+    /* Three ways to move the bytes (COAST_HOST_PATH=staged|hybrid|zerocopy overrides the default):
+     *   staged  : H2D -> kernel -> D2H per chunk over three streams (any host memory);
+     *   hybrid  : pinned input + a kernel that reads each input byte once: the chunks' kernels read mapped host memory
+     *             directly through the TMA ring (no upload copies, no input staging), outputs are staged and downloaded
+     *             per chunk;
+     *   zerocopy: ONE launch reads and WRITES mapped host memory.  Measured r02: SM stores of 16-32 bytes per lane to host
+     *             memory lose to the copy engine (profiles/r02_e2e_zero_copy_experiment.md); kept for small calls. */
     const char* hp = getenv("COAST_HOST_PATH");
     const int streams_once = d->kernel == COAST_K_CRC16 || d->kernel == COAST_K_SHA256 || d->kernel == COAST_K_AES128 ||
                              d->kernel == COAST_K_CHSTONE_SHA;
-    if (streams_once && !(hp && !strcmp(hp, "staged")) && (G.zero_copy_default || (hp && !strcmp(hp, "zerocopy")))) {
-        CUdeviceptr zi = ib ? host_alias(d->d_in, (size_t)(d->n_units * ib)) : (CUdeviceptr)G.counters /* never read */;
+    const int want = hp ? (!strcmp(hp, "zerocopy") ? 2 : !strcmp(hp, "hybrid") ? 1 : 0) : G.host_path_default;
+    CUdeviceptr zin = 0;
+    if (streams_once && want && ib) zin = host_alias(d->d_in, (size_t)(d->n_units * ib));
+    if (want == 2 && streams_once) {
+        CUdeviceptr zi = ib ? zin : (CUdeviceptr)G.counters /* never read */;
         CUdeviceptr zo = host_alias(d->d_out, (size_t)(d->n_units * ob));
         CUdeviceptr za = per_unit_key ? host_alias(d->d_aux, (size_t)(d->n_units * 16)) : 0;
         CUdeviceptr zs = d->d_status ? host_alias(d->d_status, (size_t)d->n_units) : 0;
@@ -907,10 +965,11 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int* dwc_
             G.last_host_path = "zerocopy";
             return sync_impl(G.hs[2], out, dwc_fired);
         }
-        if (hp && !strcmp(hp, "zerocopy")) return fail(COAST_ERR_BAD_ARG, "COAST_HOST_PATH=zerocopy needs pinned (mapped) host buffers");
+        if (hp) return fail(COAST_ERR_BAD_ARG, "COAST_HOST_PATH=zerocopy needs pinned (mapped) host buffers");
     }
-    rc = run_host_staged(d, ib, ob, per_unit_key); if (rc) return rc;
-    G.last_host_path = "staged";
+    if (hp && want == 1 && streams_once && ib && !zin) return fail(COAST_ERR_BAD_ARG, "COAST_HOST_PATH=hybrid needs a pinned (mapped) input buffer");
+    rc = run_host_staged(d, ib, ob, per_unit_key, want ? zin : 0); if (rc) return rc;
+    G.last_host_path = (want && zin) ? "hybrid" : "staged";
     DRV(p_cuStreamSynchronize(G.hs[0])); DRV(p_cuStreamSynchronize(G.hs[1]));
     return sync_impl(G.hs[2], out, dwc_fired);
 }

@@ -168,7 +168,7 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
     const uint32_t win = smem_u32(smem_raw);                    // shared-window address of the dynamic region
     uint8_t* ring_mem = smem_raw + ((1024u - (win & 1023u)) & 1023u);
     Ring ring;
-    ring.init(ring_mem, tmap);
+    ring.init(ring_mem, tmap, (a.mode >> 8) & 15u);             // XMR_AES_ROWPACK: 16-byte blocks described as 64- or 256-byte rows
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {   // build the tables
         uint32_t* t01 = reinterpret_cast<uint32_t*>(smem_raw + (AES_TAB01 - win));

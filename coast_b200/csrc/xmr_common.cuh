@@ -210,7 +210,12 @@ struct TileRing {
     uint8_t* tiles;
     uint64_t* full;
     const CUtensorMap* tmap;
-    __device__ __forceinline__ void init(uint8_t* smem, const CUtensorMap* map) {
+    // The host may describe the same dense bytes with rows 2^pack_shift times longer (box {ROW_BYTES << s, BOX_ROWS >> s}):
+    // identical shared-memory image, fewer and larger requests -- what matters when the tensor lives in mapped HOST memory
+    // and every row is its own PCIe read (16-byte AES rows: r02 zero-copy experiment).
+    uint32_t pack_shift = 0;
+    __device__ __forceinline__ void init(uint8_t* smem, const CUtensorMap* map, uint32_t row_pack_shift = 0) {
+        pack_shift = row_pack_shift;
         tiles = smem;
         full = reinterpret_cast<uint64_t*>(smem + XMR_STAGES * STAGE_STRIDE);
         tmap = map;
@@ -228,7 +233,7 @@ struct TileRing {
 #pragma unroll
             for (int l = 0; l < LOADS; ++l)
                 tma_load_2d(tiles + stage * STAGE_STRIDE + l * BOX_ROWS * ROW_BYTES, tmap, &full[stage], 0,
-                            (int)(tile * TILE_ROWS + l * BOX_ROWS));
+                            (int)((tile * TILE_ROWS + l * BOX_ROWS) >> pack_shift));
         }
     }
     __device__ __forceinline__ const uint8_t* wait(uint32_t it) {

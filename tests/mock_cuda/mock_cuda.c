@@ -187,6 +187,10 @@ CUresult cuMemFreeHost(void* p) { return do_free((CUdeviceptr)(uintptr_t)p); }
 CUresult cuStreamCreate(CUstream* s, unsigned int flags) { (void)flags; *s = (CUstream)(uintptr_t)(0x1000 + ++n_streams); return CUDA_SUCCESS; }
 CUresult cuStreamDestroy_v2(CUstream s) { (void)s; return CUDA_SUCCESS; }
 CUresult cuStreamSynchronize(CUstream s) { LOG("{\"op\":\"stream_sync\",\"stream\":%d}", stream_id(s)); return CUDA_SUCCESS; }
+CUresult cuEventCreate(CUevent* e, unsigned int flags) { (void)flags; *e = (CUevent)&fake_mod; return CUDA_SUCCESS; }
+CUresult cuEventRecord(CUevent e, CUstream s) { (void)e; LOG("{\"op\":\"event_record\",\"stream\":%d}", stream_id(s)); return CUDA_SUCCESS; }
+CUresult cuEventDestroy_v2(CUevent e) { (void)e; return CUDA_SUCCESS; }
+CUresult cuStreamWaitEvent(CUstream s, CUevent e, unsigned int f) { (void)e; (void)f; LOG("{\"op\":\"wait_event\",\"stream\":%d}", stream_id(s)); return CUDA_SUCCESS; }
 CUresult cuGetErrorString(CUresult r, const char** s) { (void)r; *s = "mock driver error"; return CUDA_SUCCESS; }
 
 CUresult cuTensorMapEncodeTiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank, void* addr, const cuuint64_t* gdim,

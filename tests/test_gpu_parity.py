@@ -369,7 +369,14 @@ def test_host_call_zero_copy_and_staged_agree_with_the_oracle(rt, oracle, case):
     p = 0.02
     o_out, o_st = oracle.run(kernel, nc, inp, n, plan=oracle.make_plan(oracle.PLAN_BERNOULLI, seed=21, p=p), unit_base=123, **okw)
     plan = cb.FaultPlan(mode=cb.PLAN_BERNOULLI, seed=21, p=p)
-    for pinned in (True, False):
+    import os
+    for pinned, path in ((True, "zerocopy"), (True, "hybrid"), (True, "staged"), (False, None)):
+        if path:
+            os.environ["COAST_HOST_PATH"] = path
+        else:
+            os.environ.pop("COAST_HOST_PATH", None)
+        if case == "sha0" and path == "hybrid":
+            continue                                        # nothing to read: there is no input to alias
         mk = (lambda a: torch.from_numpy(a.copy()).pin_memory()) if pinned else (lambda a: a.copy())
         h_in = mk(inp)
         h_out = mk(np.zeros(n * ob, dtype=np.uint8))
@@ -382,11 +389,12 @@ def test_host_call_zero_copy_and_staged_agree_with_the_oracle(rt, oracle, case):
         from coast_b200.runtime import _Stats
         st = _Stats()
         rc = rt.L.coast_run_host_noabort(C.byref(d), C.byref(st))
+        os.environ.pop("COAST_HOST_PATH", None)
         assert rc == 0, rt.L.coast_last_error()
-        assert rt.last_host_path == ("zerocopy" if pinned else "staged")
+        assert rt.last_host_path == (path or "staged")
         got = h_out.numpy() if pinned else h_out
-        assert got.tobytes() == o_out.tobytes(), (case, pinned)
-        assert {k: getattr(st, k) for k in STAT_KEYS} == {k: o_st[k] for k in STAT_KEYS}, (case, pinned)
+        assert got.tobytes() == o_out.tobytes(), (case, path)
+        assert {k: getattr(st, k) for k in STAT_KEYS} == {k: o_st[k] for k in STAT_KEYS}, (case, path)
         status = h_status.numpy() if pinned else h_status
         bad_units = int((status != 0).sum())
         assert int(status.max()) <= 32                              # every byte was written (0xEE poison gone)
@@ -394,6 +402,28 @@ def test_host_call_zero_copy_and_staged_agree_with_the_oracle(rt, oracle, case):
             assert bad_units == o_st["dwc_detected"]
         else:
             assert int(status.astype(np.int64).sum()) == o_st["errors_corrected"]
+
+
+@pytest.mark.parametrize("kernel", ["gemm", "mm"])
+def test_matmul_host_call_row_blocks_equal_the_device_launch(rt, oracle, kernel):
+    """coast_run_host() pipelines a large matmul by C row blocks (B once, A rows up / launch / C rows down per block on rotating
+    streams); the plan is keyed by the global element index, so outputs AND counters equal one launch on device buffers"""
+    import torch
+    import coast_b200 as cb
+    M, N, K = 1024, 256, 256
+    if kernel == "gemm":
+        A = (oracle.fill_philox(M * K, 0, 4).astype(np.float64) / 2 ** 31 - 1.0).astype(np.float32)
+        B = (oracle.fill_philox(K * N, 0, 44).astype(np.float64) / 2 ** 31 - 1.0).astype(np.float32)
+        kid = cb.K_GEMM_TF32
+    else:
+        A, B, kid = oracle.fill_philox(M * K, 0, 4), oracle.fill_philox(K * N, 0, 44), cb.K_MM_U32
+    plan = cb.FaultPlan(mode=cb.PLAN_BERNOULLI, seed=5, p=0.001)
+    d_out, st_dev = rt.run(kid, 3, dev(rt, A), M * N, flags=3, M=M, N=N, K=K, aux=dev(rt, B), plan=plan, unit_base=40)
+    h_a, h_b = torch.from_numpy(A.view(np.int32).copy()).pin_memory(), torch.from_numpy(B.view(np.int32).copy()).pin_memory()
+    h_c = torch.zeros(M * N, dtype=torch.int32).pin_memory()
+    st = rt.run_host(kid, 3, h_a, h_c, M * N, flags=3, M=M, N=N, K=K, h_aux=h_b, plan=plan, unit_base=40)
+    assert rt.last_host_path == "row-blocks"
+    assert h_c.numpy().tobytes() == d_out.cpu().numpy().tobytes() and st.as_dict() == st_dev.as_dict() and st.injected > 0
 
 
 def test_reference_entry_points(rt, oracle, golden):

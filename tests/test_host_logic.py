@@ -33,6 +33,8 @@ def mock_dir(tmp_path_factory, built_lib):
 
 def run_child(mock_dir, tmp_path, ops, env_extra=None):
     log = tmp_path / "mock.log"
+    if log.exists():
+        log.unlink()                                        # one log per child run
     env = dict(os.environ, LD_LIBRARY_PATH=f"{mock_dir}:" + os.environ.get("LD_LIBRARY_PATH", ""), MOCK_CUDA_LOG=str(log))
     env.update(env_extra or {})
     res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock_cuda", "child.py"), json.dumps({"ops": ops})],
@@ -82,8 +84,10 @@ def test_launch_geometry_and_argument_block(mock_dir, tmp_path, kernel, nc, n, u
     if tile_rows:                                           # TMA-tiled kernels: one tensor map over exactly the caller's rows
         assert a.n_tiles == -(-n // tile_rows) and la["grid"] <= 148 * 8
         tm = [e for e in ev if e["op"] == "tmap"]
-        assert len(tm) == 1 and tm[0]["dim1"] == n and tm[0]["box1"] <= 256 and tile_rows % tm[0]["box1"] == 0
-        assert tm[0]["box_bytes"] * (tile_rows // tm[0]["box1"]) * 2 + 64 <= la["smem"]     # two ring stages fit
+        pack = tm[0]["dim0"] * 4 // (16 if kernel == K_AES128 else ub)      # AES: the same dense bytes as 64- or 256-byte rows
+        assert (pack == 16 and (a.mode >> 8) & 15 == 4) if kernel == K_AES128 else pack == 1
+        assert len(tm) == 1 and tm[0]["dim1"] * pack == n and tm[0]["box1"] <= 256 and tile_rows % (tm[0]["box1"] * pack) == 0
+        assert tm[0]["box_bytes"] * (tile_rows // (tm[0]["box1"] * pack)) * 2 + 64 <= la["smem"]     # two ring stages fit
     if kernel == K_QSORT:                                   # per-unit scratch from the pool, released after the launch
         big = [e for e in ev if e["op"] == "alloc" and e["bytes"] >= la["grid"] * 4 * 32 * ub]
         assert big and a.aux != 0
@@ -239,6 +243,23 @@ def test_aes_per_unit_keys_with_write_back_through_the_host_call(mock_dir, tmp_p
     assert ev[-1] == {"op": "exit", "live_allocations": 0}
 
 
+def test_large_matmul_through_the_host_call_is_pipelined_by_row_blocks(mock_dir, tmp_path):
+    """B once; A rows up / launch / C rows down per block on rotating streams; every block's launch is keyed by its global element index"""
+    M, N, K = 1024, 256, 128
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="run_host_aux", kernel=K_GEMM_TF32, nc=3, n=M * N, M=M, N=N, K=K, in_bytes=M * K * 4,
+                                                  aux_bytes=K * N * 4, out_bytes=M * N * 4, unit_base=5), dict(op="shutdown")])
+    r = res["ops"][0]
+    assert r["rc"] == 0 and not [e for e in ev if e["op"] == "error"], (r, [e for e in ev if e["op"] == "error"])
+    launches = [(e, args_of(e)) for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
+    assert len(launches) == 8 and len({e["stream"] for e, _ in launches}) == 3
+    assert [a.M for _, a in launches] == [128] * 8 and [a.unit_base for _, a in launches] == [5 + i * 128 * N for i in range(8)]
+    assert len([e for e in ev if e["op"] == "h2d" and e["host"] == r["host_aux"]]) == 1            # B goes up once
+    _contiguous([(e["host"] - r["host_in"], e["bytes"]) for e in ev if e["op"] == "h2d" and 0 <= e["host"] - r["host_in"] < M * K * 4], M * K * 4)
+    _contiguous([(e["host"] - r["host_out"], e["bytes"]) for e in ev if e["op"] == "d2h" and 0 <= e["host"] - r["host_out"] < M * N * 4], M * N * 4)
+    assert len([e for e in ev if e["op"] == "wait_event"]) == 8 and len([e for e in ev if e["op"] == "event_record"]) == 1
+    assert ev[-1] == {"op": "exit", "live_allocations": 0}
+
+
 def test_matmul_through_the_host_call_is_one_shot(mock_dir, tmp_path):
     M = N = K = 128
     res, ev = run_child(mock_dir, tmp_path, [dict(op="run_host_aux", kernel=K_MM_U32, nc=3, n=M * N, M=M, N=N, K=K, in_bytes=M * K * 4,
@@ -324,7 +345,7 @@ def test_pinned_buffers_take_the_zero_copy_host_call(mock_dir, tmp_path):
     no staging allocations; COAST_HOST_PATH=staged forces the chunked pipeline on the same buffers"""
     n = 300000
     op = dict(op="run_host_pinned", kernel=K_SHA256, nc=3, n=n, unit_bytes=64, in_bytes=64 * n, out_bytes=32 * n, unit_base=77, status=True)
-    res, ev = run_child(mock_dir, tmp_path, [op, dict(op="shutdown")])
+    res, ev = run_child(mock_dir, tmp_path, [op, dict(op="shutdown")], env_extra={"COAST_HOST_PATH": "zerocopy"})
     r = res["ops"][0]
     assert r["rc"] == 0 and not [e for e in ev if e["op"] == "error"], (r, [e for e in ev if e["op"] == "error"])
     launches = [e for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
@@ -333,17 +354,31 @@ def test_pinned_buffers_take_the_zero_copy_host_call(mock_dir, tmp_path):
     assert (a.inp, a.out, a.status, a.n_units, a.unit_base) == (r["host_in"], r["host_out"], r["host_status"], n, 77)
     assert not [e for e in ev if e["op"] == "h2d"] and all(e["bytes"] <= 64 for e in ev if e["op"] == "d2h")     # only the counters come back by copy
     assert ev[-1] == {"op": "exit", "live_allocations": 0}
-    res, ev = run_child(mock_dir, tmp_path / "..", [op, dict(op="shutdown")], env_extra={"COAST_HOST_PATH": "staged"})
+    for forced in ({"COAST_HOST_PATH": "staged"}, {}):                       # the default is the staged pipeline (r02 measurement)
+        res, ev = run_child(mock_dir, tmp_path / "..", [op, dict(op="shutdown")], env_extra=forced)
+        r = res["ops"][0]
+        assert r["rc"] == 0 and len([e for e in ev if e["op"] == "launch" and "_nc" in e["name"]]) > 1
+        _contiguous([(e["host"] - r["host_in"], e["bytes"]) for e in ev if e["op"] == "h2d"], 64 * n)
+    # hybrid: chunked launches read the pinned input in place (no upload copies), outputs and status bytes are staged per chunk
+    res, ev = run_child(mock_dir, tmp_path / "..", [op, dict(op="shutdown")], env_extra={"COAST_HOST_PATH": "hybrid"})
     r = res["ops"][0]
-    assert r["rc"] == 0 and len([e for e in ev if e["op"] == "launch" and "_nc" in e["name"]]) > 1
-    _contiguous([(e["host"] - r["host_in"], e["bytes"]) for e in ev if e["op"] == "h2d"], 64 * n)
+    launches = [args_of(e) for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
+    assert r["rc"] == 0 and len(launches) > 1 and not [e for e in ev if e["op"] == "h2d"]
+    done = 0
+    for a in launches:
+        assert a.inp == r["host_in"] + 64 * done and a.unit_base == 77 + done and a.out != r["host_out"] + 32 * done
+        done += a.n_units
+    assert done == n
+    _contiguous([(e["host"] - r["host_out"], e["bytes"]) for e in ev if e["op"] == "d2h" and 0 <= e["host"] - r["host_out"] < 32 * n], 32 * n)
 
 
 def test_zero_copy_is_refused_for_pageable_buffers_only_when_forced(mock_dir, tmp_path):
     op = dict(op="run_host", kernel=K_SHA256, nc=3, n=1000, unit_bytes=64, in_bytes=64000, out_bytes=32000)
     res, ev = run_child(mock_dir, tmp_path, [op], env_extra={"COAST_HOST_PATH": "zerocopy"})
     assert res["ops"][0]["rc"] != 0 and "pinned" in res["ops"][0]["err"]
-    res, ev = run_child(mock_dir, tmp_path / "..", [op])                       # default: falls back to the staged pipeline
+    res, ev = run_child(mock_dir, tmp_path / "..", [op], env_extra={"COAST_HOST_PATH": "hybrid"})
+    assert res["ops"][0]["rc"] != 0 and "pinned" in res["ops"][0]["err"]
+    res, ev = run_child(mock_dir, tmp_path / "..", [op])                       # default: the staged pipeline
     assert res["ops"][0]["rc"] == 0 and [e for e in ev if e["op"] == "h2d"]
 
 

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--side", type=int, default=1024)
     ap.add_argument("--stream-bytes", type=int, default=16384, help="chsha: bytes per stream (the benchmark's is 2 x 8192)")
     ap.add_argument("--flags", type=lambda x: int(x, 0), default=0, help="extra COAST_F_* bits, e.g. 0x8 = -i, 0x10 = -s")
+    ap.add_argument("--aes-mode", type=lambda x: int(x, 0), default=0, help="aes: COAST_AES_* bits (1 decrypt, 2 per-unit keys, 4 key write-back)")
     ap.add_argument("--time", action="store_true", help="print CUDA-event ms per launch (outside any profiler)")
     a = ap.parse_args()
     import torch
@@ -43,8 +44,11 @@ def main():
     elif a.kernel == "aes":
         d_in = torch.empty(n * 16, dtype=torch.uint8, device="cuda"); rt.fill_philox(d_in, 3)
         out = torch.empty(n * 16, dtype=torch.uint8, device="cuda")
-        d = rt.make_desc(cb.K_AES128, a.nc, d_in, out, n, flags=flags, key=bytes(16), plan=plan)
-        alg = n * 32
+        keys = None
+        if a.aes_mode & 2:
+            keys = torch.empty(n * 16, dtype=torch.uint8, device="cuda"); rt.fill_philox(keys, 5)
+        d = rt.make_desc(cb.K_AES128, a.nc, d_in, out, n, flags=flags, key=bytes(16), plan=plan, mode=a.aes_mode, d_aux=keys)
+        alg = n * (48 if keys is not None else 32)
     elif a.kernel == "chsha":
         ub = a.stream_bytes
         d_in = torch.empty(n * ub, dtype=torch.uint8, device="cuda"); rt.fill_philox(d_in, 6)
