@@ -11,8 +11,15 @@
  *   - everything else (gcc / nvcc host code linked against libcoast_rt.so -- the default):
  *     protection is applied at RUN TIME by the launch ABI (include/coast_rt.h), there is no
  *     IR to annotate, and gcc rejects attributes in some positions the tests use them
- *     (`int checkGolden() __NO_xMR {`, tests/matrixMultiply/matrixMultiply.c:115), so the
- *     scope directives expand to nothing.  What they MEAN for the runtime:
+ *     (`int checkGolden() __NO_xMR {`, tests/matrixMultiply/matrixMultiply.c:115), so in the COMPILED
+ *     translation unit the scope directives expand to nothing -- but they are not ignored: the BOARD=b200 pass
+ *     preprocesses every source a second time with COAST_SCOPE_SCAN (third back end below), reads the directives
+ *     with include/makefiles/coast_scope.c and decides from them which calls become protected launches:
+ *       - a function in the SoR (explicit __xMR, or default scope without __DEFAULT_NO_xMR / __NO_xMR) that has a
+ *         runtime kernel (include/makefiles/coast_entries.tab) is offloaded;
+ *       - __NO_xMR on such a function keeps its calls on the CPU, unprotected, as in the reference;
+ *       - an explicit __xMR on a function with no kernel that calls none FAILS THE BUILD, naming it.
+ *     What the directives MEAN for the runtime:
  *
  *   directive                        reference meaning (interface.cpp:364-601)          B200 runtime
  *   -------------------------------  -------------------------------------------------  ---------------------------------
@@ -30,6 +37,10 @@
 
 #if defined(COAST_LLVM_PASS)
 #  define COAST_ANNOTATE_(s) __attribute__((annotate(s)))
+#elif defined(COAST_SCOPE_SCAN)
+/* `gcc -E` only: the directive survives preprocessing as a token sequence that include/makefiles/coast_scope.c reads to
+ * decide the sphere of replication (what processAnnotations() does with llvm.global.annotations, interface.cpp:364-532) */
+#  define COAST_ANNOTATE_(s) __coast_anno__(s)
 #else
 #  define COAST_ANNOTATE_(s)
 #endif
