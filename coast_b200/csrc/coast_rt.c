@@ -115,6 +115,7 @@ static struct {
      * same few maps every call */
     struct { const void* base; uint32_t row_bytes, box_rows; uint64_t rows; int swz; CUtensorMap map; } tmaps[16];
     int n_tmaps, tmap_next;
+    unsigned warned_store_votes;     /* one warning per kernel and process */
     int host_path_default;           /* host-call path for pinned buffers: 0 = staged, 1 = hybrid, 2 = zero-copy */
     const char* last_host_path;      /* "staged" | "hybrid" | "zerocopy" | "row-blocks" | "one-shot": what the last coast_run_host did */
 } G;
@@ -262,6 +263,12 @@ static int stats_reset_impl(void* stream) {
 }
 int coast_stats_reset(void* stream) { ENTER(); LEAVE(stats_reset_impl(stream)); }
 
+/* COAST_REPORT_COUNTERS=1: print the reference's two run-time symbols when the process exits -- what a debugger would read
+ * out of a board (passes.rst "Error Logging"); the unchanged tests never print them */
+static void report_counters(void) {
+    fprintf(stderr, "coast_rt: TMR_ERROR_CNT=%u __SYNC_COUNT=%llu\n", TMR_ERROR_CNT, (unsigned long long)__SYNC_COUNT);
+}
+
 static int init_impl(int device) {
     if (G.inited) {
         if (device == G.device) return ensure_ctx();
@@ -301,6 +308,8 @@ static int init_impl(int device) {
     DRV(p_cuStreamSynchronize(NULL));
     const char* env = getenv("COAST_OPT_PASSES");
     if (env && !G.def_set) coast_set_opt_passes(env);
+    { const char* rc_env = getenv("COAST_REPORT_COUNTERS"); static int registered;
+      if (rc_env && strcmp(rc_env, "0") && !registered) { registered = 1; atexit(report_counters); } }
     return COAST_OK;
 }
 int coast_init(int device) { ENTER(); LEAVE(init_impl(device)); }
@@ -343,6 +352,10 @@ int coast_parse_opt_passes(const char* s, uint32_t* num_clones, uint32_t* flags)
         else if (!strcmp(tok, "-countErrors")) fl |= COAST_F_COUNT_ERRORS;
         else if (!strcmp(tok, "-countSyncs")) fl |= COAST_F_COUNT_SYNCS;
         else if (!strcmp(tok, "-noMemReplication")) fl |= COAST_F_NO_MEM_REPLICATION;
+        else if (!strcmp(tok, "-storeDataSync")) fl |= COAST_F_STORE_DATA_SYNC;
+        else if (!strcmp(tok, "-noStoreDataSync")) fl |= COAST_F_NO_STORE_DATA_SYNC;
+        else if (!strcmp(tok, "-noLoadSync")) fl |= COAST_F_NO_LOAD_SYNC;
+        else if (!strcmp(tok, "-noStoreAddrSync")) fl |= COAST_F_NO_STORE_ADDR_SYNC;
         else if (!strcmp(tok, "-i")) fl |= COAST_F_INTERLEAVE;
         else if (!strcmp(tok, "-s")) fl |= COAST_F_SEGMENT;
         else if (!strcmp(tok, "-verbose")) fl |= COAST_F_VERBOSE;
@@ -351,8 +364,6 @@ int coast_parse_opt_passes(const char* s, uint32_t* num_clones, uint32_t* flags)
             fprintf(stderr, "coast_rt: -reportErrors is deprecated in the reference (counts AGREEING syncs, "
                             "synchronization.cpp:1323-1350) and is not emulated; use -countErrors\n");
         }
-        /* since v1.2 these are the default / no-ops on this path (passes.rst:337, synchronization.cpp:211-215) */
-        else if (!strcmp(tok, "-noLoadSync") || !strcmp(tok, "-noStoreDataSync") || !strcmp(tok, "-noStoreAddrSync")) { }
         else fprintf(stderr, "coast_rt: OPT_PASSES token '%s' has no effect on the B200 runtime (ignored)\n", tok);
     }
     if (tmr && dwc) return fail(COAST_ERR_BAD_ARG, "-TMR and -DWC are mutually exclusive");
@@ -360,6 +371,21 @@ int coast_parse_opt_passes(const char* s, uint32_t* num_clones, uint32_t* flags)
     if (num_clones) *num_clones = nc;
     if (flags) *flags = fl;
     return COAST_OK;
+}
+
+static int store_votes_wanted(uint32_t fl) {
+    return (fl & (COAST_F_STORE_DATA_SYNC | COAST_F_NO_MEM_REPLICATION)) && !(fl & COAST_F_NO_STORE_DATA_SYNC);
+}
+static int store_votes_built(uint32_t kernel) { return kernel == COAST_K_CRC16 || kernel == COAST_K_MM_U32; }
+
+uint32_t coast_flags_honoured(uint32_t kernel, uint32_t nc, uint32_t fl) {
+    uint32_t h = fl & (COAST_F_COUNT_ERRORS | COAST_F_COUNT_SYNCS | COAST_F_VERBOSE | COAST_F_MAJORITY_VOTER);
+    if (kernel == COAST_K_SHA256 && nc == 3) h |= fl & (COAST_F_INTERLEAVE | COAST_F_SEGMENT);
+    if (store_votes_built(kernel))
+        h |= fl & (COAST_F_NO_MEM_REPLICATION | COAST_F_STORE_DATA_SYNC | COAST_F_NO_STORE_DATA_SYNC);
+    else if (!store_votes_wanted(fl))
+        h |= fl & (COAST_F_NO_STORE_DATA_SYNC);              /* asking for less than what is not there is honoured trivially */
+    return h;
 }
 
 int coast_set_opt_passes(const char* s) {
@@ -565,6 +591,22 @@ static int launch_impl(const coast_launch_desc* d, void* stream) {
         if (a.plan_mode > COAST_PLAN_TABLE) return fail(COAST_ERR_BAD_ARG, "unknown fault plan mode %u", a.plan_mode);
     }
     a.n_sites = coast_fault_sites(d->kernel, d->unit_bytes, d->K);
+    /* in-loop store votes (-storeDataSync / -noMemReplication): built for CRC16 and MM_U32, loud everywhere else */
+    const int store_votes = store_votes_wanted(d->flags) && nc > 1;
+    if (store_votes && !store_votes_built(d->kernel)) {
+        static const char* const kname[COAST_K_COUNT_] = { "crc16", "sha256", "aes128", "mm_u32", "gemm_tf32", "qsort", "chstone_sha" };
+        const char* strict = getenv("COAST_STRICT_FLAGS");
+        if (strict && strcmp(strict, "0"))
+            return fail(COAST_ERR_UNSUPPORTED, "-noMemReplication / -storeDataSync: the %s kernel has no in-loop store votes "
+                                               "(COAST_STRICT_FLAGS is set)", kname[d->kernel]);
+        if (!(G.warned_store_votes & (1u << d->kernel))) {
+            G.warned_store_votes |= 1u << d->kernel;
+            fprintf(stderr, "coast_rt: WARNING: -noMemReplication / -storeDataSync are NOT honoured by the %s kernel: it has no in-loop "
+                            "store votes and runs the default sync set (SoR-exit votes only).  COAST_STRICT_FLAGS=1 makes this an error.\n",
+                    kname[d->kernel]);
+        }
+    }
+    if (store_votes && store_votes_built(d->kernel)) a.flags |= XMR_F_STORE_VOTES;
 
     char name[64];
     unsigned smem = 0; int tma = 0; int block = XMR_CTA_THREADS; int mm_tiled = 0; int qs_scratch = 0;
@@ -589,7 +631,7 @@ static int launch_impl(const coast_launch_desc* d, void* stream) {
         break;
     case COAST_K_CRC16:
         if (d->unit_bytes < 1 || d->unit_bytes > 255) return fail(COAST_ERR_BAD_ARG, "crc16 length is an unsigned char (1..255)");
-        if (d->unit_bytes == 64 && aligned16 && d->n_units < 0x7FFFFF00ull) {
+        if (d->unit_bytes == 64 && aligned16 && d->n_units < 0x7FFFFF00ull && !store_votes) {
             /* table kernel: 1024-thread CTAs (768 unprotected), shared window = [.., 0x10000) unused | 64 KiB byte-step
              * table | tile ring at 0x20000 (CrcGeom in xmr_crc16.cuh) */
             tma = 1; block = nc == 1 ? 768 : 1024; tile_rows = (unsigned)(block / 32) * upw; row_bytes = 64;
@@ -622,6 +664,7 @@ static int launch_impl(const coast_launch_desc* d, void* stream) {
         {   /* tensor-core path (exact, u8 limbs on kind::i8) for tile-aligned problems; COAST_MM_PATH=tiled|naive overrides */
             const char* path = getenv("COAST_MM_PATH");
             const int want_tc = !path || !strcmp(path, "tc") || !strcmp(path, "tct");
+            if (store_votes) break;                              /* per-k votes on `sum`: the plain kernel (one lane per replica per element) */
             if (want_tc && d->M % 128u == 0 && d->N % 64u == 0 && d->K % 128u == 0 && aligned16 &&
                 !(((uintptr_t)d->d_aux) & 15u) && !(((uintptr_t)d->d_out) & 15u))
                 /* measured at 4096^3: A staged in TMEM wins for TMR (1.54 vs 2.45 ms); smem operands win for 1-2 replicas */
@@ -629,7 +672,7 @@ static int launch_impl(const coast_launch_desc* d, void* stream) {
             if (path && !strcmp(path, "naive")) break;
         }
         /* register-tiled fast path: 64 x 128 x 16 tiles, NC x 128 threads (replicas on adjacent warps) */
-        if (d->M % 64u == 0 && d->N % 128u == 0 && d->K % 16u == 0 && aligned16 && !(((uintptr_t)d->d_aux) & 15u) &&
+        if (!store_votes && d->M % 64u == 0 && d->N % 128u == 0 && d->K % 16u == 0 && aligned16 && !(((uintptr_t)d->d_aux) & 15u) &&
             !(((uintptr_t)d->d_out) & 15u)) {
             mm_tiled = 1; block = (int)nc * 128; smem = 64u * 1024u;
             snprintf(name, sizeof name, "xmr_mm_u32_tiled_nc%u_inj%d", nc, inj);

@@ -24,6 +24,11 @@ typedef struct xmr_args {
     unsigned char key[16];
 } xmr_args;
 
+/* internal flag (set by the host in xmr_args.flags, never by callers): in-loop store votes are in effect (coast_rt.h) */
+#define XMR_F_STORE_VOTES 0x8000u
+/* AES: bits 8..11 of xmr_args.mode = log2 of the blocks per tensor-map row (the host describes the dense 16-byte blocks as
+ * 64- or 256-byte rows when the count allows) */
+
 /* counter slots (mirror coast_stats) */
 #define XMR_CTR_ERRORS   0
 #define XMR_CTR_DWC      1

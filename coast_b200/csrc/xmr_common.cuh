@@ -120,6 +120,22 @@ __device__ __forceinline__ Voted vote_f32(float x, bool majority) {
     return v;
 }
 
+// In-loop store vote (-storeDataSync / -noMemReplication, synchronization.cpp:476-560): every lane of the unit reads all
+// NC copies, so -- unlike vote_u32 -- ALL replica lanes hold the result and, under TMR, continue with the voted value
+// (:519-529 hands `sel` to the three stores).  DWC keeps its own value (the reference would have aborted).  Returns 1 if
+// the copies disagree.  Must be called by all 32 lanes; `x` is a value of at most 32 bits.
+template <int NC>
+__device__ __forceinline__ uint32_t store_vote(uint32_t& x, int lane, bool majority) {
+    if (NC == 1) return 0u;
+    const int base = Lanes<NC>::unit(lane) * NC;
+    const uint32_t r0 = __shfl_sync(0xFFFFFFFFu, x, base), r1 = __shfl_sync(0xFFFFFFFFu, x, base + 1);
+    if (NC == 2) return r0 != r1 ? 1u : 0u;
+    const uint32_t r2 = __shfl_sync(0xFFFFFFFFu, x, base + 2);
+    const bool c01 = r0 == r1, c02 = r0 == r2;
+    x = majority ? ((r0 & r1) | (r0 & r2) | (r1 & r2)) : (c01 ? r0 : r2);
+    return (c01 && c02) ? 0u : 1u;
+}
+
 // ---------------------------------------------------------------- per-thread tallies -> counters
 struct Tally {
     uint32_t errors = 0, dwc = 0, syncs = 0, injected = 0;

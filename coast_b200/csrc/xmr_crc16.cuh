@@ -190,13 +190,36 @@ __device__ __forceinline__ void crc16_gen_body(const xmr_args& a) {
             }
         }
         uint32_t crc = 0xFFFFu;
-        for (uint32_t i = 0; i < len; ++i) {
-            uint32_t b = __ldg(msg + i);
-            if (INJECT && fsite == len + i) b ^= fmask;
-            crc = crc16_step(crc, b);
-            if (INJECT && fsite == i) crc ^= fmask;
+        if (!(a.flags & XMR_F_STORE_VOTES)) {
+            for (uint32_t i = 0; i < len; ++i) {
+                uint32_t b = __ldg(msg + i);
+                if (INJECT && fsite == len + i) b ^= fmask;
+                crc = crc16_step(crc, b);
+                if (INJECT && fsite == i) crc ^= fmask;
+            }
+            crc_vote_store<NC>(crc, static_cast<uint16_t*>(a.out), local, a.unit_base + local, valid, lane, a.flags, tally);
+        } else {
+            // -storeDataSync / -noMemReplication: the three assignments of the loop body are voted (crc16.c:26-28), the
+            // replicas continue with the voted value; 3 votes per byte + the SoR exit
+            const bool majority = a.flags & COAST_F_MAJORITY_D;
+            uint32_t bad = 0;
+            for (uint32_t i = 0; i < len; ++i) {
+                uint32_t b = __ldg(msg + i);
+                if (INJECT && fsite == len + i) b ^= fmask;
+                uint32_t x = ((crc >> 8) ^ b) & 0xFFu;                              // :26
+                bad += store_vote<NC>(x, lane, majority);
+                x = (x ^ (x >> 4)) & 0xFFu;                                         // :27
+                bad += store_vote<NC>(x, lane, majority);
+                crc = ((crc << 8) ^ (x << 12) ^ (x << 5) ^ x) & 0xFFFFu;            // :28
+                bad += store_vote<NC>(crc, lane, majority);
+                if (INJECT && fsite == i) crc ^= fmask;
+            }
+            bad += store_vote<NC>(crc, lane, majority);                             // :30
+            if (valid && Lanes<NC>::voter(lane)) {
+                static_cast<uint16_t*>(a.out)[local] = (uint16_t)crc;
+                tally.unit_exit<NC>(bad, 3u * len + 1u, a.flags, a.unit_base + local);
+            }
         }
-        crc_vote_store<NC>(crc, static_cast<uint16_t*>(a.out), local, a.unit_base + local, valid, lane, a.flags, tally);
     }
     tally.flush(a.counters);
 }

@@ -43,14 +43,31 @@ __device__ __forceinline__ void mm_u32_body(const xmr_args& a) {
         const uint32_t* ap = A + (size_t)i * K;
         const uint32_t* bp = B + j;
         uint32_t sum = 0;
-        for (uint32_t k = 0; k < K; ++k) {                      // :12-14
-            sum += __ldg(ap + k) * __ldg(bp + (size_t)k * N);
-            if (INJECT && fsite == k) sum ^= fmask;
-        }
-        Voted v = vote_u32<NC, 4>(sum, a.flags & COAST_F_MAJORITY_D);
-        if (valid && Lanes<NC>::voter(lane)) {
-            C[local] = v.vote;                                  // :16
-            tally.unit_exit<NC>(v.bad, 1u, a.flags, a.unit_base + local);
+        if (!(a.flags & XMR_F_STORE_VOTES)) {
+            for (uint32_t k = 0; k < K; ++k) {                  // :12-14
+                sum += __ldg(ap + k) * __ldg(bp + (size_t)k * N);
+                if (INJECT && fsite == k) sum ^= fmask;
+            }
+            Voted v = vote_u32<NC, 4>(sum, a.flags & COAST_F_MAJORITY_D);
+            if (valid && Lanes<NC>::voter(lane)) {
+                C[local] = v.vote;                              // :16
+                tally.unit_exit<NC>(v.bad, 1u, a.flags, a.unit_base + local);
+            }
+        } else {
+            // -storeDataSync / -noMemReplication: `sum += ...` (:13) is voted at every k, the replicas continue with the voted
+            // value; K votes + the SoR-exit store (:16)
+            const bool majority = a.flags & COAST_F_MAJORITY_D;
+            uint32_t bad = 0;
+            for (uint32_t k = 0; k < K; ++k) {
+                sum += __ldg(ap + k) * __ldg(bp + (size_t)k * N);
+                bad += store_vote<NC>(sum, lane, majority);
+                if (INJECT && fsite == k) sum ^= fmask;
+            }
+            bad += store_vote<NC>(sum, lane, majority);
+            if (valid && Lanes<NC>::voter(lane)) {
+                C[local] = sum;
+                tally.unit_exit<NC>(bad, K + 1u, a.flags, a.unit_base + local);
+            }
         }
     }
     tally.flush(a.counters);

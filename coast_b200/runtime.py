@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 K_CRC16, K_SHA256, K_AES128, K_MM_U32, K_GEMM_TF32, K_QSORT, K_CHSTONE_SHA = range(7)
 F_COUNT_ERRORS, F_COUNT_SYNCS, F_NO_MEM_REPLICATION = 0x1, 0x2, 0x4
 F_INTERLEAVE, F_SEGMENT, F_VERBOSE, F_MAJORITY_VOTER = 0x8, 0x10, 0x20, 0x100
+F_STORE_DATA_SYNC, F_NO_STORE_DATA_SYNC, F_NO_LOAD_SYNC, F_NO_STORE_ADDR_SYNC = 0x200, 0x400, 0x800, 0x1000
 PLAN_NONE, PLAN_BERNOULLI, PLAN_TABLE = 0, 1, 2
 AES_DECRYPT, AES_KEY_PER_UNIT, AES_KEY_WRITEBACK = 1, 2, 4
 NO_FAULT_UNIT = 0xFFFFFFFFFFFFFFFF
@@ -95,7 +96,7 @@ def lib_path() -> str:
 _LIB = None
 
 EXPORTS = [
-    "coast_init", "coast_numa_node", "coast_shutdown", "coast_last_error", "coast_version", "coast_parse_opt_passes", "coast_launch",
+    "coast_init", "coast_numa_node", "coast_shutdown", "coast_last_error", "coast_version", "coast_parse_opt_passes", "coast_flags_honoured", "coast_launch",
     "coast_sync", "coast_sync_noabort", "coast_stats_snapshot", "coast_stats_reset", "coast_fault_sites",
     "coast_fault_site_bits", "coast_out_bytes_per_unit", "coast_out_bytes", "coast_votes_per_unit", "coast_malloc", "coast_free",
     "coast_memcpy_h2d", "coast_memcpy_d2h", "coast_memset", "coast_host_alloc", "coast_host_free",
@@ -121,6 +122,8 @@ def load_library():
         L.coast_init.argtypes = [C.c_int]
         L.coast_parse_opt_passes.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.coast_set_opt_passes.argtypes = [C.c_char_p]
+        L.coast_flags_honoured.argtypes = [C.c_uint32] * 3
+        L.coast_flags_honoured.restype = C.c_uint32
         L.coast_launch.argtypes = [C.POINTER(LaunchDesc), C.c_void_p]
         L.coast_run_host.argtypes = [C.POINTER(LaunchDesc), C.POINTER(_Stats)]
         L.coast_run_host_noabort.argtypes = [C.POINTER(LaunchDesc), C.POINTER(_Stats)]

@@ -81,8 +81,8 @@ typedef enum coast_kernel_id {
  * on this path.  coast_parse_opt_passes() maps the token string onto these. */
 #define COAST_F_COUNT_ERRORS        0x0001u /* -countErrors  synchronization.cpp:1354-1465 */
 #define COAST_F_COUNT_SYNCS         0x0002u /* -countSyncs   synchronization.cpp:1415-1425 */
-#define COAST_F_NO_MEM_REPLICATION  0x0004u /* -noMemReplication: accepted; inputs are always
-                                               ONE staged copy read by every replica (passes.rst:331) */
+#define COAST_F_NO_MEM_REPLICATION  0x0004u /* -noMemReplication (rule D2, passes.rst "Replication Rules"): variables live ONCE, stores
+                                               are voted (synchronization.cpp:205-215) -> in-loop store votes, see below */
 #define COAST_F_INTERLEAVE          0x0008u /* -i : replicas on adjacent LANES of one warp        */
 #define COAST_F_SEGMENT             0x0010u /* -s : replicas on adjacent WARPS of one CTA (reference default,
                                                interface.cpp:245-247); layout hint only, results identical */
@@ -91,6 +91,17 @@ typedef enum coast_kernel_id {
                                                synchronization.cpp:1323-1350).  Parsed, warned, NOT emulated. */
 #define COAST_F_MAJORITY_VOTER      0x0100u /* extension: bitwise 2-of-3 majority instead of the reference's
                                                select voter.  Off by default (reference semantics). */
+#define COAST_F_STORE_DATA_SYNC     0x0200u /* -storeDataSync: vote the data of every store (rule C4), synchronization.cpp:211-215 */
+#define COAST_F_NO_STORE_DATA_SYNC  0x0400u /* -noStoreDataSync: no store-data votes (:333-335); the SoR-exit votes stay (:304-322) */
+#define COAST_F_NO_LOAD_SYNC        0x0800u /* -noLoadSync: with -noMemReplication, no votes on load address offsets (C3, :347-360) */
+#define COAST_F_NO_STORE_ADDR_SYNC  0x1000u /* -noStoreAddrSync: ... nor on store address offsets (C5, :362-375) */
+/* IN-LOOP STORE VOTES = (-storeDataSync or -noMemReplication) and not -noStoreDataSync: every assignment to a data variable
+ * of the protected function is voted and, under TMR, all replicas continue with the voted value; __SYNC_COUNT grows
+ * accordingly (crc16: 3 per byte + 1; matrix_multiply: K + 1 per element).  Built for CRC16 and MM_U32 (which then run
+ * their general kernels).  The other kernels cannot honour it: they WARN on stderr and run the default sync set, or
+ * fail with COAST_ERR_UNSUPPORTED when COAST_STRICT_FLAGS=1.  coast_flags_honoured() tells which.
+ * Address-offset votes need a data-dependent subscript; crc16 and matrix_multiply have none, so -noLoadSync /
+ * -noStoreAddrSync change nothing there. */
 
 /* ------------------------------------------------------------------ */
 /* Fault plan: the on-device replacement of simulation/platform         */
@@ -208,6 +219,9 @@ const char* coast_version(void);
  * Unknown tokens are warned about on stderr and ignored, as `opt` would for passes
  * that are not loaded.  Returns 0, or COAST_ERR_BAD_ARG if both -TMR and -DWC. */
 int  coast_parse_opt_passes(const char* opt_passes, uint32_t* num_clones, uint32_t* flags);
+/* The subset of `flags` that changes what `kernel` executes (sync set, counters, replica layout); the rest is accepted
+ * with a warning (or refused under COAST_STRICT_FLAGS=1). */
+uint32_t coast_flags_honoured(uint32_t kernel, uint32_t num_clones, uint32_t flags);
 
 /* --- the launch (replaces dataflowProtection::run + the emitted code) */
 int  coast_launch(const coast_launch_desc* desc, void* stream);

@@ -529,6 +529,87 @@ static void run_replica(const orc_desc* d, uint64_t local, const orc_fault* f, u
     }
 }
 
+/* ------------------------------------------------------------------ */
+/* 8f-1: -storeDataSync / -noMemReplication -- votes INSIDE the loops     */
+/* Rule C4 ("the data used in stores is synchronized", passes.rst repl_details; populateSyncPoints                    */
+/* synchronization.cpp:197-221: a store of a non-pointer, computed value is a sync point when -storeDataSync is given  */
+/* or memory is not replicated; syncStoreInst :476-560 votes the stored value and, under TMR, hands the VOTED value to */
+/* all three copies :519-529).  With -noMemReplication (rule D2: variables live once, in ECC-protected memory; loads   */
+/* are still executed per replica from that one address, passes.rst) the replicas re-converge at every assignment.     */
+/* Granularity here = the C assignments to the DATA variables of the function (x, crc / sum); pointer stores are never */
+/* voted (:199-204) and the loop counters are control state the kernels keep uniform.            */
+/* Address-offset votes (C3/C5, syncGEP :417-470; -noLoadSync / -noStoreAddrSync prune them) need a data-dependent     */
+/* index: crc16 has no subscripts and matrix_multiply indexes with loop counters only, so the set is empty for both.   */
+/* A flip at a fault site lands on the replica's copy AFTER the assignment's vote (its reloaded register), so it is    */
+/* caught by the next vote on a value computed from it.  Unpinned like every mid-computation site (header).           */
+/* ------------------------------------------------------------------ */
+int orc_store_votes(uint32_t flags) {
+    return (flags & (ORC_F_STORE_DATA_SYNC | ORC_F_NO_MEM_REPLICATION)) && !(flags & ORC_F_NO_STORE_DATA_SYNC);
+}
+int orc_store_votes_supported(uint32_t kernel) { return kernel == ORC_K_CRC16 || kernel == ORC_K_MM_U32; }
+
+typedef struct { uint32_t nc, flags; uint64_t errors, syncs; int disagree; } sv_ctx;
+/* one store vote on v[0..nc) (width <= 32 bits); TMR: every copy continues with the voted value */
+static void sv_vote(sv_ctx* c, uint32_t v[3]) {
+    if (c->nc == 1) return;
+    if (c->nc == 2) { if (v[0] != v[1]) c->disagree = 1; return; }
+    const int c01 = v[0] == v[1], c02 = v[0] == v[2];
+    const uint32_t voted = (c->flags & ORC_F_MAJORITY) ? ((v[0] & v[1]) | (v[0] & v[2]) | (v[1] & v[2])) : (c01 ? v[0] : v[2]);
+    if (!(c01 && c02)) { c->disagree = 1; if (c->flags & ORC_F_COUNT_ERRORS) c->errors++; }
+    if ((c->flags & ORC_F_COUNT_SYNCS) && (c->flags & ORC_F_COUNT_ERRORS)) c->syncs++;
+    v[0] = v[1] = v[2] = voted;
+}
+static uint16_t sv_crc16_unit(const uint8_t* data, uint32_t len, const orc_fault* f, sv_ctx* c) {
+    uint32_t crc[3] = { 0xFFFFu, 0xFFFFu, 0xFFFFu }, x[3] = { 0, 0, 0 };
+    for (uint32_t n = 0; n < len; ++n) {
+        for (uint32_t r = 0; r < c->nc; ++r) {
+            uint8_t b = data[n];                                                    /* per-replica load of the one copy */
+            if (f->active && f->replica == r && f->site == len + n) b ^= (uint8_t)(1u << f->bit);
+            x[r] = (uint8_t)((crc[r] >> 8) ^ b);                                    /* crc16.c:26 */
+        }
+        sv_vote(c, x);
+        for (uint32_t r = 0; r < c->nc; ++r) x[r] = (uint8_t)(x[r] ^ (x[r] >> 4));  /* :27 */
+        sv_vote(c, x);
+        for (uint32_t r = 0; r < c->nc; ++r)
+            crc[r] = (uint16_t)((uint16_t)(crc[r] << 8) ^ (uint16_t)(x[r] << 12) ^ (uint16_t)(x[r] << 5) ^ (uint16_t)x[r]);   /* :28 */
+        sv_vote(c, crc);
+        for (uint32_t r = 0; r < c->nc; ++r)
+            if (f->active && f->replica == r && f->site == n) crc[r] ^= (1u << f->bit);
+    }
+    sv_vote(c, crc);                                                                /* :30 the SoR exit */
+    return (uint16_t)crc[0];
+}
+static uint32_t sv_mm_elem(const uint32_t* A, const uint32_t* B, uint32_t K, uint32_t N, uint32_t i, uint32_t j, const orc_fault* f, sv_ctx* c) {
+    uint32_t sum[3] = { 0, 0, 0 };
+    for (uint32_t k = 0; k < K; ++k) {
+        for (uint32_t r = 0; r < c->nc; ++r) sum[r] += A[(size_t)i * K + k] * B[(size_t)k * N + j];   /* mm_common_tmr.c:13 */
+        sv_vote(c, sum);
+        for (uint32_t r = 0; r < c->nc; ++r)
+            if (f->active && f->replica == r && f->site == k) sum[r] ^= (1u << f->bit);
+    }
+    sv_vote(c, sum);                                                                /* :16 r[i][j] = sum */
+    return sum[0];
+}
+static void sv_run_range(const orc_desc* d, uint64_t u0, uint64_t u1, orc_stats* st) {
+    const uint32_t nc = d->num_clones;
+    for (uint64_t local = u0; local < u1; ++local) {
+        orc_fault f;
+        orc_fault_for_unit(d->plan, d->kernel, nc, d->unit_bytes, d->K, d->unit_base + local, local, &f);
+        if (f.active) st->injected++;
+        sv_ctx c = { nc, d->flags, 0, 0, 0 };
+        if (d->kernel == ORC_K_CRC16) {
+            uint16_t v = sv_crc16_unit((const uint8_t*)d->in + local * d->unit_bytes, d->unit_bytes, &f, &c);
+            memcpy((uint8_t*)d->out + local * 2, &v, 2);
+        } else {
+            uint32_t v = sv_mm_elem((const uint32_t*)d->in, (const uint32_t*)d->aux, d->K, d->N, (uint32_t)(local / d->N), (uint32_t)(local % d->N), &f, &c);
+            memcpy((uint8_t*)d->out + local * 4, &v, 4);
+        }
+        st->errors_corrected += c.errors; st->syncs += c.syncs;
+        if (nc == 2 && c.disagree) st->dwc_detected++;
+        if (c.disagree && d->unit_base + local < st->first_fault_unit) st->first_fault_unit = d->unit_base + local;
+    }
+}
+
 int orc_run_range(const orc_desc* d, uint64_t u0, uint64_t u1, orc_stats* st) {
     if (!d || d->num_clones < 1 || d->num_clones > 3 || d->kernel > ORC_K_CHSTONE_SHA) return -1;
     if (d->kernel == ORC_K_CHSTONE_SHA && (d->unit_bytes < 64u || (d->unit_bytes & 63u) || d->unit_bytes >= (1u << 29))) return -1;
@@ -564,6 +645,7 @@ int orc_run_range(const orc_desc* d, uint64_t u0, uint64_t u1, orc_stats* st) {
         }
         return 0;
     }
+    if (orc_store_votes(d->flags) && orc_store_votes_supported(d->kernel)) { sv_run_range(d, u0, u1, st); return 0; }
     const uint32_t ob = orc_out_bytes_per_unit(d->kernel);
     const uint32_t nv = orc_votes_per_unit(d->kernel);
     const uint32_t es = ob / nv;

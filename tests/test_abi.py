@@ -68,7 +68,8 @@ def test_every_kernel_the_host_code_can_name_is_in_the_cubin(built_lib):
     ("-DWC #-DebugStatements", 2, 0),                      # tests/matrixMultiply/Makefile:3
     ("", 1, 0),                                            # tests/aes/Makefile:3
     ("-TMR -countErrors -countSyncs -noMemReplication -i", 3, 0x1 | 0x2 | 0x4 | 0x8),
-    ("-DWC -noLoadSync -noStoreDataSync -noStoreAddrSync -s", 2, 0x10),   # unittest/cfg/full.yml sweep
+    ("-DWC -noLoadSync -noStoreDataSync -noStoreAddrSync -s", 2, 0x10 | 0x400 | 0x800 | 0x1000),   # unittest/cfg/full.yml sweep
+    ("-TMR -noMemReplication -storeDataSync -countErrors -countSyncs", 3, 0x4 | 0x200 | 0x3),
     ("-TMR -CFCSS -someUnknownPass", 3, 0),                # unknown tokens: warn and ignore
 ])
 def test_parse_opt_passes(built_lib, s, nc, fl):

@@ -98,18 +98,52 @@ def test_every_sweep_entry_parses_without_an_ignored_token(built_lib):
         assert lib.coast_parse_opt_passes(passes.encode(), C.byref(nc), C.byref(fl)) == 0
 
 
+def _store_votes(passes):
+    return ("-noMemReplication" in passes or "-storeDataSync" in passes) and "-noStoreDataSync" not in passes
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("target,regex", [("matrixMultiply", r"Number of errors: 0"), ("crc16", r"result: 5ba3"),
                                           ("aes", r"Number of errors: 0")])
 def test_unittest_full_yml_sweep_on_the_gpu(target, regex):
-    """unittest.py:61-86 over cfg/full.yml: every benchmark x every OPT_PASSES must exit 0 and match its regex"""
+    """unittest.py:61-86 over cfg/full.yml: every benchmark x every OPT_PASSES must exit 0 and match its regex -- and the
+    variants must DIFFER where the reference's do: -noMemReplication turns every assignment into a sync point
+    (synchronization.cpp:205-215), which shows in __SYNC_COUNT (crc16: 3 per byte + 1 for the 13-byte message = 40 instead of 1;
+    matrixMultiply 9x9: 81 x (9 + 1) per matrix_multiply call instead of 81) and in the kernel the runtime picks; a kernel that
+    cannot honour the flag (aes) says so on stderr instead of silently running the default."""
     exe = os.path.join(OUT, target, target + ".out")
     if not os.path.exists(exe):
         pytest.skip("binary was not built on the CPU box (needs the reference checkout)")
+    seen = {}
     for passes in FULL_YML_SWEEP:
-        env = dict(os.environ, COAST_OPT_PASSES_OVERRIDE=passes + " -verbose")
+        count = " -countErrors -countSyncs" if "-TMR" in passes else ""
+        env = dict(os.environ, COAST_OPT_PASSES_OVERRIDE=passes + count + " -verbose", COAST_REPORT_COUNTERS="1")
         res = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env)
         assert res.returncode == 0, (passes, res.stdout + res.stderr)
         assert re.search(regex, res.stdout), (passes, res.stdout + res.stderr)
         want = "_nc3_" if "-TMR" in passes else "_nc2_" if "-DWC" in passes else "_nc1_"
         assert want in res.stderr, (passes, res.stderr)      # -verbose names the kernel actually launched
+        m = re.search(r"TMR_ERROR_CNT=(\d+) __SYNC_COUNT=(\d+)", res.stderr)
+        assert m and int(m.group(1)) == 0, (passes, res.stderr)
+        seen[passes] = int(m.group(2))
+        warned = "NOT honoured" in res.stderr
+        assert warned == (target == "aes" and _store_votes(passes)), (passes, res.stderr)
+    if target == "crc16":
+        assert seen["-TMR -countErrors"] == seen["-TMR"] == 1 and seen["-TMR -noMemReplication"] == 3 * 13 + 1
+        assert seen["-TMR -noMemReplication -noStoreDataSync"] == 1 and seen["-TMR -noMemReplication -noLoadSync"] == 40
+        assert seen["-DWC -noMemReplication"] == 0            # __SYNC_COUNT only exists under TMR -countErrors (:1415-1425)
+    if target == "matrixMultiply":
+        calls = seen["-TMR"] // 81                            # generateGolden + test: matrix_multiply is called twice (matrixMultiply.c:131-139)
+        assert calls >= 1 and seen["-TMR"] == 81 * calls and seen["-TMR -noMemReplication"] == 81 * (9 + 1) * calls
+    if target == "aes":
+        assert len(set(seen[p] for p in FULL_YML_SWEEP if "-TMR" in p)) == 1     # and says so: see `warned`
+
+
+@pytest.mark.gpu
+def test_strict_flags_turn_an_unhonoured_flag_into_an_error():
+    exe = os.path.join(OUT, "aes", "aes.out")
+    if not os.path.exists(exe):
+        pytest.skip("binary was not built on the CPU box (needs the reference checkout)")
+    env = dict(os.environ, COAST_OPT_PASSES_OVERRIDE="-TMR -noMemReplication", COAST_STRICT_FLAGS="1")
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env)
+    assert res.returncode != 0 and "has no in-loop store votes" in res.stderr

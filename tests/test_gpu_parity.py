@@ -426,6 +426,32 @@ def test_matmul_host_call_row_blocks_equal_the_device_launch(rt, oracle, kernel)
     assert h_c.numpy().tobytes() == d_out.cpu().numpy().tobytes() and st.as_dict() == st_dev.as_dict() and st.injected > 0
 
 
+@pytest.mark.parametrize("nc", [2, 3])
+@pytest.mark.parametrize("flagname", ["F_STORE_DATA_SYNC", "F_NO_MEM_REPLICATION"])
+def test_store_votes_crc16_and_mm_match_the_oracle(rt, oracle, nc, flagname):
+    """8f-1: -storeDataSync / -noMemReplication = votes on every assignment inside the loops (oracle: sv_crc16_unit / sv_mm_elem);
+    outputs, corrected-error count, __SYNC_COUNT and the per-unit status all equal the oracle, zero-fault and under faults at
+    every site class; lengths include 64 (the table kernel must NOT be picked) and the 13-byte reference message"""
+    import coast_b200 as cb
+    extra = getattr(cb, flagname)
+    for L, n in ((13, 777), (64, 5000), (255, 100)):
+        m = msgs(oracle, n, L, 1)
+        g, st = both(rt, oracle, oracle.K_CRC16, nc, m, n, unit_bytes=L, flags=3 | extra)
+        assert st["syncs"] == (n * (3 * L + 1) if nc == 3 else 0)
+        g, st = both(rt, oracle, oracle.K_CRC16, nc, m, n, unit_bytes=L, flags=3 | extra, plan_kw=dict(seed=4, p=0.3))
+        assert st["injected"] > 0 and (st["errors_corrected"] == st["injected"] if nc == 3 else st["dwc_detected"] > 0)
+    sites = np.arange(26, dtype=np.uint32)
+    table = np.array([oracle.fault_entry(int(s) % nc, int(s), int(s) % 8) for s in sites], dtype=np.uint32)
+    both(rt, oracle, oracle.K_CRC16, nc, msgs(oracle, 26, 13, 1), 26, unit_bytes=13, flags=3 | extra, table=table)
+    for (M, N, K) in ((9, 9, 9), (64, 128, 32), (128, 64, 128)):          # the tiled / tensor-core shapes must fall back to the plain kernel
+        A, B = oracle.fill_philox(M * K, 0, 4), oracle.fill_philox(K * N, 0, 44)
+        g, st = both(rt, oracle, oracle.K_MM_U32, nc, A, M * N, flags=3 | extra, M=M, N=N, K=K, aux=B, plan_kw=dict(seed=6, p=0.2))
+        assert st["syncs"] == (M * N * (K + 1) if nc == 3 else 0)
+    # -noStoreDataSync switches the in-loop votes off again
+    g, st = both(rt, oracle, oracle.K_CRC16, 3, msgs(oracle, 100, 13, 1), 100, unit_bytes=13, flags=3 | extra | cb.F_NO_STORE_DATA_SYNC)
+    assert st["syncs"] == 100
+
+
 def test_reference_entry_points(rt, oracle, golden):
     """the four functions the unchanged reference tests call (BOARD=b200 flow), under -TMR -countErrors"""
     import ctypes as C

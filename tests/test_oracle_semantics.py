@@ -129,3 +129,42 @@ def test_quicksort_branch_sync_points(oracle):
     tab[5] = oracle.fault_entry(1, 32 * L + 17, 30)
     o, s = oracle.run(oracle.K_QSORT, 3, a, n, unit_bytes=4 * L, flags=3, plan=oracle.make_plan(oracle.PLAN_TABLE, table=tab))
     assert (o.view(np.int32).reshape(n, L) == want).all() and s["injected"] == 1 and s["errors_corrected"] >= 1 and s["first_fault_unit"] == 5
+
+
+# ---------------------------------------------------------------- 8f-1: in-loop store votes
+def test_store_votes_change_the_sync_count_not_the_result(oracle):
+    """-storeDataSync / -noMemReplication (synchronization.cpp:205-215, syncStoreInst :476-560): every assignment to a data
+    variable is voted -- crc16: 3 per byte + the exit, matrix_multiply: K + the exit -- and -noStoreDataSync removes them again"""
+    import numpy as np
+    n, L = 50, 13
+    msg = oracle.fill_philox((n * L + 3) // 4, 0, 1).view(np.uint8)[: n * L].copy()
+    base, st0 = oracle.run(oracle.K_CRC16, 3, msg, n, unit_bytes=L, flags=3)
+    assert st0["syncs"] == n
+    for extra in (oracle.F_STORE_DATA_SYNC, oracle.F_NO_MEM_REPLICATION, oracle.F_NO_MEM_REPLICATION | oracle.F_NO_LOAD_SYNC):
+        out, st = oracle.run(oracle.K_CRC16, 3, msg, n, unit_bytes=L, flags=3 | extra)
+        assert out.tobytes() == base.tobytes() and st["syncs"] == n * (3 * L + 1) and st["errors_corrected"] == 0
+    out, st = oracle.run(oracle.K_CRC16, 3, msg, n, unit_bytes=L, flags=3 | oracle.F_NO_MEM_REPLICATION | oracle.F_NO_STORE_DATA_SYNC)
+    assert st["syncs"] == n                                     # C4 switched off again: only the forced SoR-exit votes remain
+    M = N = K = 9
+    A, B = oracle.fill_philox(M * K, 0, 4), oracle.fill_philox(K * N, 0, 44)
+    base, st0 = oracle.run(oracle.K_MM_U32, 3, A, M * N, flags=3, M=M, N=N, K=K, aux=B)
+    out, st = oracle.run(oracle.K_MM_U32, 3, A, M * N, flags=3 | oracle.F_NO_MEM_REPLICATION, M=M, N=N, K=K, aux=B)
+    assert out.tobytes() == base.tobytes() and st0["syncs"] == M * N and st["syncs"] == M * N * (K + 1)
+
+
+def test_store_votes_correct_a_flip_at_the_next_assignment(oracle):
+    """every site, one flipped replica: the output is always the fault-free one; TMR counts exactly one corrected vote per flip
+    (the next vote on a value computed from the flipped copy); DWC flags the unit"""
+    import numpy as np
+    L = 7
+    sites = list(range(2 * L))
+    n = len(sites)
+    msg = oracle.fill_philox((n * L + 3) // 4, 0, 1).view(np.uint8)[: n * L].copy()
+    clean, _ = oracle.run(oracle.K_CRC16, 1, msg, n, unit_bytes=L)
+    for rep in (0, 1, 2):
+        table = np.array([oracle.fault_entry(rep, s, (s * 5) % (16 if s < L else 8)) for s in sites], dtype=np.uint32)
+        out, st = oracle.run(oracle.K_CRC16, 3, msg, n, unit_bytes=L, flags=3 | oracle.F_STORE_DATA_SYNC, plan=oracle.make_plan(oracle.PLAN_TABLE, table=table))
+        assert out.tobytes() == clean.tobytes() and st["errors_corrected"] == n and st["injected"] == n
+        if rep < 2:
+            out, st = oracle.run(oracle.K_CRC16, 2, msg, n, unit_bytes=L, flags=oracle.F_STORE_DATA_SYNC, plan=oracle.make_plan(oracle.PLAN_TABLE, table=table))
+            assert st["dwc_detected"] == n
