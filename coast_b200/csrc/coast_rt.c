@@ -475,10 +475,15 @@ static int encode_rows_map(CUtensorMap* map, const void* base, uint32_t row_byte
 
 /* tcgen05 TF32 GEMM: A through a 2-D map (box 32 k x 128 m), B (row-major K x N, N contiguous) through a 3-D view
  * {32 n, K, N/32} (box 32 x 32 x 4) so one TMA lands the [n-chunk][k][128 B] layout the MN-major UMMA descriptor reads. */
-#define GEMM_SMEM (6u * (16384u + 16384u) + 1024u + 256u)
+/* tile geometry mirrors xmr::gemm::Geom<NC>: unprotected 128 x 256 tiles on 4 stages, DWC/TMR 128 x 128 on 6 stages */
 static int launch_gemm_tf32(const coast_launch_desc* d, xmr_args* a, int inj, CUstream stream) {
     char name[64];
-    snprintf(name, sizeof name, "xmr_gemm_tf32_nc%u_inj%d", d->num_clones, inj);
+    const int wide = d->num_clones == 1 && d->N % 256u == 0;
+    if (d->num_clones == 1 && !wide) snprintf(name, sizeof name, "xmr_gemm_tf32n_nc1_inj%d", inj);
+    else snprintf(name, sizeof name, "xmr_gemm_tf32_nc%u_inj%d", d->num_clones, inj);
+    const unsigned bn = wide ? 256u : 128u, stages = wide ? 4u : 6u;
+    const unsigned GEMM_SMEM = stages * (16384u + 32u * bn * 4u) + 1024u + 256u;
+    { const char* g = getenv("COAST_GEMM_GROUP_M"); if (g && atoi(g) > 0 && atoi(g) < 256) a->mode = (a->mode & ~0xFFu) | (unsigned)atoi(g); }
     CUfunction fn; int occ = 1;
     int rc = get_fn(name, GEMM_SMEM, &fn, &occ); if (rc) return rc;
     CUtensorMap ma, mb;
@@ -494,13 +499,13 @@ static int launch_gemm_tf32(const coast_launch_desc* d, xmr_args* a, int inj, CU
     {
         cuuint64_t gdim[3] = { 32, d->K, d->N / 32u };
         cuuint64_t gstr[2] = { (cuuint64_t)d->N * 4u, 128u };
-        cuuint32_t box[3] = { 32, 32, 4 };
+        cuuint32_t box[3] = { 32, 32, bn / 32u };
         cuuint32_t estr[3] = { 1, 1, 1 };
         DRV(p_cuTensorMapEncodeTiled(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)d->d_aux, gdim, gstr, box, estr,
                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
     }
-    unsigned tiles = (d->M / 128u) * (d->N / 128u);
+    unsigned tiles = (d->M / 128u) * (d->N / bn);
     unsigned grid = tiles < (unsigned)G.sm_count ? tiles : (unsigned)G.sm_count;
     void* params[3] = { a, &ma, &mb };
     if (d->flags & COAST_F_VERBOSE) fprintf(stderr, "coast_rt: %s grid=%u smem=%u tiles=%u\n", name, grid, GEMM_SMEM, tiles);

@@ -18,30 +18,51 @@
 // Fault site 0 = the replica's final accumulator value (32 bits) as read back for the vote.
 //
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4..7 = epilogue (TMEM lane quarter = warp % 4).  Persistent CTAs, one per SM, tile = 128 x 128.
+// warps 4..7 = epilogue (TMEM lane quarter = warp % 4).  Persistent CTAs, one per SM.
+//
+// r02: an SS-mode kind::tf32 MMA of 128 x 128 x 8 reads 8 KiB of operands from shared memory for 64 tensor-pipe cycles =
+// 128 B/clk, exactly the SM's shared-memory bandwidth -- the r01 kernels were shared-memory-read bound (ncu: tensor pipe
+// 70 % unprotected).  Two remedies, chosen per replica count (Geom<NC>):
+//   NC >= 2 : the A tile of a stage is copied ONCE from shared memory into TMEM (tcgen05.cp, 4 x 128x256b) and the NC
+//             replica MMAs of every k-step read A from TMEM (TS mode); shared-memory reads drop from 128 to 85 (TMR) /
+//             96 (DWC) B/clk.  Tile 128 x 128, NC accumulators + 32 columns of staged A.
+//   NC == 1 : tile 128 x 256 (MMA N = 256: 12 KiB per 128 cycles = 96 B/clk) with TWO accumulator buffers, so the epilogue
+//             of tile i overlaps the main loop of tile i+1.
 #pragma once
 #include "xmr_common.cuh"
 
 namespace xmr {
 namespace gemm {
 
-constexpr int BM = 128, BN = 128, BK = 32;          // BK fp32 = 128 bytes = one swizzle row
+constexpr int BM = 128, BK = 32;                     // BK fp32 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 8;                            // 32 bytes of tf32
-constexpr int STAGES = 6;
 constexpr uint32_t A_STAGE = BM * BK * 4;            // 16 KiB
-constexpr uint32_t B_STAGE = BK * BN * 4;            // 16 KiB, laid out [BN/32 chunks][BK rows][128 B]
-constexpr uint32_t SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr uint32_t TMEM_COLS = 512;                  // 3 replicas x 128 fp32 columns (power of two >= 384)
-constexpr uint32_t GROUP_M = 16;                     // tile rasterisation: 16 tile-rows per group, column-major inside
+constexpr uint32_t TMEM_COLS = 512;
+template <int NC, bool WIDE = (NC == 1)> struct Geom {         // WIDE: 128 x 256 tiles (unprotected, N % 256 == 0)
+    static constexpr int BN = WIDE ? 256 : 128;
+    static constexpr int STAGES = WIDE ? 4 : 6;
+    static constexpr int ACC_BUFS = NC == 1 ? 2 : 1;             // accumulator sets (double-buffered when TMEM allows)
+    static constexpr bool ATMEM = NC > 1;                         // stage A in TMEM, MMAs in TS mode
+    static constexpr uint32_t B_STAGE = BK * BN * 4;              // laid out [BN/32 chunks][BK rows][128 B]
+    static constexpr uint32_t ACC_COLS = (uint32_t)NC * BN * ACC_BUFS;
+    static constexpr uint32_t A_COLS = ATMEM ? BK : 0;            // one tf32 per 32-bit column
+    static_assert(ACC_COLS + A_COLS <= TMEM_COLS, "TMEM budget");
+    static constexpr uint32_t SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + 1024 /*align slack*/ + 256 /*barriers*/;
+    // Instruction descriptor: c_format F32 (1) [4,6), a/b_format TF32 (2) [7,10)/[10,13), a_major K (0) [15], b_major MN (1) [16]
+    // (B is row-major K x N: N contiguous), N>>3 [17,23), M>>4 [24,29)
+    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+constexpr uint32_t GROUP_M_DEFAULT = 16;             // tile rasterisation: 16 tile-rows per group, column-major inside
+constexpr uint32_t GROUP_M = GROUP_M_DEFAULT;        // (xmr_mm_tc.cuh uses the fixed value)
 
 // Persistent CTAs take tiles blockIdx.x, +grid, ...; consecutive tile ids therefore run concurrently.  Row-major ids
 // make one wave touch ~5 A row-blocks and ALL of B (ncu r01: 489 MB read for 134 MB of operands); grouping 16 tile-rows
 // and walking columns inside the group keeps a wave on ~16 A row-blocks x ~10 B column-blocks, which the 126 MB L2 holds.
-__device__ __forceinline__ void tile_coords(uint32_t tile, uint32_t tiles_m, uint32_t tiles_n, uint32_t& tm, uint32_t& tn) {
-    const uint32_t per_group = GROUP_M * tiles_n;
+__device__ __forceinline__ void tile_coords(uint32_t tile, uint32_t tiles_m, uint32_t tiles_n, uint32_t group_m, uint32_t& tm, uint32_t& tn) {
+    const uint32_t per_group = group_m * tiles_n;
     const uint32_t g = tile / per_group, w = tile - g * per_group;
-    const uint32_t rows = min(GROUP_M, tiles_m - g * GROUP_M);
-    tm = g * GROUP_M + w % rows;
+    const uint32_t rows = min(group_m, tiles_m - g * group_m);
+    tm = g * group_m + w % rows;
     tn = w / rows;
 }
 
@@ -63,6 +84,17 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// A operand from TMEM (128 lanes x 8 columns = 128 rows x 8 tf32 of K), B from shared memory
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// shared memory (matrix descriptor, 128 rows x 256 bits) -> TMEM (128 lanes x 8 columns); SASS UTCCP
+__device__ __forceinline__ void tc_cp_a_128x256b(uint32_t taddr, uint64_t s_desc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(s_desc) : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread = TMEM lane (row), registers = columns
 __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -92,12 +124,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)swizzle << 61);
 }
-// Instruction descriptor (InstrDescriptor): c_format F32 (1) [4,6), a/b_format TF32 (2) [7,10)/[10,13),
-// a_major K (0) [15], b_major MN (1) [16] (B is row-major K x N: N contiguous), N>>3 [17,23), M>>4 [24,29)
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-template <int NC, bool INJECT>
+template <int NC, bool INJECT, bool WIDE = (NC == 1)>
 __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* map_a, const CUtensorMap* map_b) {
+    using G = Geom<NC, WIDE>;
+    constexpr int BN = G::BN, STAGES = G::STAGES, ACC_BUFS = G::ACC_BUFS;
+    constexpr uint32_t B_STAGE = G::B_STAGE;
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023u) & ~(uintptr_t)1023u);
     uint8_t* sA = smem;
@@ -105,18 +136,18 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE + B_STAGE));
     uint64_t* full = bars;                 // [STAGES]  TMA -> MMA
     uint64_t* empty = bars + STAGES;       // [STAGES]  MMA -> TMA
-    uint64_t* tmem_full = bars + 2 * STAGES;       // MMA -> epilogue
-    uint64_t* tmem_empty = bars + 2 * STAGES + 1;  // epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+    uint64_t* tmem_full = bars + 2 * STAGES;                    // [ACC_BUFS] MMA -> epilogue
+    uint64_t* tmem_empty = bars + 2 * STAGES + ACC_BUFS;        // [ACC_BUFS] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_BUFS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles_n = a.N / BN, tiles_m = a.M / BM, n_tiles = tiles_m * tiles_n, kblocks = a.K / BK;
+    const uint32_t group_m = (a.mode & 0xFFu) ? (a.mode & 0xFFu) : GROUP_M_DEFAULT;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(map_a); tma_prefetch_desc(map_b);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 128);
+        for (int b = 0; b < ACC_BUFS; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
         fence_barrier_init();
     }
     if (warp == 2) {                                            // one warp allocates TMEM and later frees it
@@ -127,20 +158,21 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_a = tmem_base + G::ACC_COLS;            // ATMEM: the staged A tile of the current stage
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             uint32_t tm, tn;
-            tile_coords(tile, tiles_m, tiles_n, tm, tn);
+            tile_coords(tile, tiles_m, tiles_n, group_m, tm, tn);
             const int m0 = (int)tm * BM, n0 = (int)tn * BN;
             for (uint32_t kb = 0; kb < kblocks; ++kb, ++it) {
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&full[s], A_STAGE + B_STAGE);
                 tma_load_2d(sA + s * A_STAGE, map_a, &full[s], (int)(kb * BK), m0);              // box {32 k, 128 m}
-                tma_load_3d(sB + s * B_STAGE, map_b, &full[s], 0, (int)(kb * BK), n0 / 32);      // box {32 n, 32 k, 4 chunks}
+                tma_load_3d(sB + s * B_STAGE, map_b, &full[s], 0, (int)(kb * BK), n0 / 32);      // box {32 n, 32 k, BN/32 chunks}
             }
         }
     } else if (warp == 1) {
@@ -150,8 +182,10 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
         const bool leader = elect_one();
         uint32_t it = 0, tcount = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-            mbar_wait(tmem_empty, (tcount & 1u) ^ 1u);         // epilogue drained the accumulators of the previous tile
+            const uint32_t buf = tcount % ACC_BUFS, use = tcount / ACC_BUFS;
+            mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);       // epilogue drained this accumulator set
             tc_fence_after();
+            const uint32_t acc0 = tmem_base + buf * (uint32_t)(NC * BN);
             for (uint32_t kb = 0; kb < kblocks; ++kb, ++it) {
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                 mbar_wait(&full[s], ph);
@@ -162,18 +196,25 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
                     // B: MN-major, 32B-atom swizzle: atom = 4 k-rows x 128 B (512 B, SBO); N chunks BK*128 B apart (LBO);
                     // one UMMA_K = 8 k-rows = 1024 B further down the chunk
                     const uint64_t db0 = smem_desc(smem_u32(sB + s * B_STAGE), BK * 128, 512, SWZ_128B_BASE32B);
+                    if (G::ATMEM) {   // tcgen05.cp and tcgen05.mma execute in issue order: this copy cannot overtake the MMAs still reading stage it-1
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            tc_cp_a_128x256b(tmem_a + k * UMMA_K, da0 + (uint64_t)((k * UMMA_K * 4) >> 4));
+                    }
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t da = da0 + (uint64_t)((k * UMMA_K * 4) >> 4), db = db0 + (uint64_t)((k * 1024) >> 4);
 #pragma unroll
-                        for (int r = 0; r < NC; ++r)
-                            tc_mma_tf32(tmem_base + r * BN, da, db, IDESC, (kb | (uint32_t)k) ? 1u : 0u);
+                        for (int r = 0; r < NC; ++r) {
+                            if (G::ATMEM) tc_mma_tf32_ts(acc0 + r * BN, tmem_a + k * UMMA_K, db, G::IDESC, (kb | (uint32_t)k) ? 1u : 0u);
+                            else tc_mma_tf32(acc0 + r * BN, da, db, G::IDESC, (kb | (uint32_t)k) ? 1u : 0u);
+                        }
                     }
-                    tc_commit(&empty[s]);                       // smem slot free once these MMAs retire
+                    tc_commit(&empty[s]);                       // smem slot free once these MMAs (and the copy) retire
                 }
                 __syncwarp();
             }
-            if (leader) tc_commit(tmem_full);                   // accumulators complete
+            if (leader) tc_commit(&tmem_full[buf]);             // accumulators complete
             __syncwarp();
         }
     } else if (warp >= 4) {
@@ -186,12 +227,13 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
         uint32_t tcount = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
             uint32_t tm, tn;
-            tile_coords(tile, tiles_m, tiles_n, tm, tn);
+            tile_coords(tile, tiles_m, tiles_n, group_m, tm, tn);
             const uint32_t m0 = tm * BM, n0 = tn * BN;
-            mbar_wait(tmem_full, tcount & 1u);
+            const uint32_t buf = tcount % ACC_BUFS, use = tcount / ACC_BUFS;
+            mbar_wait(&tmem_full[buf], use & 1u);
             tc_fence_after();
             const uint32_t row = m0 + q * 32 + lane;
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t lane_addr = tmem_base + buf * (uint32_t)(NC * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[3][32];
@@ -229,7 +271,7 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
                 }
             }
             tc_fence_before();
-            mbar_arrive(tmem_empty);                            // 128 arrivals release the accumulators
+            mbar_arrive(&tmem_empty[buf]);                      // 128 arrivals release this accumulator set
         }
         tally.flush(a.counters);
     }
@@ -252,3 +294,11 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
     }
 XMR_GEMM_KERNEL(1, 0) XMR_GEMM_KERNEL(2, 0) XMR_GEMM_KERNEL(3, 0)
 XMR_GEMM_KERNEL(1, 1) XMR_GEMM_KERNEL(2, 1) XMR_GEMM_KERNEL(3, 1)
+// unprotected, N a multiple of 128 but not of 256: 128 x 128 tiles (shared-memory operands, two accumulator buffers)
+#define XMR_GEMM_KERNEL_NARROW(INJ)                                                                      \
+    extern "C" __global__ void __launch_bounds__(256, 1)                                                 \
+    xmr_gemm_tf32n_nc1_inj##INJ(const __grid_constant__ xmr_args a, const __grid_constant__ CUtensorMap map_a, \
+                                const __grid_constant__ CUtensorMap map_b) {                             \
+        xmr::gemm::gemm_body<1, INJ != 0, false>(a, &map_a, &map_b);                                     \
+    }
+XMR_GEMM_KERNEL_NARROW(0) XMR_GEMM_KERNEL_NARROW(1)

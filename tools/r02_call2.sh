@@ -18,6 +18,14 @@ python tools/profile_target.py --kernel aes --nc 2 --log2n 24 --iters 10 --time 
 python tools/profile_target.py --kernel aes --nc 2 --log2n 24 --iters 10 --time --aes-mode 7
 } > "$out/aes_timings.txt" 2>&1
 cat "$out/aes_timings.txt"
+{
+for nc in 1 2 3; do python tools/profile_target.py --kernel gemm --nc $nc --side 4096 --iters 20 --time; done
+python tools/profile_target.py --kernel gemm --nc 3 --side 4096 --iters 20 --time --inject 0.001
+for g in 8 32; do COAST_GEMM_GROUP_M=$g python tools/profile_target.py --kernel gemm --nc 3 --side 4096 --iters 20 --time; done
+python tools/profile_target.py --kernel gemm --nc 1 --side 8192 --iters 10 --time
+python tools/profile_target.py --kernel gemm --nc 3 --side 8192 --iters 10 --time
+} > "$out/gemm_timings.txt" 2>&1
+cat "$out/gemm_timings.txt"
 for hp in staged hybrid; do
   for wl in sha256 aes crc16; do
     timeout 300 python bench.py --steps 20 --warmup 5 --no-also --no-cpu-baseline --workload $wl --host-path $hp > "$out/bench_${wl}_${hp}.json" 2> "$out/bench_${wl}_${hp}.err"; echo "bench $wl $hp rc=$?" | tee -a "$out/summary.txt"
@@ -27,6 +35,9 @@ timeout 300 python bench.py --steps 20 --warmup 5 --no-also --no-cpu-baseline --
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:xmr_aes128_enc_nc2_inj1 -c 1 -o "$out/aes_enc_nc2_inj1" python tools/profile_target.py --kernel aes --nc 2 --log2n 24 --iters 2 --inject 0.0009765625 > "$out/ncu1.log" 2>&1; echo "ncu1 rc=$?" | tee -a "$out/summary.txt"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:xmr_aes128_enc_nc2_inj0 -c 1 -o "$out/aes_enc_nc2_inj0" python tools/profile_target.py --kernel aes --nc 2 --log2n 24 --iters 2 > "$out/ncu2.log" 2>&1; echo "ncu2 rc=$?" | tee -a "$out/summary.txt"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:xmr_aes128_dec_nc2_inj0 -c 1 -o "$out/aes_dec_nc2_inj0" python tools/profile_target.py --kernel aes --nc 2 --log2n 24 --iters 2 --aes-mode 1 > "$out/ncu3.log" 2>&1; echo "ncu3 rc=$?" | tee -a "$out/summary.txt"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:xmr_gemm_tf32_nc3_inj0 -c 1 -o "$out/gemm_nc3" python tools/profile_target.py --kernel gemm --nc 3 --side 4096 --iters 2 > "$out/ncu4.log" 2>&1; echo "ncu4 rc=$?" | tee -a "$out/summary.txt"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:xmr_gemm_tf32_nc1_inj0 -c 1 -o "$out/gemm_nc1" python tools/profile_target.py --kernel gemm --nc 1 --side 4096 --iters 2 > "$out/ncu5.log" 2>&1; echo "ncu5 rc=$?" | tee -a "$out/summary.txt"
+COAST_GEMM_GROUP_M=32 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:xmr_gemm_tf32_nc3_inj0 -c 1 --csv --log-file "$out/gemm_nc3_g32_traffic.csv" python tools/profile_target.py --kernel gemm --nc 3 --side 4096 --iters 2 > "$out/ncu6.log" 2>&1; echo "ncu6 rc=$?" | tee -a "$out/summary.txt"
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/r02c2/bench_*.json')):
