@@ -166,11 +166,19 @@ __device__ __forceinline__ void crc16_b64_body(const xmr_args& a, const CUtensor
     tally.flush(a.counters);
 }
 
-// General path: any length 1..255, bytes read straight from global memory.
+// General path: any length 1..255, bytes read straight from global memory (word loads when every message is 4-byte
+// aligned).  Table form of the byte step (r02; the r01 general path ran the 10.6-instruction arithmetic step):
+//     crc' = ((crc << 8) & 0xFFFF) ^ T[(crc >> 8) ^ b],   T[x] = crc16_step(0, x)
+// with T replicated over the 32 lanes in shared memory (bank = lane: conflict-free whatever the data).
 template <int NC, bool INJECT>
 __device__ __forceinline__ void crc16_gen_body(const xmr_args& a) {
     constexpr int UPW = Lanes<NC>::kUnitsPerWarp;
+    __shared__ uint32_t tab[256 * 32];
+    for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) tab[i] = crc16_step(0u, (uint32_t)i >> 5);   // the reference's own byte step fills the table
+    __syncthreads();
     const int lane = threadIdx.x & 31;
+    const uint32_t* const tl = tab + lane;
+    const bool words = ((reinterpret_cast<uintptr_t>(a.in) | a.unit_bytes) & 3u) == 0;
     const int r = Lanes<NC>::replica(lane);
     const unsigned long long gwarp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
@@ -191,10 +199,12 @@ __device__ __forceinline__ void crc16_gen_body(const xmr_args& a) {
         }
         uint32_t crc = 0xFFFFu;
         if (!(a.flags & XMR_F_STORE_VOTES)) {
+            uint32_t w = 0;
             for (uint32_t i = 0; i < len; ++i) {
-                uint32_t b = __ldg(msg + i);
+                if (words) { if ((i & 3u) == 0) w = __ldg(reinterpret_cast<const uint32_t*>(msg + i)); }
+                uint32_t b = words ? (w >> (8u * (i & 3u))) & 0xFFu : (uint32_t)__ldg(msg + i);
                 if (INJECT && fsite == len + i) b ^= fmask;
-                crc = crc16_step(crc, b);
+                crc = ((crc << 8) & 0xFFFFu) ^ tl[(((crc >> 8) ^ b) & 0xFFu) << 5];
                 if (INJECT && fsite == i) crc ^= fmask;
             }
             crc_vote_store<NC>(crc, static_cast<uint16_t*>(a.out), local, a.unit_base + local, valid, lane, a.flags, tally);

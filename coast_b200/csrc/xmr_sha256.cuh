@@ -201,13 +201,25 @@ __device__ __forceinline__ void sha256_gen_body(const xmr_args& a) {
         }
         uint32_t st[8];
         sha_init(st);
+        // r02: whole blocks come in as 4 x 16-byte (or 16 x 4-byte) loads when every message is that aligned; the byte walk
+        // is left for the padded tail and for unaligned batches (r01 fetched 64 single bytes per block)
+        const uintptr_t al = reinterpret_cast<uintptr_t>(a.in) | len;
         for (uint32_t blk = 0; blk < nblk; ++blk) {
             uint32_t m[16];
+            if ((al & 15u) == 0 && blk * 64u + 64u <= len) {
 #pragma unroll
-            for (int w = 0; w < 16; ++w) {
-                uint32_t p = blk * 64u + 4u * w;
-                m[w] = (sha_padded_byte(msg, len, p) << 24) | (sha_padded_byte(msg, len, p + 1) << 16) |
-                       (sha_padded_byte(msg, len, p + 2) << 8) | sha_padded_byte(msg, len, p + 3);
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(msg + blk * 64u) + c);
+                    m[4 * c + 0] = bswap(q.x); m[4 * c + 1] = bswap(q.y); m[4 * c + 2] = bswap(q.z); m[4 * c + 3] = bswap(q.w);
+                }
+            } else {
+#pragma unroll
+                for (int w = 0; w < 16; ++w) {
+                    const uint32_t p = blk * 64u + 4u * w;
+                    if ((al & 3u) == 0 && p + 4u <= len) m[w] = bswap(__ldg(reinterpret_cast<const uint32_t*>(msg + p)));
+                    else m[w] = (sha_padded_byte(msg, len, p) << 24) | (sha_padded_byte(msg, len, p + 1) << 16) |
+                                (sha_padded_byte(msg, len, p + 2) << 8) | sha_padded_byte(msg, len, p + 3);
+                }
             }
             if (blk == nblk - 1) {                            // :155-163, 64-bit big-endian bit count
                 m[14] = len >> 29;
