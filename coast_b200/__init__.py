@@ -8,7 +8,7 @@ streams and ``torch.distributed`` -- plumbing only.
 """
 from .runtime import (  # noqa: F401
     AES_DECRYPT, AES_KEY_PER_UNIT, AES_KEY_WRITEBACK, F_COUNT_ERRORS, F_COUNT_SYNCS, F_INTERLEAVE, F_MAJORITY_VOTER,
-    F_NO_MEM_REPLICATION, F_SEGMENT, F_VERBOSE, K_AES128, K_CHSTONE_SHA, K_CRC16, K_GEMM_TF32, K_MM_U32, K_QSORT, K_SHA256,
+    F_NO_MEM_REPLICATION, F_SEGMENT, F_VERBOSE, K_AES128, K_CHSTONE_AES, K_CHSTONE_SHA, K_CRC16, K_GEMM_TF32, K_MM_U32, K_QSORT, K_SHA256,
     F_NO_LOAD_SYNC, F_NO_STORE_ADDR_SYNC, F_NO_STORE_DATA_SYNC, F_STORE_DATA_SYNC,
     NO_FAULT_UNIT, PLAN_BERNOULLI, PLAN_NONE, PLAN_TABLE, CoastError, FaultPlan, LaunchDesc, Runtime, Stats,
     fault_entry, lib_path, load_library, parse_opt_passes,

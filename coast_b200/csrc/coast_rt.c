@@ -409,21 +409,22 @@ uint32_t coast_fault_sites(uint32_t kernel, uint32_t unit_bytes, uint32_t K) {
     case COAST_K_GEMM_TF32: return 1u;
     case COAST_K_QSORT:     return 33u * (unit_bytes / 4u);
     case COAST_K_CHSTONE_SHA: return 421u * (unit_bytes / 64u + 1u);
+    case COAST_K_CHSTONE_AES: return 176u;
     default:                return 0u;
     }
 }
 uint32_t coast_fault_site_bits(uint32_t kernel, uint32_t unit_bytes, uint32_t K, uint32_t site) {
     (void)K;
     if (kernel == COAST_K_CRC16) return site < unit_bytes ? 16u : 8u;
-    if (kernel == COAST_K_AES128) return 8u;
+    if (kernel == COAST_K_AES128 || kernel == COAST_K_CHSTONE_AES) return 8u;
     return 32u;
 }
 uint32_t coast_out_bytes_per_unit(uint32_t kernel) {
-    static const uint32_t ob[COAST_K_COUNT_] = { 2, 32, 16, 4, 4, 0, 20 };
+    static const uint32_t ob[COAST_K_COUNT_] = { 2, 32, 16, 4, 4, 0, 20, 64 };
     return kernel < COAST_K_COUNT_ ? ob[kernel] : 0;
 }
 uint32_t coast_votes_per_unit(uint32_t kernel) {
-    static const uint32_t nv[COAST_K_COUNT_] = { 1, 32, 16, 1, 1, 0, 5 };
+    static const uint32_t nv[COAST_K_COUNT_] = { 1, 32, 16, 1, 1, 0, 5, 16 };
     return kernel < COAST_K_COUNT_ ? nv[kernel] : 0;
 }
 uint32_t coast_out_bytes(uint32_t kernel, uint32_t unit_bytes) {
@@ -433,8 +434,14 @@ static uint64_t in_bytes_per_unit(const coast_launch_desc* d) {
     switch (d->kernel) {
     case COAST_K_CRC16: case COAST_K_SHA256: case COAST_K_QSORT: case COAST_K_CHSTONE_SHA: return d->unit_bytes;
     case COAST_K_AES128: return 16;
+    case COAST_K_CHSTONE_AES: return 64;
     default: return 0;
     }
+}
+/* bytes of per-unit aux data the host call stages next to the input (AES keys) */
+static uint64_t aux_bytes_per_unit(const coast_launch_desc* d) {
+    if (!(d->mode & COAST_AES_KEY_PER_UNIT)) return 0;
+    return d->kernel == COAST_K_AES128 ? 16 : d->kernel == COAST_K_CHSTONE_AES ? 64 : 0;
 }
 
 /* ------------------------------------------------------------------ */
@@ -599,7 +606,7 @@ static int launch_impl(const coast_launch_desc* d, void* stream) {
     /* in-loop store votes (-storeDataSync / -noMemReplication): built for CRC16 and MM_U32, loud everywhere else */
     const int store_votes = store_votes_wanted(d->flags) && nc > 1;
     if (store_votes && !store_votes_built(d->kernel)) {
-        static const char* const kname[COAST_K_COUNT_] = { "crc16", "sha256", "aes128", "mm_u32", "gemm_tf32", "qsort", "chstone_sha" };
+        static const char* const kname[COAST_K_COUNT_] = { "crc16", "sha256", "aes128", "mm_u32", "gemm_tf32", "qsort", "chstone_sha", "chstone_aes" };
         const char* strict = getenv("COAST_STRICT_FLAGS");
         if (strict && strcmp(strict, "0"))
             return fail(COAST_ERR_UNSUPPORTED, "-noMemReplication / -storeDataSync: the %s kernel has no in-loop store votes "
@@ -697,6 +704,16 @@ static int launch_impl(const coast_launch_desc* d, void* stream) {
             return fail(COAST_ERR_BAD_ARG, "CHStone sha streams are whole 64-byte blocks, 64 <= unit_bytes < 2^29 (got %u)", d->unit_bytes);
         if (!aligned16 || (((uintptr_t)d->d_out) & 3u)) return fail(COAST_ERR_BAD_ARG, "CHStone sha: d_in must be 16-byte and d_out 4-byte aligned");
         snprintf(name, sizeof name, "xmr_chsha_nc%u_inj%d", nc, inj);
+        break;
+    case COAST_K_CHSTONE_AES:
+        if ((d->mode & COAST_AES_KEY_PER_UNIT) && !d->d_aux) return fail(COAST_ERR_BAD_ARG, "per-unit keys need d_aux");
+        if (!aligned16 || (((uintptr_t)d->d_out) & 15u) || ((d->mode & COAST_AES_KEY_PER_UNIT) && (((uintptr_t)d->d_aux) & 15u)))
+            return fail(COAST_ERR_BAD_ARG, "CHStone aes buffers must be 16-byte aligned");
+        block = 512; smem = (d->mode & COAST_AES_DECRYPT) ? 0x38000u : 0x30000u;        /* same shared-memory tables as the TI kernels */
+        {
+            static const char* const stem[2] = { "xmr_chaes_enc", "xmr_chaes_dec" };
+            snprintf(name, sizeof name, "%s_nc%u_inj%d", stem[(d->mode & COAST_AES_DECRYPT) ? 1 : 0], nc, inj);
+        }
         break;
     case COAST_K_GEMM_TF32:
         if (!d->d_aux || !d->M || !d->N || !d->K) return fail(COAST_ERR_BAD_ARG, "GEMM needs A (d_in), B (d_aux) and M,N,K");
@@ -862,6 +879,7 @@ static int drain_host_streams(void) {
 /* Chunked pipeline: H2D -> kernel -> D2H per chunk, chunks round-robin over 3 streams / 3 staging slots. */
 static int run_host_staged(const coast_launch_desc* d, uint64_t ib, uint64_t ob, int per_unit_key, CUdeviceptr zin) {
     int rc;
+    const uint64_t ab = aux_bytes_per_unit(d);
     const uint64_t ibs = ib ? ib : 1;                          /* divisor of the chunk schedule */
     /* each chunk is its own launch (own tensor map); the fault plan is keyed by the global unit index so
      * chunking never changes results */
@@ -897,8 +915,8 @@ static int run_host_staged(const coast_launch_desc* d, uint64_t ib, uint64_t ob,
         c.d_out = (void*)G.h_out[slot];
         c.n_units = n; c.unit_base = d->unit_base + done;
         if (per_unit_key) {
-            rc = slot_reserve(&G.h_aux[slot], &G.h_aux_cap[slot], (size_t)(chunk * 16)); if (rc) goto fail;
-            STEP(p_cuMemcpyHtoDAsync_v2(G.h_aux[slot], (const uint8_t*)d->d_aux + done * 16, (size_t)(n * 16), G.hs[slot]));
+            rc = slot_reserve(&G.h_aux[slot], &G.h_aux_cap[slot], (size_t)(chunk * ab)); if (rc) goto fail;
+            STEP(p_cuMemcpyHtoDAsync_v2(G.h_aux[slot], (const uint8_t*)d->d_aux + done * ab, (size_t)(n * ab), G.hs[slot]));
             c.d_aux = (void*)G.h_aux[slot];
         }
         if (d->d_status) {                                         /* kernels index status[] chunk-locally: stage it per slot */
@@ -907,7 +925,7 @@ static int run_host_staged(const coast_launch_desc* d, uint64_t ib, uint64_t ob,
         }
         rc = launch_impl(&c, G.hs[slot]); if (rc) goto fail;
         STEP(p_cuMemcpyDtoHAsync_v2((uint8_t*)d->d_out + done * ob, G.h_out[slot], (size_t)(n * ob), G.hs[slot]));
-        if (per_unit_key && (d->mode & COAST_AES_KEY_WRITEBACK))
+        if (per_unit_key && d->kernel == COAST_K_AES128 && (d->mode & COAST_AES_KEY_WRITEBACK))
             STEP(p_cuMemcpyDtoHAsync_v2((uint8_t*)d->d_aux + done * 16, G.h_aux[slot], (size_t)(n * 16), G.hs[slot]));
         if (d->d_status) STEP(p_cuMemcpyDtoHAsync_v2((uint8_t*)d->d_status + done, G.h_stat[slot], (size_t)n, G.hs[slot]));
         done += n; slot = (slot + 1) % 3;
@@ -983,7 +1001,7 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int* dwc_
     const uint64_t ib = in_bytes_per_unit(d);
     /* a zero-length SHA-256 message (sha256_hash(len = 0) hashes one padded block) has nothing to stage */
     if (!ob || (!ib && d->kernel != COAST_K_SHA256)) return fail(COAST_ERR_UNSUPPORTED, "coast_run_host: kernel %u", d->kernel);
-    const int per_unit_key = d->kernel == COAST_K_AES128 && (d->mode & COAST_AES_KEY_PER_UNIT);
+    const int per_unit_key = aux_bytes_per_unit(d) != 0;
     if (d->n_units == 0) return sync_impl(G.hs[2], out, dwc_fired);
 
     /* Three ways to move the bytes (COAST_HOST_PATH=staged|hybrid|zerocopy overrides the default):
@@ -995,14 +1013,14 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int* dwc_
      *             memory lose to the copy engine (profiles/r02_e2e_zero_copy_experiment.md); kept for small calls. */
     const char* hp = getenv("COAST_HOST_PATH");
     const int streams_once = d->kernel == COAST_K_CRC16 || d->kernel == COAST_K_SHA256 || d->kernel == COAST_K_AES128 ||
-                             d->kernel == COAST_K_CHSTONE_SHA;
+                             d->kernel == COAST_K_CHSTONE_SHA || d->kernel == COAST_K_CHSTONE_AES;
     const int want = hp ? (!strcmp(hp, "zerocopy") ? 2 : !strcmp(hp, "hybrid") ? 1 : 0) : G.host_path_default;
     CUdeviceptr zin = 0;
     if (streams_once && want && ib) zin = host_alias(d->d_in, (size_t)(d->n_units * ib));
     if (want == 2 && streams_once) {
         CUdeviceptr zi = ib ? zin : (CUdeviceptr)G.counters /* never read */;
         CUdeviceptr zo = host_alias(d->d_out, (size_t)(d->n_units * ob));
-        CUdeviceptr za = per_unit_key ? host_alias(d->d_aux, (size_t)(d->n_units * 16)) : 0;
+        CUdeviceptr za = per_unit_key ? host_alias(d->d_aux, (size_t)(d->n_units * aux_bytes_per_unit(d))) : 0;
         CUdeviceptr zs = d->d_status ? host_alias(d->d_status, (size_t)d->n_units) : 0;
         if (zi && zo && (!per_unit_key || za) && (!d->d_status || zs)) {
             coast_launch_desc c = *d;
@@ -1115,6 +1133,21 @@ void coast_xmr_chstone_sha_stream(const unsigned char* indata, const int* in_i, 
     d.kernel = COAST_K_CHSTONE_SHA; d.n_units = 1; d.unit_bytes = (uint32_t)total; d.d_in = cat; d.d_out = digest;
     entry_run(&d);
     free(cat);
+}
+void coast_xmr_chstone_aes(int* statemt, const int* key, int type, int dir) {
+    if (type != 128128) {
+        fprintf(stderr, "coast_rt: chstone/aes type %d: only 128128 (the benchmark's, aes.c:126-127) has a protected kernel\n", type);
+        abort();
+    }
+    coast_launch_desc d; memset(&d, 0, sizeof d);
+    entry_mode(&d.num_clones, &d.flags);
+    /* 16-byte aligned bounce buffers: the program's statemt[] / key[] are plain int arrays */
+    int st[16] __attribute__((aligned(16))), k[16] __attribute__((aligned(16)));
+    memcpy(st, statemt, sizeof st); memcpy(k, key, sizeof k);
+    d.kernel = COAST_K_CHSTONE_AES; d.n_units = 1; d.d_in = st; d.d_out = st; d.d_aux = k;
+    d.mode = (dir ? COAST_AES_DECRYPT : 0) | COAST_AES_KEY_PER_UNIT;
+    entry_run(&d);
+    memcpy(statemt, st, sizeof st);
 }
 void coast_xmr_matrix_multiply_u32(const uint32_t* f, const uint32_t* s, uint32_t* r, int side) {
     coast_launch_desc d; memset(&d, 0, sizeof d);

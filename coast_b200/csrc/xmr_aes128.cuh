@@ -158,6 +158,35 @@ __device__ __forceinline__ void aes_rounds(const AesLaneBases& L, uint32_t (&s)[
     }
 }
 
+// the shared-memory tables of one direction (all threads of the CTA; the caller synchronises)
+template <bool DEC>
+__device__ __forceinline__ void aes_build_tables(uint8_t* smem_raw, uint32_t win, int tid) {
+    uint32_t* t01 = reinterpret_cast<uint32_t*>(smem_raw + (AES_TAB01 - win));
+    uint32_t* t23 = reinterpret_cast<uint32_t*>(smem_raw + (AES_TAB23 - win));
+    for (int i = tid; i < 256 * 64; i += AES_THREADS) {
+        uint32_t v;
+        if (!DEC) v = XMR_AES_TE0[i >> 6];
+        else v = inv_mix_column((uint32_t)XMR_AES_RSBOX[i >> 6]);   // TD0[x]: InvMixColumns of the column (InvS[x], 0, 0, 0) = (14, 9, 13, 11) . InvS[x]
+        const bool hi = (i & 32) != 0;
+        t01[i] = hi ? __byte_perm(v, 0u, 0x2103u) : v;                               // T1 = rotl8
+        t23[i] = hi ? __byte_perm(v, 0u, 0x0321u) : __byte_perm(v, 0u, 0x1032u);     // T3 = rotl24 : T2 = rotl16
+    }
+    if (DEC) {
+        uint32_t* sis = reinterpret_cast<uint32_t*>(smem_raw + (AES_SIS - win));
+        for (int i = tid; i < 256 * 32; i += AES_THREADS) {
+            const uint32_t is = XMR_AES_RSBOX[i >> 5], sb = XMR_AES_SBOX[i >> 5];
+            sis[i] = is | (sb << 8) | (is << 16) | (sb << 24);
+        }
+    }
+}
+__device__ __forceinline__ AesLaneBases aes_lane_bases(int lane) {
+    AesLaneBases L;
+    L.lb0 = AES_TAB01 + 4u * lane; L.lb1 = AES_TAB01 + 128u + 4u * lane;
+    L.lb2 = AES_TAB23 + 4u * lane; L.lb3 = AES_TAB23 + 128u + 4u * lane;
+    L.sis2x = 2u * (AES_SIS + 4u * lane);
+    return L;
+}
+
 template <int NC, bool INJECT, bool DEC, bool PERKEY>
 __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap* tmap) {
     constexpr int UPW = Lanes<NC>::kUnitsPerWarp;
@@ -170,32 +199,9 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
     Ring ring;
     ring.init(ring_mem, tmap, (a.mode >> 8) & 15u);             // XMR_AES_ROWPACK: 16-byte blocks described as 64- or 256-byte rows
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {   // build the tables
-        uint32_t* t01 = reinterpret_cast<uint32_t*>(smem_raw + (AES_TAB01 - win));
-        uint32_t* t23 = reinterpret_cast<uint32_t*>(smem_raw + (AES_TAB23 - win));
-        for (int i = tid; i < 256 * 64; i += AES_THREADS) {
-            uint32_t v;
-            if (!DEC) v = XMR_AES_TE0[i >> 6];
-            else {                                              // TD0[x]: InvMixColumns of the column (InvS[x], 0, 0, 0) = (14, 9, 13, 11) . InvS[x]
-                v = inv_mix_column((uint32_t)XMR_AES_RSBOX[i >> 6]);
-            }
-            const bool hi = (i & 32) != 0;
-            t01[i] = hi ? __byte_perm(v, 0u, 0x2103u) : v;                               // T1 = rotl8
-            t23[i] = hi ? __byte_perm(v, 0u, 0x0321u) : __byte_perm(v, 0u, 0x1032u);     // T3 = rotl24 : T2 = rotl16
-        }
-        if (DEC) {
-            uint32_t* sis = reinterpret_cast<uint32_t*>(smem_raw + (AES_SIS - win));
-            for (int i = tid; i < 256 * 32; i += AES_THREADS) {
-                const uint32_t is = XMR_AES_RSBOX[i >> 5], sb = XMR_AES_SBOX[i >> 5];
-                sis[i] = is | (sb << 8) | (is << 16) | (sb << 24);
-            }
-        }
-    }
+    aes_build_tables<DEC>(smem_raw, win, tid);
     __syncthreads();
-    AesLaneBases L;
-    L.lb0 = AES_TAB01 + 4u * lane; L.lb1 = AES_TAB01 + 128u + 4u * lane;
-    L.lb2 = AES_TAB23 + 4u * lane; L.lb3 = AES_TAB23 + 128u + 4u * lane;
-    L.sis2x = 2u * (AES_SIS + 4u * lane);
+    const AesLaneBases L = aes_lane_bases(lane);
     const int r = Lanes<NC>::replica(lane);
     const int u = Lanes<NC>::unit(lane);
 
@@ -317,6 +323,92 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
     tally.flush(a.counters);
 }
 
+// ---------------------------------------------------------------------------------------------
+// CHStone `aes` (tests/chstone/aes/aes_enc.c:66-134, aes_dec.c:66-140, aes_func.c, aes_key.c; type 128128): the same
+// cipher with one byte per `int`.  Unit = one block: 16 ints in (64 bytes), 16 ints out; the key (16 ints per unit in
+// d_aux, or the 16 bytes of the descriptor) is expanded on the fly per replica and never written back (KeySchedule fills
+// word[][], aes_key.c:129-163, the key itself is untouched).  SoR exit = the 16 `int` elements of statemt (compared one
+// by one, aes_enc.c:130-131): 16 votes.  Same rounds, tables and fault hooks as the TI kernel; a fault site is
+// "statemt[i] right after a round-key addition", which is where the TI enumeration puts it too (header).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack4(uint4 q) { return (q.x & 0xFFu) | ((q.y & 0xFFu) << 8) | ((q.z & 0xFFu) << 16) | ((q.w & 0xFFu) << 24); }
+__device__ __forceinline__ uint4 unpack4(uint32_t w) { return make_uint4(w & 0xFFu, (w >> 8) & 0xFFu, (w >> 16) & 0xFFu, w >> 24); }
+
+template <int NC, bool INJECT, bool DEC>
+__device__ __forceinline__ void chstone_aes_body(const xmr_args& a) {
+    constexpr int UPW = Lanes<NC>::kUnitsPerWarp;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t win = smem_u32(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    aes_build_tables<DEC>(smem_raw, win, tid);
+    __syncthreads();
+    const AesLaneBases L = aes_lane_bases(lane);
+    const int r = Lanes<NC>::replica(lane);
+    const unsigned long long gwarp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long n_wtiles = (a.n_units + UPW - 1) / UPW;
+    const bool per_unit = a.mode & 2u;
+    const bool majority = a.flags & COAST_F_MAJORITY_D;
+    const uint32_t rk_unused[4] = {0u, 0u, 0u, 0u};
+    Tally tally(a);
+    for (unsigned long long wt = gwarp; wt < n_wtiles; wt += nwarps) {
+        const unsigned long long local = wt * UPW + Lanes<NC>::unit(lane);
+        const bool valid = local < a.n_units;
+        const unsigned long long ld = valid ? local : 0ull;
+        uint32_t s[1][4], k[1][4];
+        const uint4* ip = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(a.in) + ld * 64ull);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[0][c] = pack4(__ldg(ip + c));
+        if (per_unit) {
+            const uint4* kp = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(a.aux) + ld * 64ull);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) k[0][c] = pack4(__ldg(kp + c));
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                k[0][c] = (uint32_t)a.key[4 * c] | ((uint32_t)a.key[4 * c + 1] << 8) | ((uint32_t)a.key[4 * c + 2] << 16) | ((uint32_t)a.key[4 * c + 3] << 24);
+        }
+        uint32_t fbit[1] = {0u}; int frd[1] = {-2}, fcol[1] = {0};
+        bool hooks = false;
+        if (INJECT) {
+            Fault f = fault_for_unit(a, NC, ld, [](uint32_t) { return 8u; });
+            bool mid = false;
+            if (f.active && valid) {
+                if (Lanes<NC>::voter(lane)) tally.injected++;
+                if ((int)f.replica == r) {
+                    const uint32_t i = f.site < 16u ? f.site : ((f.site - 16u) & 15u);
+                    frd[0] = f.site < 16u ? -1 : (int)((f.site - 16u) >> 4);
+                    fcol[0] = (int)(i >> 2);
+                    fbit[0] = (1u << f.bit) << (8u * (i & 3u));
+                    if (frd[0] < 0) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) s[0][c] ^= fcol[0] == c ? fbit[0] : 0u;
+                    } else mid = true;
+                }
+            }
+            hooks = __any_sync(0xFFFFFFFFu, mid);
+        }
+        if (DEC) {
+#pragma unroll
+            for (int rd = 0; rd < 10; ++rd) key_next<true>(L, k[0], rd);          // word[][40..43]: the last round key (aes_dec.c:115)
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[0][c] ^= k[0][c];                           // AddRoundKey(0) / AddRoundKey(10)
+        if (INJECT && hooks) aes_rounds<1, DEC, true, true>(L, s, k, rk_unused, fbit, frd, fcol);
+        else aes_rounds<1, DEC, true, false>(L, s, k, rk_unused, fbit, frd, fcol);
+        uint32_t o[4], bad = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { Voted v = vote_u32<NC, 1>(s[0][c], majority); o[c] = v.vote; bad += v.bad; }   // one byte per int: 16 element votes
+        if (valid && Lanes<NC>::voter(lane)) {
+            uint4* op = reinterpret_cast<uint4*>(static_cast<uint8_t*>(a.out) + local * 64ull);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) op[c] = unpack4(o[c]);
+            tally.unit_exit<NC>(bad, 16u, a.flags, a.unit_base + local);
+        }
+    }
+    tally.flush(a.counters);
+}
+
 }  // namespace xmr
 
 #define XMR_AES_KERNEL(NAME, NC, INJ, DEC, PERKEY)                                                       \
@@ -329,3 +421,9 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
     XMR_AES_KERNEL(enck, NC, INJ, false, true) XMR_AES_KERNEL(deck, NC, INJ, true, true)
 XMR_AES_ALL(1, 0) XMR_AES_ALL(2, 0) XMR_AES_ALL(3, 0)
 XMR_AES_ALL(1, 1) XMR_AES_ALL(2, 1) XMR_AES_ALL(3, 1)
+#define XMR_CHAES_KERNEL(NAME, NC, INJ, DEC)                                                             \
+    extern "C" __global__ void __launch_bounds__(xmr::AES_THREADS, 1)                                    \
+    xmr_chaes_##NAME##_nc##NC##_inj##INJ(const __grid_constant__ xmr_args a) { xmr::chstone_aes_body<NC, INJ != 0, DEC>(a); }
+#define XMR_CHAES_ALL(NC, INJ) XMR_CHAES_KERNEL(enc, NC, INJ, false) XMR_CHAES_KERNEL(dec, NC, INJ, true)
+XMR_CHAES_ALL(1, 0) XMR_CHAES_ALL(2, 0) XMR_CHAES_ALL(3, 0)
+XMR_CHAES_ALL(1, 1) XMR_CHAES_ALL(2, 1) XMR_CHAES_ALL(3, 1)

@@ -12,7 +12,7 @@ from dataclasses import dataclass
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-K_CRC16, K_SHA256, K_AES128, K_MM_U32, K_GEMM_TF32, K_QSORT, K_CHSTONE_SHA = range(7)
+K_CRC16, K_SHA256, K_AES128, K_MM_U32, K_GEMM_TF32, K_QSORT, K_CHSTONE_SHA, K_CHSTONE_AES = range(8)
 F_COUNT_ERRORS, F_COUNT_SYNCS, F_NO_MEM_REPLICATION = 0x1, 0x2, 0x4
 F_INTERLEAVE, F_SEGMENT, F_VERBOSE, F_MAJORITY_VOTER = 0x8, 0x10, 0x20, 0x100
 F_STORE_DATA_SYNC, F_NO_STORE_DATA_SYNC, F_NO_LOAD_SYNC, F_NO_STORE_ADDR_SYNC = 0x200, 0x400, 0x800, 0x1000
@@ -21,7 +21,7 @@ AES_DECRYPT, AES_KEY_PER_UNIT, AES_KEY_WRITEBACK = 1, 2, 4
 NO_FAULT_UNIT = 0xFFFFFFFFFFFFFFFF
 ERR_NO_DRIVER, ERR_NOT_INIT, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_BUSY = -100001, -100002, -100003, -100004, -100005
 
-OUT_BYTES = {K_CRC16: 2, K_SHA256: 32, K_AES128: 16, K_MM_U32: 4, K_GEMM_TF32: 4, K_CHSTONE_SHA: 20}
+OUT_BYTES = {K_CRC16: 2, K_SHA256: 32, K_AES128: 16, K_MM_U32: 4, K_GEMM_TF32: 4, K_CHSTONE_SHA: 20, K_CHSTONE_AES: 64}
 
 
 def out_bytes(kernel: int, unit_bytes: int = 0) -> int:
@@ -103,7 +103,7 @@ EXPORTS = [
     "coast_stream_create", "coast_stream_destroy", "coast_stream_sync", "coast_fill_philox", "coast_run_host",
     "coast_run_host_noabort", "coast_last_host_path",
     "coast_set_opt_passes", "coast_xmr_crc16", "coast_xmr_sha256_hash", "coast_xmr_aes_enc_dec",
-    "coast_xmr_matrix_multiply_u32", "coast_xmr_chstone_sha_stream", "TMR_ERROR_CNT", "__SYNC_COUNT", "FAULT_DETECTED_DWC",
+    "coast_xmr_matrix_multiply_u32", "coast_xmr_chstone_sha_stream", "coast_xmr_chstone_aes", "TMR_ERROR_CNT", "__SYNC_COUNT", "FAULT_DETECTED_DWC",
 ]
 
 

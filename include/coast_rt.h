@@ -68,7 +68,9 @@ typedef enum coast_kernel_id {
                               branch conditions are the sync points, voted inside the loops */
     COAST_K_CHSTONE_SHA = 6, /* tests/chstone/sha/sha.c:93-193: the CHStone `sha` benchmark -- one unit
                                 is one STREAM (a serial chain of unit_bytes/64 + 1 compressions), five u32 votes */
-    COAST_K_COUNT_    = 7
+    COAST_K_CHSTONE_AES = 7, /* tests/chstone/aes/{aes_enc,aes_dec,aes_func,aes_key}.c: CHStone `aes`, type 128128 --
+                                one byte per int; 16 int votes */
+    COAST_K_COUNT_    = 8
 } coast_kernel_id;
 
 /* numClones of dataflowProtection::run: 3 = -TMR, 2 = -DWC, 1 = unprotected
@@ -160,6 +162,9 @@ typedef struct coast_fault_plan {
  *   QSORT    in : n_units x unit_bytes, arrays of L = unit_bytes/4 int32 (L <= 1024)   out: the sorted arrays
  *   CHSTONE_SHA in : n_units x unit_bytes stream bytes (unit_bytes a multiple of 64, 64 <= unit_bytes < 2^29)
  *            out: n_units x 5 uint32 = sha_info_digest[5] (sha.h:38)
+ *   CHSTONE_AES in : n_units x 16 int32 = statemt[0..16) (aes.c:83; one byte per int, only the low 8 bits are used)
+ *            out: n_units x 16 int32;  aux: n_units x 16 int32 keys with COAST_AES_KEY_PER_UNIT, else `key` below;
+ *            mode bit0 = decrypt.  The key is never modified (KeySchedule expands into word[][], aes_key.c:129-163).
  */
 #define COAST_AES_DECRYPT       0x1u
 #define COAST_AES_KEY_PER_UNIT  0x2u
@@ -292,6 +297,10 @@ void coast_xmr_matrix_multiply_u32(const uint32_t* f, const uint32_t* s, uint32_
 /* chstone/sha/sha.c:182-193 sha_stream(): hashes the vsize chunks indata[j][0 .. in_i[j]) (rows block_size bytes apart)
  * into digest[5].  The benchmark's globals are passed in by the generated glue; chunks must be multiples of 64 bytes. */
 void coast_xmr_chstone_sha_stream(const unsigned char* indata, const int* in_i, int vsize, int block_size, uint32_t* digest);
+/* chstone/aes: the cipher of encrypt() (dir 0, aes_enc.c:102-125) / decrypt() (dir 1, aes_dec.c:87-125) on statemt[], in place;
+ * `type` must be 128128 (the benchmark's).  The printf and the main_result self-check of those functions are host effects
+ * the generated glue reproduces. */
+void coast_xmr_chstone_aes(int* statemt, const int* key, int type, int dir);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,7 @@ static uint32_t sha_blocks(uint32_t len) { return (len + 8u) / 64u + 1u; }
 
 uint32_t orc_fault_sites(uint32_t kernel, uint32_t unit_bytes, uint32_t K) {
     switch (kernel) {
+    case ORC_K_CHSTONE_AES: return 176u;
     case ORC_K_CRC16:     return 2u * unit_bytes;
     case ORC_K_SHA256:    return SHA_SITES_PER_BLOCK * sha_blocks(unit_bytes);
     case ORC_K_AES128:    return 16u + 160u;
@@ -72,6 +73,7 @@ uint32_t orc_fault_site_bits(uint32_t kernel, uint32_t unit_bytes, uint32_t K, u
     switch (kernel) {
     case ORC_K_CRC16:  return site < unit_bytes ? 16u : 8u;
     case ORC_K_AES128: return 8u;
+    case ORC_K_CHSTONE_AES: return 8u;         /* statemt[] holds one byte per int (aes.c:83); above bit 7 the S-box index leaves the table */
     default:           return 32u;
     }
 }
@@ -79,7 +81,7 @@ uint32_t orc_fault_site_bits(uint32_t kernel, uint32_t unit_bytes, uint32_t K, u
 uint32_t orc_out_bytes_per_unit(uint32_t kernel) {
     switch (kernel) {
     case ORC_K_CRC16: return 2; case ORC_K_SHA256: return 32; case ORC_K_AES128: return 16;
-    case ORC_K_MM_U32: case ORC_K_GEMM_TF32: return 4; case ORC_K_CHSTONE_SHA: return 20; default: return 0;
+    case ORC_K_MM_U32: case ORC_K_GEMM_TF32: return 4; case ORC_K_CHSTONE_SHA: return 20; case ORC_K_CHSTONE_AES: return 64; default: return 0;
     }
 }
 
@@ -94,7 +96,9 @@ uint32_t orc_out_bytes(uint32_t kernel, uint32_t unit_bytes) {
 uint32_t orc_votes_per_unit(uint32_t kernel) {
     switch (kernel) {
     case ORC_K_CRC16: return 1; case ORC_K_SHA256: return 32; case ORC_K_AES128: return 16;
-    case ORC_K_MM_U32: case ORC_K_GEMM_TF32: return 1; case ORC_K_CHSTONE_SHA: return 5; default: return 0;
+    case ORC_K_MM_U32: case ORC_K_GEMM_TF32: return 1; case ORC_K_CHSTONE_SHA: return 5;
+    case ORC_K_CHSTONE_AES: return 16;                      /* int statemt[i], compared element-wise (aes_enc.c:130-131) */
+    default: return 0;
     }
 }
 
@@ -365,6 +369,99 @@ void orc_aes128(uint8_t s[16], uint8_t key[16], int dir, const orc_fault* f) {
 }
 
 /* ------------------------------------------------------------------ */
+/* CHStone `aes`  tests/chstone/aes/{aes_enc,aes_dec,aes_func,aes_key}.c, type 128128               */
+/* One byte per `int`; the key schedule is expanded once into word[4][44] (KeySchedule aes_key.c:79-165) and the */
+/* key itself is never modified.  encrypt() aes_enc.c:66-134: AddRoundKey(0); 9 x {ByteSub_ShiftRow;            */
+/* MixColumn_AddRoundKey(i)}; ByteSub_ShiftRow; AddRoundKey(10).  decrypt() aes_dec.c:66-140: AddRoundKey(10);   */
+/* InversShiftRow_ByteSub; 9 x {AddRoundKey_InversMixColumn(i); InversShiftRow_ByteSub} for i = 9..1;            */
+/* AddRoundKey(0).  The printf and the `main_result +=` self-check inside both functions are host effects of the */
+/* benchmark, not part of the protected arithmetic.                                                              */
+/* Fault sites: 0..15 = statemt[i] as loaded; 16+16r+i = statemt[i] right after the (r+2)-th round-key addition   */
+/* (encrypt: after MixColumn_AddRoundKey(r+1) / the final AddRoundKey; decrypt: after the first loop of          */
+/* AddRoundKey_InversMixColumn(9-r) aes_func.c:443-449 / the final AddRoundKey(0)).                              */
+/* ------------------------------------------------------------------ */
+static int chs_xt(int v) { v <<= 1; if ((v >> 8) == 1) v ^= 283; return v; }           /* the `x << 1; if ((x >> 8) == 1) x ^= 283` idiom */
+static void chs_key_schedule(const int32_t key[16], int word[4][44]) {                 /* aes_key.c:129-163, nk = nb = 4, 10 rounds */
+    static const int rcon0[10] = { 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80, 0x1b, 0x36 };   /* :64-73 */
+    for (int j = 0; j < 4; ++j) for (int i = 0; i < 4; ++i) word[i][j] = key[i + j * 4];
+    for (int j = 4; j < 44; ++j) {
+        int temp[4];
+        if (j % 4 == 0) {                                                               /* RotByte + SubByte :137-143 */
+            temp[0] = AES_S[word[1][j - 1] & 0xFF] ^ rcon0[j / 4 - 1];
+            temp[1] = AES_S[word[2][j - 1] & 0xFF]; temp[2] = AES_S[word[3][j - 1] & 0xFF]; temp[3] = AES_S[word[0][j - 1] & 0xFF];
+        } else {
+            for (int i = 0; i < 4; ++i) temp[i] = word[i][j - 1];
+        }
+        for (int i = 0; i < 4; ++i) word[i][j] = word[i][j - 4] ^ temp[i];
+    }
+}
+static void chs_add_round_key(int st[16], int word[4][44], int n) {                    /* aes_func.c:537-543 */
+    for (int j = 0; j < 4; ++j) for (int i = 0; i < 4; ++i) st[i + j * 4] ^= word[i][j + 4 * n];
+}
+static void chs_bytesub_shiftrow(int st[16]) {                                         /* aes_func.c:141-165: row r rotates left by r */
+    int t[16];
+    for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r) t[r + 4 * c] = AES_S[st[r + 4 * ((c + r) & 3)] & 0xFF];
+    memcpy(st, t, sizeof t);
+}
+static void chs_inv_shiftrow_bytesub(int st[16]) {                                     /* aes_func.c:261-285 */
+    int t[16];
+    for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r) t[r + 4 * c] = AES_IS[st[r + 4 * ((c - r) & 3)] & 0xFF];
+    memcpy(st, t, sizeof t);
+}
+static void chs_mixcolumn(int st[16]) {                                                /* aes_func.c:375-426 without the key */
+    for (int j = 0; j < 4; ++j) {
+        int a[4], o[4];
+        for (int i = 0; i < 4; ++i) a[i] = st[i + j * 4];
+        for (int i = 0; i < 4; ++i) o[i] = chs_xt(a[i]) ^ (chs_xt(a[(i + 1) & 3]) ^ a[(i + 1) & 3]) ^ a[(i + 2) & 3] ^ a[(i + 3) & 3];
+        for (int i = 0; i < 4; ++i) st[i + j * 4] = o[i];
+    }
+}
+static void chs_inv_mixcolumn(int st[16]) {                                            /* aes_func.c:450-503: (14, 11, 13, 9) */
+    for (int j = 0; j < 4; ++j) {
+        int a[4], o[4];
+        for (int i = 0; i < 4; ++i) a[i] = st[i + j * 4];
+        for (int i = 0; i < 4; ++i) {
+            const int x0 = a[i], x1 = a[(i + 1) & 3], x2 = a[(i + 2) & 3], x3 = a[(i + 3) & 3];
+            const int m14 = chs_xt(chs_xt(chs_xt(x0) ^ x0) ^ x0);                       /* ((2x ^ x) 2 ^ x) 2 */
+            const int m11 = chs_xt(chs_xt(chs_xt(x1)) ^ x1) ^ x1;                       /* ((2x) 2 ^ x) 2 ^ x */
+            const int m13 = chs_xt(chs_xt(chs_xt(x2) ^ x2)) ^ x2;                       /* ((2x ^ x) 2) 2 ^ x */
+            const int m9 = chs_xt(chs_xt(chs_xt(x3))) ^ x3;                             /* 8x ^ x */
+            o[i] = m14 ^ m11 ^ m13 ^ m9;
+        }
+        for (int i = 0; i < 4; ++i) st[i + j * 4] = o[i];
+    }
+}
+void orc_chstone_aes(int32_t statemt[16], const int32_t key[16], int dir, const orc_fault* f) {
+    pthread_once(&aes_once, aes_tables);
+    int word[4][44], st[16];
+    const int has = f && f->active;
+    for (int i = 0; i < 16; ++i) st[i] = statemt[i];
+    if (has && f->site < 16u) st[f->site] ^= (1 << f->bit);                            /* the replica's private copy of the input */
+    chs_key_schedule(key, word);
+    if (!dir) {
+        chs_add_round_key(st, word, 0);                                                 /* aes_enc.c:118 */
+        for (int i = 1; i <= 10; ++i) {
+            chs_bytesub_shiftrow(st);                                                   /* :121 / :124 */
+            if (i < 10) chs_mixcolumn(st);                                              /* :122 MixColumn_AddRoundKey = MixColumn, */
+            chs_add_round_key(st, word, i);                                             /*      then the key (:386-387) / :125 */
+            if (has && f->site >= 16u && (f->site - 16u) / 16u == (uint32_t)(i - 1)) st[(f->site - 16u) % 16u] ^= (1 << f->bit);
+        }
+    } else {
+        chs_add_round_key(st, word, 10);                                                /* aes_dec.c:115 */
+        chs_inv_shiftrow_bytesub(st);                                                   /* :117 */
+        for (int i = 9; i >= 1; --i) {
+            chs_add_round_key(st, word, i);                                             /* :121 first loop of AddRoundKey_InversMixColumn */
+            if (has && f->site >= 16u && (f->site - 16u) / 16u == (uint32_t)(9 - i)) st[(f->site - 16u) % 16u] ^= (1 << f->bit);
+            chs_inv_mixcolumn(st);
+            chs_inv_shiftrow_bytesub(st);                                               /* :122 */
+        }
+        chs_add_round_key(st, word, 0);                                                 /* :125 */
+        if (has && f->site >= 16u && (f->site - 16u) / 16u == 9u) st[(f->site - 16u) % 16u] ^= (1 << f->bit);
+    }
+    for (int i = 0; i < 16; ++i) statemt[i] = st[i];
+}
+
+/* ------------------------------------------------------------------ */
 /* a7: matrix_multiply()  tests/mm_common/mm_common_tmr.c:3-20,          */
 /*     tests/matrixMultiply/matrixMultiply.c:95-112                      */
 /* `sum` is an unsigned long truncated to mm_t/unsigned on store (:16 /  */
@@ -525,6 +622,14 @@ static void run_replica(const orc_desc* d, uint64_t local, const orc_fault* f, u
         orc_chstone_sha((const uint8_t*)d->in + local * d->unit_bytes, d->unit_bytes, dg, f);
         memcpy(out, dg, 20);
     } break;
+    case ORC_K_CHSTONE_AES: {
+        int32_t st[16], key[16];
+        memcpy(st, (const uint8_t*)d->in + local * 64, 64);
+        if (d->mode & ORC_AES_KEY_PER_UNIT) memcpy(key, (const uint8_t*)d->aux + local * 64, 64);
+        else for (int i = 0; i < 16; ++i) key[i] = d->key[i];
+        orc_chstone_aes(st, key, (d->mode & ORC_AES_DECRYPT) ? 1 : 0, f);
+        memcpy(out, st, 64);
+    } break;
     default: break;
     }
 }
@@ -611,7 +716,7 @@ static void sv_run_range(const orc_desc* d, uint64_t u0, uint64_t u1, orc_stats*
 }
 
 int orc_run_range(const orc_desc* d, uint64_t u0, uint64_t u1, orc_stats* st) {
-    if (!d || d->num_clones < 1 || d->num_clones > 3 || d->kernel > ORC_K_CHSTONE_SHA) return -1;
+    if (!d || d->num_clones < 1 || d->num_clones > 3 || d->kernel >= ORC_K_COUNT_) return -1;
     if (d->kernel == ORC_K_CHSTONE_SHA && (d->unit_bytes < 64u || (d->unit_bytes & 63u) || d->unit_bytes >= (1u << 29))) return -1;
     if (d->kernel == ORC_K_QSORT) {
         const uint32_t L = d->unit_bytes / 4u, nc = d->num_clones;
@@ -656,7 +761,7 @@ int orc_run_range(const orc_desc* d, uint64_t u0, uint64_t u1, orc_stats* st) {
         orc_fault f;
         orc_fault_for_unit(d->plan, d->kernel, nc, d->unit_bytes, d->K, d->unit_base + local, local, &f);
         if (f.active) st->injected++;
-        uint8_t rep[3][32];
+        uint8_t rep[3][64];
         for (uint32_t r = 0; r < nc; ++r) run_replica(d, local, (f.active && f.replica == r) ? &f : &none, rep[r]);
         uint8_t* out = (uint8_t*)d->out + local * ob;
         int disagree = 0;

@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 enum { ORC_K_CRC16 = 0, ORC_K_SHA256 = 1, ORC_K_AES128 = 2, ORC_K_MM_U32 = 3, ORC_K_GEMM_TF32 = 4, ORC_K_QSORT = 5,
-       ORC_K_CHSTONE_SHA = 6 };
+       ORC_K_CHSTONE_SHA = 6, ORC_K_CHSTONE_AES = 7, ORC_K_COUNT_ = 8 };
 enum { ORC_F_COUNT_ERRORS = 1, ORC_F_COUNT_SYNCS = 2, ORC_F_NO_MEM_REPLICATION = 4, ORC_F_MAJORITY = 0x100,
        ORC_F_STORE_DATA_SYNC = 0x200, ORC_F_NO_STORE_DATA_SYNC = 0x400, ORC_F_NO_LOAD_SYNC = 0x800, ORC_F_NO_STORE_ADDR_SYNC = 0x1000 };
 /* In-loop store votes (rule C4): -storeDataSync forces them, -noMemReplication needs them (one memory copy: stores are voted,
@@ -79,6 +79,7 @@ uint16_t orc_crc16(const uint8_t* data, uint32_t len, const orc_fault* f);
 void     orc_sha256(const uint8_t* data, uint32_t len, uint8_t digest[32], const orc_fault* f);
 void     orc_aes128(uint8_t state[16], uint8_t key[16], int dir, const orc_fault* f);
 void     orc_chstone_sha(const uint8_t* data, uint32_t len, uint32_t digest[5], const orc_fault* f);   /* len % 64 == 0 */
+void     orc_chstone_aes(int32_t statemt[16], const int32_t key[16], int dir, const orc_fault* f);     /* type 128128 */
 uint32_t orc_mm_u32_elem(const uint32_t* A, const uint32_t* B, uint32_t K, uint32_t N, uint32_t i, uint32_t j,
                          const orc_fault* f);
 float    orc_gemm_tf32_elem(const float* A, const float* B, uint32_t K, uint32_t N, uint32_t i, uint32_t j,

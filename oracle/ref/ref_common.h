@@ -44,8 +44,8 @@
  * C type the reference stores; `nv` = elements per unit. */
 typedef struct ref_stats { uint64_t errors_corrected, dwc_detected, syncs, injected, first_fault_unit; } ref_stats;
 
-static inline void ref_vote(uint8_t rep[3][32], uint32_t nc, uint32_t es, uint32_t nv, int count_errors,
-                            int count_syncs, uint64_t unit, uint8_t* out, ref_stats* st) {
+static inline void ref_vote_n(const uint8_t* const rep[3], uint32_t nc, uint32_t es, uint32_t nv, int count_errors,
+                              int count_syncs, uint64_t unit, uint8_t* out, ref_stats* st) {
     int disagree = 0;
     if (nc == 1) { memcpy(out, rep[0], (size_t)es * nv); return; }
     if (nc == 2) {
@@ -61,6 +61,11 @@ static inline void ref_vote(uint8_t rep[3][32], uint32_t nc, uint32_t es, uint32
         if (count_errors && count_syncs) st->syncs += nv;
     }
     if (disagree && unit < st->first_fault_unit) st->first_fault_unit = unit;
+}
+static inline void ref_vote(uint8_t rep[3][32], uint32_t nc, uint32_t es, uint32_t nv, int count_errors,
+                            int count_syncs, uint64_t unit, uint8_t* out, ref_stats* st) {
+    const uint8_t* const p[3] = { rep[0], rep[1], rep[2] };
+    ref_vote_n(p, nc, es, nv, count_errors, count_syncs, unit, out, st);
 }
 
 /* A fault in ONE replica's private copy of its input (memory replication, rule D1,

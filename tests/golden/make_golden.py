@@ -15,6 +15,8 @@ Contents
   aes     : the 568 NIST AESAVS records of tests/aes/ECB*.h (80 bytes each: key|key2|cipher|plain|input),
             and what aes_enc_dec() leaves in state[] and key[] for each direction
   mm      : mm_tmr.c 9x9 uint32 operands, results_matrix, xor_golden; matrixMultiply.c int operands/results
+  chaes   : tests/chstone/aes: the benchmark's FIPS-197 vector through the reference's own encrypt()/decrypt(), 40 random
+            (block, key) pairs both directions, DWC/TMR runs of the reference functions with a flipped input byte in one replica
   chsha   : tests/chstone/sha: the golden outData of sha_driver.c (the 16 KiB indata itself is NOT copied: only its
             SHA-256, the GPU test reads the bytes from oracle/_ref/libref_chsha.so), reference digests of Philox
             streams of several lengths, and TMR/DWC runs with input flips
@@ -267,6 +269,51 @@ def main():
         rq.ref_quick_sort(b_.ctypes.data, ln)
         qs["random"].append({"input": [int(v) for v in a_], "sorted": [int(v) for v in b_]})
     g["qsort"] = qs
+
+    # ---------------------------------------------------------------- chstone aes (tests/chstone/aes), appended last
+    ra = po.ref("chaes")
+    ra.ref_chaes.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    assert ra.ref_chaes_run_main() == 0                      # the benchmark as shipped prints RESULT: PASS
+    st_ = np.zeros(32, dtype=np.int32); k_ = np.zeros(32, dtype=np.int32)
+    st_[:16] = [50, 67, 246, 168, 136, 90, 48, 141, 49, 49, 152, 162, 224, 55, 7, 52]         # aes.c:93-108 = FIPS-197 Appendix B
+    k_[:16] = [43, 126, 21, 22, 40, 174, 210, 166, 171, 247, 21, 136, 9, 207, 79, 60]         # aes.c:110-125
+    ca = {"kat_plain": [int(v) for v in st_[:16]], "kat_key": [int(v) for v in k_[:16]], "random": []}
+    assert ra.ref_chaes(st_.ctypes.data, k_.ctypes.data, 0) == 0                              # encrypt(): main_result unchanged
+    ca["kat_cipher"] = [int(v) for v in st_[:16]]
+    assert ra.ref_chaes(st_.ctypes.data, k_.ctypes.data, 1) == 0 and [int(v) for v in st_[:16]] == ca["kat_plain"]
+    assert [int(v) for v in k_[:16]] == ca["kat_key"]        # the key is never modified
+    for _ in range(40):
+        blk = rng.integers(0, 256, 16, dtype=np.int64).astype(np.int32); key = rng.integers(0, 256, 16, dtype=np.int64).astype(np.int32)
+        rec = {"block": [int(v) for v in blk], "key": [int(v) for v in key]}
+        for d_, nm in ((0, "enc"), (1, "dec")):
+            a_ = np.zeros(32, dtype=np.int32); kk = np.zeros(32, dtype=np.int32)
+            a_[:16] = blk; kk[:16] = key
+            ra.ref_chaes(a_.ctypes.data, kk.ctypes.data, d_)
+            rec[nm] = [int(v) for v in a_[:16]]
+        ca["random"].append(rec)
+    n = 12
+    blocks = rng.integers(0, 256, 16 * n, dtype=np.int64).astype(np.int32)
+    keys = rng.integers(0, 256, 16 * n, dtype=np.int64).astype(np.int32)
+    plan = []
+    faults = (po.RefFault * n)()
+    for u in range(n):
+        if u % 4 == 3:
+            faults[u] = po.RefFault(0, -1, 0); plan.append(None)
+        else:
+            r_, by, bi = int(rng.integers(0, 3)), int(rng.integers(0, 16)), int(rng.integers(0, 8))
+            faults[u] = po.RefFault(r_, by, bi); plan.append([r_, by, bi])
+    ra.ref_chaes_xmr.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int,
+                                 C.c_void_p, C.POINTER(po.RefStats)]
+    ca.update({"xmr_n": n, "xmr_blocks": [int(v) for v in blocks], "xmr_keys": [int(v) for v in keys], "xmr_faults": plan, "xmr_runs": {}})
+    for d_ in (0, 1):
+        for nc in (3, 2):
+            fl = (po.RefFault * n)(*[po.RefFault(f.replica, f.byte if f.replica < nc else -1, f.bit) for f in faults])
+            out = np.zeros(16 * n, dtype=np.int32)
+            st = po.RefStats()
+            st.first_fault_unit = po.NO_FAULT_UNIT
+            ra.ref_chaes_xmr(blocks.ctypes.data, out.ctypes.data, n, keys.ctypes.data, 1, d_, nc, 1, 1, fl, C.byref(st))
+            ca["xmr_runs"][f"{d_}_{nc}"] = {"out": [int(x) for x in out], "stats": st.as_dict()}
+    g["chaes"] = ca
 
     path = os.path.join(ROOT, "tests", "golden", "coast_golden.json")
     with open(path, "w") as f:

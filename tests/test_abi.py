@@ -47,7 +47,8 @@ def test_every_kernel_the_host_code_can_name_is_in_the_cubin(built_lib):
     import subprocess
     src = open(os.path.join(ROOT, "coast_b200", "csrc", "coast_rt.c")).read()
     fmts = set(re.findall(r'"(xmr_[A-Za-z0-9_%]+)"', src))
-    stems = {"xmr_qsort", "xmr_qsortn", "xmr_aes128_enc", "xmr_aes128_dec", "xmr_aes128_enck", "xmr_aes128_deck"}   # stems of a "%s_nc%u_inj%d"
+    stems = {"xmr_qsort", "xmr_qsortn", "xmr_aes128_enc", "xmr_aes128_dec", "xmr_aes128_enck", "xmr_aes128_deck",
+             "xmr_chaes_enc", "xmr_chaes_dec"}               # stems of a "%s_nc%u_inj%d"
     assert stems <= fmts
     fmts = (fmts - stems) | {s + "_nc%u_inj%d" for s in stems}
     names = set()

@@ -13,7 +13,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
-from build_reference_tests import CASES, OUT, REF, make_cmd  # noqa: E402  (the list the driver's build() uses too)
+from build_reference_tests import CASES, OUT, REF, exe_path, make_cmd  # noqa: E402  (the list the driver's build() uses too)
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout absent (GPU box)")
@@ -21,13 +21,14 @@ from build_reference_tests import CASES, OUT, REF, make_cmd  # noqa: E402  (the 
 def test_unchanged_reference_tests_build_against_the_runtime(built_lib, tdir, target, extra, entry, _re, _rc):
     res = subprocess.run(make_cmd(tdir, extra, rebuild=True), capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
-    exe = os.path.join(OUT, target, target + ".out")
+    exe = exe_path(target, extra)
     assert os.path.exists(exe)
-    asm = "".join(open(os.path.join(OUT, target, f)).read() for f in os.listdir(os.path.join(OUT, target)) if f.endswith(".xmr.s"))
+    odir = os.path.dirname(exe)
+    asm = "".join(open(os.path.join(odir, f)).read() for f in os.listdir(odir) if f.endswith(".xmr.s"))
     assert re.search(r"call\s+" + entry + r"@PLT", asm), "the pass did not redirect the protected-region call"
     needed = subprocess.run(["readelf", "-d", exe], capture_output=True, text=True).stdout
     assert "libcoast_rt.so" in needed
-    glue = open(os.path.join(OUT, target, "coast_glue.c")).read()
+    glue = open(os.path.join(odir, "coast_glue.c")).read()
     assert "coast_set_opt_passes" in glue
 
 
@@ -55,7 +56,7 @@ def test_coast_h_has_the_full_macro_surface():
 @pytest.mark.gpu
 @pytest.mark.parametrize("tdir,target,extra,entry,regex,rc", CASES)
 def test_unchanged_reference_tests_run_on_the_gpu(tdir, target, extra, entry, regex, rc):
-    exe = os.path.join(OUT, target, target + ".out")
+    exe = exe_path(target, extra)
     if not os.path.exists(exe):
         pytest.skip("binary was not built on the CPU box (needs the reference checkout)")
     res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
