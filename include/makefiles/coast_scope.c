@@ -175,7 +175,7 @@ static int scan(FILE* f) {
 
 /* ------------------------------------------------------------------ plan */
 #define MAX_N 2048
-typedef struct { char name[128]; int explicit_xmr, explicit_no, defined; } fn_rec;
+typedef struct { char name[128]; int explicit_xmr, explicit_no, defined, ret_val, call_once, isr; } fn_rec;
 static fn_rec fns[MAX_N]; static int n_fns;
 static struct { char a[128], b[128]; } calls[8 * MAX_N]; static int n_calls;
 static struct { char fn[128], sym[128]; char sub[32][64]; int n_sub; } entries[64]; static int n_entries;
@@ -238,6 +238,9 @@ int main(int argc, char** argv) {
                 fn_rec* r = fn_get(b);
                 if (!strcmp(c, "xMR") || !strcmp(c, "protected_lib")) { r->explicit_xmr = 1; r->explicit_no = 0; }   /* interface.cpp:389-391, 467-471 */
                 else if (!strcmp(c, "no_xMR")) { r->explicit_no = 1; r->explicit_xmr = 0; }                           /* :383-388 */
+                else if (!strcmp(c, "repl_return_val")) r->ret_val = 1;                                               /* :464-466 */
+                else if (!strcmp(c, "coast_call_once")) r->call_once = 1;                                             /* :396-399 */
+                else if (!strcmp(c, "isr_function")) { r->isr = 1; r->explicit_no = 1; r->explicit_xmr = 0; }         /* :461-463: never cloned */
             }
             else if (n >= 2 && !strcmp(a, "def")) fn_get(b)->defined = 1;
             else if (n >= 3 && !strcmp(a, "call") && n_calls < 8 * MAX_N) {
@@ -268,6 +271,9 @@ int main(int argc, char** argv) {
         if (!r->defined) continue;
         const int e = entry_of(r->name), s = subsumed_by(r->name);
         const char* why = r->explicit_xmr ? "__xMR" : r->explicit_no ? "__NO_xMR" : xmr_default ? "default scope" : "outside the default scope";
+        if (r->ret_val && (e >= 0 || verbose))
+            printf("  COAST   ret-val   %s: __xMR_RET_VAL -- a kernel votes EVERY element it returns, field by field with the field's own width "
+                   "(synchronization.cpp:816-913), so a replicated return value is what the runtime entry already delivers\n", r->name);
         if (e >= 0) {
             if (in_sor[i]) {
                 /* `call crc16` / `jmp crc16` (with or without @PLT) -> the runtime entry */
