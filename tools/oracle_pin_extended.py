@@ -98,14 +98,28 @@ def main():
         n += 1
     rows.append(("quick_sort() (quicksort.c)", "random arrays of 1..1024 ints, a third with many duplicates, under the TMR wrapper", n))
 
+    # chstone aes: random blocks and keys through the reference's encrypt()/decrypt() (one byte per int, key never modified)
+    rc_ = po.ref("chaes"); rc_.ref_chaes.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    n = 0
+    for _ in range(20000):
+        blk = rng.integers(0, 256, 16, dtype=np.int64).astype(np.int32); key = rng.integers(0, 256, 16, dtype=np.int64).astype(np.int32)
+        for direction in (0, 1):
+            a_ = np.zeros(32, dtype=np.int32); k_ = np.zeros(32, dtype=np.int32)
+            a_[:16] = blk; k_[:16] = key
+            rc_.ref_chaes(a_.ctypes.data, k_.ctypes.data, direction)
+            out, _ = po.run(po.K_CHSTONE_AES, 1, blk, 1, mode=2 | direction, aux=key)
+            assert list(out.view(np.int32)) == [int(v) for v in a_[:16]] and (k_[:16] == key).all()
+            n += 1
+    rows.append(("chstone encrypt()/decrypt() (aes_enc.c, aes_dec.c)", "random block and key, both directions", n))
+
     dt = time.time() - t0
-    lines = ["# Extended oracle pin (r01) -- `python tools/oracle_pin_extended.py`", "",
+    lines = ["# Extended oracle pin (r02) -- `python tools/oracle_pin_extended.py`", "",
              "Randomized differential run of `oracle/coast_oracle.c` against the reference's own functions compiled in place",
              f"(`oracle/_ref`, byuccl/coast @ 397a26e), on the CPU box; {dt:.0f} s, seed 2026.  Zero mismatches.", "",
              "| reference function | inputs | cases |", "|---|---|---|"]
     lines += [f"| `{a}` | {b} | {c} |" for a, b, c in rows]
     text = "\n".join(lines) + "\n"
-    with open(os.path.join(ROOT, "profiles", "r01_oracle_pin_extended.md"), "w") as f:
+    with open(os.path.join(ROOT, "profiles", "r02_oracle_pin_extended.md"), "w") as f:
         f.write(text)
     print(text)
 
