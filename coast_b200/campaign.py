@@ -25,7 +25,7 @@ import numpy as np
 from . import runtime as R
 
 WORKLOADS = {"crc16": R.K_CRC16, "sha256": R.K_SHA256, "aes": R.K_AES128, "mm": R.K_MM_U32, "qsort": R.K_QSORT,
-             "chsha": R.K_CHSTONE_SHA}
+             "chsha": R.K_CHSTONE_SHA, "chaes": R.K_CHSTONE_AES}
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -57,7 +57,7 @@ def plan_faults(kernel, num_clones, unit_bytes, K, n_units, seed, threshold, uni
     site = x2 % np.uint32(ns)
     if kernel == R.K_CRC16:
         width = np.where(site < unit_bytes, 16, 8).astype(np.uint32)
-    elif kernel == R.K_AES128:
+    elif kernel in (R.K_AES128, R.K_CHSTONE_AES):
         width = np.full(n_units, 8, dtype=np.uint32)
     else:
         width = np.full(n_units, 32, dtype=np.uint32)
@@ -78,6 +78,8 @@ def site_name(kernel, unit_bytes, site):
         return f"sha256.blk{blk}.ctx_state[{s - 528}]"
     if kernel == R.K_AES128:
         return f"aes.state_in[{site}]" if site < 16 else f"aes.round{(site - 16) // 16}.state[{(site - 16) % 16}]"
+    if kernel == R.K_CHSTONE_AES:
+        return f"chaes.statemt_in[{site}]" if site < 16 else f"chaes.keyadd{(site - 16) // 16 + 1}.statemt[{(site - 16) % 16}]"
     if kernel == R.K_MM_U32:
         return f"mm.sum@k{site}"
     if kernel == R.K_QSORT:
@@ -166,11 +168,14 @@ def run_campaign(rt, workload: str, opt_passes: str, n_injections: int, seed: in
         inp, kw = A, dict(M=side, N=side, K=side, aux=B)
         ub = 0
     else:
-        ub = {R.K_CRC16: 64, R.K_SHA256: 64, R.K_AES128: 16, R.K_QSORT: 4 * 580, R.K_CHSTONE_SHA: 1024}[kernel] if unit_bytes is None else unit_bytes
+        ub = {R.K_CRC16: 64, R.K_SHA256: 64, R.K_AES128: 16, R.K_QSORT: 4 * 580, R.K_CHSTONE_SHA: 1024, R.K_CHSTONE_AES: 64}[kernel] if unit_bytes is None else unit_bytes
         nbytes = (n * ub + 3) // 4 * 4
         inp = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         rt.fill_philox(inp, data_seed)
-        if kernel == R.K_AES128:
+        if kernel == R.K_CHSTONE_AES:                          # one byte per int (aes.c:83)
+            inp = (inp.view(torch.int32) & 0xFF).view(torch.uint8)
+            kw = dict(key=bytes(range(16)))
+        elif kernel == R.K_AES128:
             kw = dict(key=bytes(16))
         else:
             kw = dict(unit_bytes=ub)
@@ -192,7 +197,7 @@ def run_campaign(rt, workload: str, opt_passes: str, n_injections: int, seed: in
     records = []
     for u in range(n_injections):
         name = site_name(kernel, ub, site[u])
-        section = "memory" if (".data[" in name or ".m[" in name or ".W[" in name or "state_in" in name or ".array[" in name) else "registers"
+        section = "memory" if (".data[" in name or ".m[" in name or ".W[" in name or "state_in" in name or "statemt_in" in name or ".array[" in name) else "registers"
         if nc == 2 and stat[u]:
             res = abort_result("FAULT_DETECTED_DWC")
             summ.detected += 1
