@@ -728,7 +728,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="headline workload only (skip the other BASELINE configs)")
-    ap.add_argument("--host-path", choices=["staged", "zerocopy"], default=None, help="force the host-call path of the e2e measurement")
+    ap.add_argument("--host-path", choices=["staged", "hybrid", "zerocopy", "one-shot"], default=None, help="force the host-call path of the e2e measurement")
     ap.add_argument("--ref-budget-s", type=float, default=90.0, help="--impl reference: CPU seconds the whole run may take")
     ap.add_argument("--threads", type=int, default=0, help="--impl reference: host threads (default: all; config 1 is 1 thread)")
     ap.add_argument("--workload", choices=["sha256", "sha256_2p30", "aes", "crc16", "gemm"], default="sha256",

@@ -272,19 +272,25 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
 #pragma unroll
         for (int j = 0; j < J; ++j) { fbit[j] = 0u; frd[j] = -2; fcol[j] = 0; }
         if (INJECT) {
-            uint32_t packed[J];
+            // The unit's Philox draw is evaluated ONCE, by one lane, with every lane of the warp busy in the same instruction:
+            // in pass t, replica lane r evaluates block j = t * NC + r of its unit (different lanes, different blocks -- no
+            // divergence), so a warp spends ceil(J / NC) evaluations per lane instead of J (r02 call 2: the per-j `if (r == j % NC)`
+            // form diverged and cost all J; r01 evaluated every block on every replica lane).
+            constexpr int PASSES = (J + NC - 1) / NC;
+            uint32_t packed[PASSES];
 #pragma unroll
-            for (int j = 0; j < J; ++j) {                       // the unit's Philox draw: evaluated by replica lane j % NC, shuffled to the others
-                packed[j] = 0u;
-                if (r == j % NC) {
-                    Fault f = fault_for_unit(a, NC, valid[j] ? local[j] : 0ull, [](uint32_t) { return 8u; });
-                    if (f.active && valid[j]) packed[j] = 0x80000000u | (f.replica << 29) | (f.site << 5) | f.bit;
-                }
+            for (int t = 0; t < PASSES; ++t) {
+                const int jt = t * NC + r;                       // this lane's block in pass t
+                const bool mine = jt < J;
+                const unsigned long long lo = (unsigned long long)tile * TROWS + (unsigned)((warp * J + (mine ? jt : 0)) * UPW + u);
+                const bool ok = mine && lo < a.n_units;
+                Fault f = fault_for_unit(a, NC, ok ? lo : 0ull, [](uint32_t) { return 8u; });
+                packed[t] = (f.active && ok) ? (0x80000000u | (f.replica << 29) | (f.site << 5) | f.bit) : 0u;
             }
             bool mid = false;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                const uint32_t e = NC == 1 ? packed[j] : __shfl_sync(0xFFFFFFFFu, packed[j], u * NC + j % NC);
+                const uint32_t e = NC == 1 ? packed[j] : __shfl_sync(0xFFFFFFFFu, packed[j / NC], u * NC + j % NC);
                 if (e & 0x80000000u) {
                     if (Lanes<NC>::voter(lane)) tally.injected++;
                     if ((int)((e >> 29) & 3u) == r) {

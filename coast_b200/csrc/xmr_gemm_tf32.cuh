@@ -23,9 +23,9 @@
 // r02: an SS-mode kind::tf32 MMA of 128 x 128 x 8 reads 8 KiB of operands from shared memory for 64 tensor-pipe cycles =
 // 128 B/clk, exactly the SM's shared-memory bandwidth -- the r01 kernels were shared-memory-read bound (ncu: tensor pipe
 // 70 % unprotected).  Two remedies, chosen per replica count (Geom<NC>):
-//   NC >= 2 : the A tile of a stage is copied ONCE from shared memory into TMEM (tcgen05.cp, 4 x 128x256b) and the NC
-//             replica MMAs of every k-step read A from TMEM (TS mode); shared-memory reads drop from 128 to 85 (TMR) /
-//             96 (DWC) B/clk.  Tile 128 x 128, NC accumulators + 32 columns of staged A.
+//   NC >= 2 : (tried) the A tile of a stage copied ONCE from shared memory into TMEM (tcgen05.cp, 4 x 128x256b) with the NC
+//             replica MMAs of every k-step reading A from TMEM (TS mode): shared-memory reads drop from 128 to 85 (TMR) /
+//             96 (DWC) B/clk -- and the time does not move (Geom::ATMEM), so these kernels are tensor-pipe bound.
 //   NC == 1 : tile 128 x 256 (MMA N = 256: 12 KiB per 128 cycles = 96 B/clk) with TWO accumulator buffers, so the epilogue
 //             of tile i overlaps the main loop of tile i+1.
 #pragma once
@@ -42,7 +42,10 @@ template <int NC, bool WIDE = (NC == 1)> struct Geom {         // WIDE: 128 x 25
     static constexpr int BN = WIDE ? 256 : 128;
     static constexpr int STAGES = WIDE ? 4 : 6;
     static constexpr int ACC_BUFS = NC == 1 ? 2 : 1;             // accumulator sets (double-buffered when TMEM allows)
-    static constexpr bool ATMEM = NC > 1;                         // stage A in TMEM, MMAs in TS mode
+    // Staging A in TMEM (tcgen05.cp + TS-mode MMAs) is built and bit-identical, but measured no faster on the B200 (r02 call 2,
+    // 4096^3: TMR 0.498 ms vs 0.495 ms with shared-memory operands; DWC 0.354 ms): the replicated MMAs are bound by the tensor
+    // pipe itself (830 TF/s issued = 96 % of the measured cuBLAS-derived TF32 peak), not by shared-memory reads.  Off.
+    static constexpr bool ATMEM = false;
     static constexpr uint32_t B_STAGE = BK * BN * 4;              // laid out [BN/32 chunks][BK rows][128 B]
     static constexpr uint32_t ACC_COLS = (uint32_t)NC * BN * ACC_BUFS;
     static constexpr uint32_t A_COLS = ATMEM ? BK : 0;            // one tf32 per 32-bit column
