@@ -491,6 +491,7 @@ static int launch_gemm_tf32(const coast_launch_desc* d, xmr_args* a, int inj, CU
     const unsigned bn = wide ? 256u : 128u, stages = wide ? 4u : 6u;
     const unsigned GEMM_SMEM = stages * (16384u + 32u * bn * 4u) + 1024u + 256u;
     { const char* g = getenv("COAST_GEMM_GROUP_M"); if (g && atoi(g) > 0 && atoi(g) < 256) a->mode = (a->mode & ~0xFFu) | (unsigned)atoi(g); }
+    { const char* h = getenv("COAST_GEMM_L2_HINTS"); if (h && strcmp(h, "0")) a->mode |= 0x100u; }     /* experiment knob, xmr_gemm_tf32.cuh */
     CUfunction fn; int occ = 1;
     int rc = get_fn(name, GEMM_SMEM, &fn, &occ); if (rc) return rc;
     CUtensorMap ma, mb;

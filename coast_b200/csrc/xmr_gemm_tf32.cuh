@@ -74,6 +74,23 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// L2 eviction-priority hints (r02 experiment, xmr_args.mode bit 8): with one 32-tile-row group the whole of A (64 MiB at 4096^3)
+// should stay in the 126 MB L2 while B streams through and C is written once -- A loads evict_last, B loads and C stores evict_first.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t l2_policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_v4_hint(void* p, uint4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -146,6 +163,7 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles_n = a.N / BN, tiles_m = a.M / BM, n_tiles = tiles_m * tiles_n, kblocks = a.K / BK;
     const uint32_t group_m = (a.mode & 0xFFu) ? (a.mode & 0xFFu) : GROUP_M_DEFAULT;
+    const bool hints = (a.mode & 0x100u) != 0;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(map_a); tma_prefetch_desc(map_b);
@@ -166,6 +184,7 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
         uint32_t it = 0;
+        const uint64_t pol_a = l2_policy_evict_last(), pol_b = l2_policy_evict_first();
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             uint32_t tm, tn;
             tile_coords(tile, tiles_m, tiles_n, group_m, tm, tn);
@@ -174,8 +193,13 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&full[s], A_STAGE + B_STAGE);
-                tma_load_2d(sA + s * A_STAGE, map_a, &full[s], (int)(kb * BK), m0);              // box {32 k, 128 m}
-                tma_load_3d(sB + s * B_STAGE, map_b, &full[s], 0, (int)(kb * BK), n0 / 32);      // box {32 n, 32 k, BN/32 chunks}
+                if (hints) {
+                    tma_load_2d_hint(sA + s * A_STAGE, map_a, &full[s], (int)(kb * BK), m0, pol_a);
+                    tma_load_3d_hint(sB + s * B_STAGE, map_b, &full[s], 0, (int)(kb * BK), n0 / 32, pol_b);
+                } else {
+                    tma_load_2d(sA + s * A_STAGE, map_a, &full[s], (int)(kb * BK), m0);              // box {32 k, 128 m}
+                    tma_load_3d(sB + s * B_STAGE, map_b, &full[s], 0, (int)(kb * BK), n0 / 32);      // box {32 n, 32 k, BN/32 chunks}
+                }
             }
         }
     } else if (warp == 1) {
@@ -226,6 +250,7 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
         const uint32_t flags = a.flags;
         const bool majority = flags & COAST_F_MAJORITY_D;
         float* C = static_cast<float*>(a.out);
+        const uint64_t pol_c = l2_policy_evict_first();
         Tally tally(a);
         uint32_t tcount = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
@@ -270,7 +295,8 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
                         o[e] = vote;
                         tally.unit_exit<NC>(bad, 1u, flags, a.unit_base + local0 + j + e);
                     }
-                    *reinterpret_cast<uint4*>(dst + j) = make_uint4(o[0], o[1], o[2], o[3]);
+                    if (hints) st_v4_hint(dst + j, make_uint4(o[0], o[1], o[2], o[3]), pol_c);
+                    else *reinterpret_cast<uint4*>(dst + j) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
             }
             tc_fence_before();

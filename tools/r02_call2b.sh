@@ -31,6 +31,16 @@ prof aes_enc_nc2_inj0 xmr_aes128_enc_nc2_inj0 --kernel aes --nc 2 --log2n 24 --i
 prof aes_dec_nc2_inj0 xmr_aes128_dec_nc2_inj0 --kernel aes --nc 2 --log2n 24 --iters 2 --aes-mode 1
 prof gemm_nc3 xmr_gemm_tf32_nc3_inj0 --kernel gemm --nc 3 --side 4096 --iters 2
 prof gemm_nc1 xmr_gemm_tf32_nc1_inj0 --kernel gemm --nc 1 --side 4096 --iters 2
+{
+for cfg in "16 0" "32 0" "16 1" "32 1"; do
+  set -- $cfg
+  echo "== GROUP_M=$1 L2_HINTS=$2"
+  COAST_GEMM_GROUP_M=$1 COAST_GEMM_L2_HINTS=$2 python tools/profile_target.py --kernel gemm --nc 3 --side 4096 --iters 20 --time
+  COAST_GEMM_GROUP_M=$1 COAST_GEMM_L2_HINTS=$2 timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+      -k regex:xmr_gemm_tf32_nc3_inj0 -c 1 --csv python tools/profile_target.py --kernel gemm --nc 3 --side 4096 --iters 2 2>/dev/null | grep -E "dram__bytes|gpu__time" | cut -d, -f10- 
+done
+} > "$out/gemm_l2_sweep.txt" 2>&1
+cat "$out/gemm_l2_sweep.txt"
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/r02c2b/bench_*.json')):
