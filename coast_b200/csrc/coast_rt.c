@@ -376,7 +376,7 @@ int coast_parse_opt_passes(const char* s, uint32_t* num_clones, uint32_t* flags)
 static int store_votes_wanted(uint32_t fl) {
     return (fl & (COAST_F_STORE_DATA_SYNC | COAST_F_NO_MEM_REPLICATION)) && !(fl & COAST_F_NO_STORE_DATA_SYNC);
 }
-static int store_votes_built(uint32_t kernel) { return kernel == COAST_K_CRC16 || kernel == COAST_K_MM_U32; }
+static int store_votes_built(uint32_t kernel) { return kernel == COAST_K_CRC16 || kernel == COAST_K_MM_U32 || kernel == COAST_K_SHA256; }
 
 uint32_t coast_flags_honoured(uint32_t kernel, uint32_t nc, uint32_t fl) {
     uint32_t h = fl & (COAST_F_COUNT_ERRORS | COAST_F_COUNT_SYNCS | COAST_F_VERBOSE | COAST_F_MAJORITY_VOTER);
@@ -627,7 +627,7 @@ static int launch_impl(const coast_launch_desc* d, void* stream) {
     const int aligned16 = (((uintptr_t)d->d_in) & 15u) == 0;
     switch (d->kernel) {
     case COAST_K_SHA256:
-        if (d->unit_bytes == 64 && aligned16 && d->n_units < 0x7FFFFF00ull) {
+        if (d->unit_bytes == 64 && aligned16 && d->n_units < 0x7FFFFF00ull && !store_votes) {
             tma = 1; tile_rows = XMR_WARPS * upw; row_bytes = 64; swz = CU_TENSOR_MAP_SWIZZLE_64B;
             smem = ring_smem(tile_rows, row_bytes);
             snprintf(name, sizeof name, "xmr_sha256_b64_nc%u_inj%d", nc, inj);

@@ -136,6 +136,22 @@ __device__ __forceinline__ uint32_t store_vote(uint32_t& x, int lane, bool major
     return (c01 && c02) ? 0u : 1u;
 }
 
+// Same for a register that packs up to four u8 elements in its TOP `nb` bytes (a big-endian-packed message word): one vote per
+// byte, returns the number of disagreeing bytes among those nb.
+template <int NC>
+__device__ __forceinline__ uint32_t store_vote_bytes(uint32_t& x, uint32_t nb, int lane, bool majority) {
+    if (NC == 1 || nb == 0u) return 0u;
+    const uint32_t live = 0xFFFFFFFFu << (8u * (4u - nb));
+    const int base = Lanes<NC>::unit(lane) * NC;
+    const uint32_t r0 = __shfl_sync(0xFFFFFFFFu, x, base), r1 = __shfl_sync(0xFFFFFFFFu, x, base + 1);
+    const uint32_t e01 = __vcmpeq4(r0, r1);
+    if (NC == 2) return __popc(~e01 & live) >> 3;
+    const uint32_t r2 = __shfl_sync(0xFFFFFFFFu, x, base + 2);
+    const uint32_t e02 = __vcmpeq4(r0, r2);
+    x = majority ? ((r0 & r1) | (r0 & r2) | (r1 & r2)) : ((r0 & e01) | (r2 & ~e01));
+    return __popc(~(e01 & e02) & live) >> 3;
+}
+
 // ---------------------------------------------------------------- per-thread tallies -> counters
 struct Tally {
     uint32_t errors = 0, dwc = 0, syncs = 0, injected = 0;

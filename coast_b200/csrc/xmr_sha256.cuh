@@ -75,6 +75,61 @@ __device__ __forceinline__ void sha_compress(uint32_t (&st)[8], uint32_t (&m)[16
     }
 }
 
+// -storeDataSync / -noMemReplication (coast_rt.h "in-loop store votes"): the same compression with EVERY assignment to a data
+// variable voted and, under TMR, all replicas continuing with the voted value -- m[i] (:34-58), a..h = ctx_state (:60-67),
+// t1, t2, h, g, f, e, d, c, b, a per round (:78-87), ctx_state += (:90-97): 720 votes.  The schedule is computed on the fly as
+// in sha_compress; every vote sees the operands it would see in the reference's order (each voted value re-converges).
+// Returns the number of votes at which the copies disagreed.  All 32 lanes must call.
+template <int NC, bool INJECT>
+__device__ __forceinline__ uint32_t sha_compress_sv(uint32_t (&st)[8], uint32_t (&m)[16], uint32_t fs, uint32_t fmask, int lane, bool majority) {
+    uint32_t bad = 0;
+#define SV(x) bad += store_vote<NC>(x, lane, majority)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { SV(m[i]); if (INJECT) m[i] ^= fs == (uint32_t)i ? fmask : 0u; }
+    uint32_t v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] = st[i]; SV(v[i]); }
+    uint32_t a = v[0], b = v[1], c = v[2], d = v[3], e = v[4], f = v[5], g = v[6], h = v[7];
+    const uint32_t ft = INJECT ? ((fs - 16u) >> 3) : 0u, fv = INJECT ? ((fs - 16u) & 7u) : 0u;
+    const bool fround = INJECT && fs >= 16u && fs < 528u;
+#pragma unroll 1
+    for (int t = 0; t < 64; ++t) {
+        if (t >= 16) {
+            const uint32_t w2 = m[(t - 2) & 15], w15 = m[(t - 15) & 15];
+            uint32_t w = (rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10)) + m[(t - 7) & 15] + (rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3)) + m[t & 15];
+            SV(w);
+            m[t & 15] = w;
+        }
+        if (INJECT && fround && ft == (uint32_t)t) {
+            a ^= fv == 0 ? fmask : 0u; b ^= fv == 1 ? fmask : 0u; c ^= fv == 2 ? fmask : 0u; d ^= fv == 3 ? fmask : 0u;
+            e ^= fv == 4 ? fmask : 0u; f ^= fv == 5 ? fmask : 0u; g ^= fv == 6 ? fmask : 0u; h ^= fv == 7 ? fmask : 0u;
+        }
+        uint32_t t1 = h + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & g)) + sha_k(t) + m[t & 15];
+        SV(t1);
+        uint32_t t2 = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+        SV(t2);
+        uint32_t x;
+        x = g; SV(x); h = x;
+        x = f; SV(x); g = x;
+        x = e; SV(x); f = x;
+        x = d + t1; SV(x); e = x;
+        x = c; SV(x); d = x;
+        x = b; SV(x); c = x;
+        x = a; SV(x); b = x;
+        x = t1 + t2; SV(x); a = x;
+    }
+    const uint32_t add[8] = {a, b, c, d, e, f, g, h};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint32_t x = st[i] + add[i];
+        SV(x);
+        st[i] = x;
+        if (INJECT) st[i] ^= (fs >= 528u && fs - 528u == (uint32_t)i) ? fmask : 0u;
+    }
+#undef SV
+    return bad;
+}
+
 __device__ __forceinline__ void sha_init(uint32_t (&st)[8]) {   // :108-115
     st[0] = 0x6a09e667u; st[1] = 0xbb67ae85u; st[2] = 0x3c6ef372u; st[3] = 0xa54ff53au;
     st[4] = 0x510e527fu; st[5] = 0x9b05688cu; st[6] = 0x1f83d9abu; st[7] = 0x5be0cd19u;
@@ -199,6 +254,9 @@ __device__ __forceinline__ void sha256_gen_body(const xmr_args& a) {
                 if ((int)f.replica == r) { fmask = 1u << f.bit; fsite = f.site; }
             }
         }
+        const bool sv = (a.flags & XMR_F_STORE_VOTES) != 0;
+        const bool majority = a.flags & COAST_F_MAJORITY_D;
+        uint32_t sv_bad = 0;
         uint32_t st[8];
         sha_init(st);
         // r02: whole blocks come in as 4 x 16-byte (or 16 x 4-byte) loads when every message is that aligned; the byte walk
@@ -226,9 +284,33 @@ __device__ __forceinline__ void sha256_gen_body(const xmr_args& a) {
                 m[15] = len << 3;
             }
             uint32_t fs = (INJECT && fsite / SHA_SITES_PER_BLOCK == blk) ? fsite % SHA_SITES_PER_BLOCK : 0xFFFFFFFFu;
-            sha_compress<INJECT>(st, m, fs, fmask);
+            if (!sv) {
+                sha_compress<INJECT>(st, m, fs, fmask);
+            } else {
+                // ctx_data[k] = data[i] (:120): one u8 vote per MESSAGE byte of this block (padding and length bytes are constants /
+                // control state), on the big-endian-packed words
+                const uint32_t lo = blk * 64u, nmsg = len > lo ? (len - lo < 64u ? len - lo : 64u) : 0u;
+#pragma unroll
+                for (int w = 0; w < 16; ++w) {
+                    const uint32_t nb = nmsg > 4u * w ? (nmsg - 4u * w < 4u ? nmsg - 4u * w : 4u) : 0u;
+                    sv_bad += store_vote_bytes<NC>(m[w], nb, lane, majority);
+                }
+                sv_bad += sha_compress_sv<NC, INJECT>(st, m, fs, fmask, lane, majority);
+            }
         }
-        sha_vote_store<NC>(st, static_cast<uint8_t*>(a.out), local, gunit, valid, lane, a.flags, tally);
+        if (!sv) {
+            sha_vote_store<NC>(st, static_cast<uint8_t*>(a.out), local, gunit, valid, lane, a.flags, tally);
+        } else {                                              // the SoR exit with the in-loop disagreements added: len + 720 per compression + 32 votes
+            uint32_t o[8], bad = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { Voted v = vote_u32<NC, 1>(st[i], majority); o[i] = bswap(v.vote); bad += v.bad; }
+            if (valid && Lanes<NC>::voter(lane)) {
+                uint4* dst = reinterpret_cast<uint4*>(static_cast<uint8_t*>(a.out) + local * 32ull);
+                dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                tally.unit_exit<NC>(bad + sv_bad, len + 720u * nblk + 32u, a.flags, gunit);
+            }
+        }
     }
     tally.flush(a.counters);
 }

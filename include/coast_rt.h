@@ -99,8 +99,8 @@ typedef enum coast_kernel_id {
 #define COAST_F_NO_STORE_ADDR_SYNC  0x1000u /* -noStoreAddrSync: ... nor on store address offsets (C5, :362-375) */
 /* IN-LOOP STORE VOTES = (-storeDataSync or -noMemReplication) and not -noStoreDataSync: every assignment to a data variable
  * of the protected function is voted and, under TMR, all replicas continue with the voted value; __SYNC_COUNT grows
- * accordingly (crc16: 3 per byte + 1; matrix_multiply: K + 1 per element).  Built for CRC16 and MM_U32 (which then run
- * their general kernels).  The other kernels cannot honour it: they WARN on stderr and run the default sync set, or
+ * accordingly (crc16: 3 per byte + 1; matrix_multiply: K + 1 per element; sha256: len + 720 per compression + 32).  Built for
+ * CRC16, MM_U32 and SHA256 (which then run their general kernels).  The other kernels cannot honour it: they WARN on stderr and run the default sync set, or
  * fail with COAST_ERR_UNSUPPORTED when COAST_STRICT_FLAGS=1.  coast_flags_honoured() tells which.
  * Address-offset votes need a data-dependent subscript; crc16 and matrix_multiply have none, so -noLoadSync /
  * -noStoreAddrSync change nothing there. */

@@ -651,7 +651,7 @@ static void run_replica(const orc_desc* d, uint64_t local, const orc_fault* f, u
 int orc_store_votes(uint32_t flags) {
     return (flags & (ORC_F_STORE_DATA_SYNC | ORC_F_NO_MEM_REPLICATION)) && !(flags & ORC_F_NO_STORE_DATA_SYNC);
 }
-int orc_store_votes_supported(uint32_t kernel) { return kernel == ORC_K_CRC16 || kernel == ORC_K_MM_U32; }
+int orc_store_votes_supported(uint32_t kernel) { return kernel == ORC_K_CRC16 || kernel == ORC_K_MM_U32 || kernel == ORC_K_SHA256; }
 
 typedef struct { uint32_t nc, flags; uint64_t errors, syncs; int disagree; } sv_ctx;
 /* one store vote on v[0..nc) (width <= 32 bits); TMR: every copy continues with the voted value */
@@ -695,6 +695,113 @@ static uint32_t sv_mm_elem(const uint32_t* A, const uint32_t* B, uint32_t K, uin
     sv_vote(c, sum);                                                                /* :16 r[i][j] = sum */
     return sum[0];
 }
+/* sha256_transform / sha256_hash with every assignment to a data variable voted, in the reference's statement order:
+ *   ctx_data[k] = data[i]              (sha256_common_tmr.c:120)   one u8 vote per message byte
+ *   m[i] = pack(...)  i < 16            (:34-40)                    16 votes
+ *   m[i] = SIG1(..) + .. i = 16..63     (:42-58)                    48 votes
+ *   a..h = ctx_state[0..7]              (:60-67)                     8 votes
+ *   t1, t2, h, g, f, e, d, c, b, a      (:78-87) x 64 rounds       640 votes
+ *   ctx_state[j] += a..h                (:90-97)                     8 votes
+ *   hash[i] = ...                       (:169-178)                  32 votes (the SoR exit)
+ * = len + 720 per compression + 32.  Not voted: stores of constants (padding bytes, the IV: syncStoreInst :507-509) and the
+ * control state derived from `len` alone (ctx_datalen, ctx_bitlen and the length bytes copied from it, loop counters).
+ * A fault site keeps its meaning (m[w] after the pack; a working variable at the entry of round t; ctx_state[j] after the final
+ * add): the flip lands on the replica's copy after that assignment's vote.  A flipped working variable can be voted more than
+ * once before it is overwritten (e.g. `b`: in t2 through MAJ, then again in `c = b`), so errors_corrected may exceed injected. */
+static void sv_sha_compress(uint32_t st[3][8], uint8_t blkb[64], uint32_t nmsg, uint32_t blk, const orc_fault* f, sv_ctx* c) {
+    const uint32_t nc = c->nc;
+    const int has = f->active && (f->site / SHA_SITES_PER_BLOCK) == blk;
+    const uint32_t s = has ? f->site % SHA_SITES_PER_BLOCK : 0xFFFFFFFFu, mask = has ? (1u << f->bit) : 0u, fr = f->replica;
+    uint32_t m[3][64], v[3][8], x[3];
+    for (uint32_t k = 0; k < nmsg; ++k) { for (uint32_t r = 0; r < 3; ++r) x[r] = blkb[k]; sv_vote(c, x); }      /* :120 */
+    for (int i = 0; i < 16; ++i) {
+        for (uint32_t r = 0; r < 3; ++r)
+            x[r] = ((uint32_t)blkb[4 * i] << 24) | ((uint32_t)blkb[4 * i + 1] << 16) | ((uint32_t)blkb[4 * i + 2] << 8) | (uint32_t)blkb[4 * i + 3];
+        sv_vote(c, x);
+        for (uint32_t r = 0; r < 3; ++r) m[r][i] = x[r];
+        if (s == (uint32_t)i && fr < nc) m[fr][i] ^= mask;
+    }
+    for (int i = 16; i < 64; ++i) {
+        for (uint32_t r = 0; r < 3; ++r) {
+            const uint32_t a = m[r][i - 2], b = m[r][i - 15];
+            x[r] = (rotr32(a, 17) ^ rotr32(a, 19) ^ (a >> 10)) + m[r][i - 7] + (rotr32(b, 7) ^ rotr32(b, 18) ^ (b >> 3)) + m[r][i - 16];
+        }
+        sv_vote(c, x);
+        for (uint32_t r = 0; r < 3; ++r) m[r][i] = x[r];
+    }
+    for (int i = 0; i < 8; ++i) {
+        for (uint32_t r = 0; r < 3; ++r) x[r] = st[r][i];
+        sv_vote(c, x);
+        for (uint32_t r = 0; r < 3; ++r) v[r][i] = x[r];
+    }
+    for (uint32_t t = 0; t < 64; ++t) {
+        if (s >= 16u && s < 528u && (s - 16u) / 8u == t && fr < nc) v[fr][(s - 16u) % 8u] ^= mask;
+        uint32_t t1[3], t2[3];
+        for (uint32_t r = 0; r < 3; ++r) {
+            const uint32_t e = v[r][4], ff = v[r][5], g = v[r][6];
+            t1[r] = v[r][7] + (rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25)) + ((e & ff) ^ (~e & g)) + SHA_K[t] + m[r][t];
+        }
+        sv_vote(c, t1);
+        for (uint32_t r = 0; r < 3; ++r) {
+            const uint32_t a = v[r][0], b = v[r][1], cc = v[r][2];
+            t2[r] = (rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22)) + ((a & b) ^ (a & cc) ^ (b & cc));
+        }
+        sv_vote(c, t2);
+        /* h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2 -- each store voted, in this order */
+        for (uint32_t r = 0; r < 3; ++r) x[r] = v[r][6];
+        sv_vote(c, x); for (uint32_t r = 0; r < 3; ++r) v[r][7] = x[r];
+        for (uint32_t r = 0; r < 3; ++r) x[r] = v[r][5];
+        sv_vote(c, x); for (uint32_t r = 0; r < 3; ++r) v[r][6] = x[r];
+        for (uint32_t r = 0; r < 3; ++r) x[r] = v[r][4];
+        sv_vote(c, x); for (uint32_t r = 0; r < 3; ++r) v[r][5] = x[r];
+        for (uint32_t r = 0; r < 3; ++r) x[r] = v[r][3] + t1[r];
+        sv_vote(c, x); for (uint32_t r = 0; r < 3; ++r) v[r][4] = x[r];
+        for (uint32_t r = 0; r < 3; ++r) x[r] = v[r][2];
+        sv_vote(c, x); for (uint32_t r = 0; r < 3; ++r) v[r][3] = x[r];
+        for (uint32_t r = 0; r < 3; ++r) x[r] = v[r][1];
+        sv_vote(c, x); for (uint32_t r = 0; r < 3; ++r) v[r][2] = x[r];
+        for (uint32_t r = 0; r < 3; ++r) x[r] = v[r][0];
+        sv_vote(c, x); for (uint32_t r = 0; r < 3; ++r) v[r][1] = x[r];
+        for (uint32_t r = 0; r < 3; ++r) x[r] = t1[r] + t2[r];
+        sv_vote(c, x); for (uint32_t r = 0; r < 3; ++r) v[r][0] = x[r];
+    }
+    for (int i = 0; i < 8; ++i) {
+        for (uint32_t r = 0; r < 3; ++r) x[r] = st[r][i] + v[r][i];
+        sv_vote(c, x);
+        for (uint32_t r = 0; r < 3; ++r) st[r][i] = x[r];
+        if (s == 528u + (uint32_t)i && fr < nc) st[fr][i] ^= mask;
+    }
+}
+static void sv_sha256_unit(const uint8_t* data, uint32_t len, uint8_t digest[32], const orc_fault* f, sv_ctx* c) {
+    uint32_t st[3][8];
+    for (uint32_t r = 0; r < 3; ++r) {
+        static const uint32_t iv[8] = { 0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u };
+        memcpy(st[r], iv, sizeof iv);
+    }
+    uint8_t buf[64];
+    uint32_t blk = 0, off = 0;
+    while (len - off >= 64u) { memcpy(buf, data + off, 64); sv_sha_compress(st, buf, 64u, blk++, f, c); off += 64u; }
+    const uint32_t rem = len - off;
+    memcpy(buf, data + off, rem);
+    buf[rem] = 0x80;
+    if (rem < 56u) {
+        memset(buf + rem + 1, 0, 55u - rem);
+    } else {
+        memset(buf + rem + 1, 0, 63u - rem);
+        sv_sha_compress(st, buf, rem, blk++, f, c);
+        memset(buf, 0, 56);
+    }
+    const uint64_t bits = (uint64_t)len * 8u;
+    for (int i = 0; i < 8; ++i) buf[63 - i] = (uint8_t)(bits >> (8 * i));
+    sv_sha_compress(st, buf, rem < 56u ? rem : 0u, blk++, f, c);
+    for (int w = 0; w < 8; ++w)
+        for (int i = 0; i < 4; ++i) {                                   /* :169-178, the SoR exit: one u8 vote per digest byte */
+            uint32_t x[3];
+            for (uint32_t r = 0; r < 3; ++r) x[r] = (st[r][w] >> (24 - 8 * i)) & 0xFFu;
+            sv_vote(c, x);
+            digest[4 * w + i] = (uint8_t)x[0];
+        }
+}
 static void sv_run_range(const orc_desc* d, uint64_t u0, uint64_t u1, orc_stats* st) {
     const uint32_t nc = d->num_clones;
     for (uint64_t local = u0; local < u1; ++local) {
@@ -705,6 +812,8 @@ static void sv_run_range(const orc_desc* d, uint64_t u0, uint64_t u1, orc_stats*
         if (d->kernel == ORC_K_CRC16) {
             uint16_t v = sv_crc16_unit((const uint8_t*)d->in + local * d->unit_bytes, d->unit_bytes, &f, &c);
             memcpy((uint8_t*)d->out + local * 2, &v, 2);
+        } else if (d->kernel == ORC_K_SHA256) {
+            sv_sha256_unit((const uint8_t*)d->in + local * d->unit_bytes, d->unit_bytes, (uint8_t*)d->out + local * 32, &f, &c);
         } else {
             uint32_t v = sv_mm_elem((const uint32_t*)d->in, (const uint32_t*)d->aux, d->K, d->N, (uint32_t)(local / d->N), (uint32_t)(local % d->N), &f, &c);
             memcpy((uint8_t*)d->out + local * 4, &v, 4);

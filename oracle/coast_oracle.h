@@ -34,7 +34,7 @@ enum { ORC_K_CRC16 = 0, ORC_K_SHA256 = 1, ORC_K_AES128 = 2, ORC_K_MM_U32 = 3, OR
 enum { ORC_F_COUNT_ERRORS = 1, ORC_F_COUNT_SYNCS = 2, ORC_F_NO_MEM_REPLICATION = 4, ORC_F_MAJORITY = 0x100,
        ORC_F_STORE_DATA_SYNC = 0x200, ORC_F_NO_STORE_DATA_SYNC = 0x400, ORC_F_NO_LOAD_SYNC = 0x800, ORC_F_NO_STORE_ADDR_SYNC = 0x1000 };
 /* In-loop store votes (rule C4): -storeDataSync forces them, -noMemReplication needs them (one memory copy: stores are voted,
- * synchronization.cpp:205-215), -noStoreDataSync removes them (:333-335).  Modelled for CRC16 and MM_U32 (orc_store_votes_supported). */
+ * synchronization.cpp:205-215), -noStoreDataSync removes them (:333-335).  Modelled for CRC16, MM_U32 and SHA256 (orc_store_votes_supported). */
 int orc_store_votes(uint32_t flags);
 int orc_store_votes_supported(uint32_t kernel);
 enum { ORC_PLAN_NONE = 0, ORC_PLAN_BERNOULLI = 1, ORC_PLAN_TABLE = 2 };

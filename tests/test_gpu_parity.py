@@ -428,7 +428,7 @@ def test_matmul_host_call_row_blocks_equal_the_device_launch(rt, oracle, kernel)
 
 @pytest.mark.parametrize("nc", [2, 3])
 @pytest.mark.parametrize("flagname", ["F_STORE_DATA_SYNC", "F_NO_MEM_REPLICATION"])
-def test_store_votes_crc16_and_mm_match_the_oracle(rt, oracle, nc, flagname):
+def test_store_votes_crc16_mm_and_sha256_match_the_oracle(rt, oracle, nc, flagname):
     """8f-1: -storeDataSync / -noMemReplication = votes on every assignment inside the loops (oracle: sv_crc16_unit / sv_mm_elem);
     outputs, corrected-error count, __SYNC_COUNT and the per-unit status all equal the oracle, zero-fault and under faults at
     every site class; lengths include 64 (the table kernel must NOT be picked) and the 13-byte reference message"""
@@ -450,6 +450,15 @@ def test_store_votes_crc16_and_mm_match_the_oracle(rt, oracle, nc, flagname):
     # -noStoreDataSync switches the in-loop votes off again
     g, st = both(rt, oracle, oracle.K_CRC16, 3, msgs(oracle, 100, 13, 1), 100, unit_bytes=13, flags=3 | extra | cb.F_NO_STORE_DATA_SYNC)
     assert st["syncs"] == 100
+    # sha256: len + 720 votes per compression + 32; lengths around the padding edges, aligned (64: NOT the TMA kernel) and ragged
+    for L, n in ((64, 700), (10, 300), (55, 100), (56, 100), (119, 64), (128, 200)):
+        m = msgs(oracle, n, L, 2)
+        g, st = both(rt, oracle, oracle.K_SHA256, nc, m, n, unit_bytes=L, flags=3 | extra)
+        assert st["syncs"] == (n * (L + 720 * ((L + 8) // 64 + 1) + 32) if nc == 3 else 0)
+        both(rt, oracle, oracle.K_SHA256, nc, m, n, unit_bytes=L, flags=3 | extra, plan_kw=dict(seed=8, p=0.5))
+    n = 1072
+    table = np.array([oracle.fault_entry(u % nc, u, (u * 7) % 32) for u in range(n)], dtype=np.uint32)
+    both(rt, oracle, oracle.K_SHA256, nc, msgs(oracle, n, 64, 2), n, unit_bytes=64, flags=3 | extra, table=table)
 
 
 def test_reference_entry_points(rt, oracle, golden):

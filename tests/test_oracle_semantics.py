@@ -168,3 +168,24 @@ def test_store_votes_correct_a_flip_at_the_next_assignment(oracle):
         if rep < 2:
             out, st = oracle.run(oracle.K_CRC16, 2, msg, n, unit_bytes=L, flags=oracle.F_STORE_DATA_SYNC, plan=oracle.make_plan(oracle.PLAN_TABLE, table=table))
             assert st["dwc_detected"] == n
+
+
+def test_sha256_store_votes_count_and_correct_every_site(oracle):
+    """sha256 under -noMemReplication / -storeDataSync: len + 720 per compression + 32 votes per message; every one of the 536 sites of
+    both compressions of a 64-byte message is corrected before the digest; a flipped working variable can be voted twice before it is
+    overwritten, so errors_corrected >= injected"""
+    import hashlib
+    import numpy as np
+    for L in (0, 1, 55, 56, 64, 100):
+        n = 6
+        m = oracle.fill_philox((n * L + 3) // 4 + 1, 0, 2).view(np.uint8)[: n * L].copy() if L else np.zeros(4, dtype=np.uint8)
+        out, st = oracle.run(oracle.K_SHA256, 3, m, n, unit_bytes=L, flags=3 | oracle.F_NO_MEM_REPLICATION)
+        assert st["syncs"] == n * (L + 720 * ((L + 8) // 64 + 1) + 32) and st["errors_corrected"] == 0
+        for u in range(n):
+            assert out[32 * u: 32 * u + 32].tobytes() == hashlib.sha256(m[L * u: L * u + L].tobytes()).digest()
+    L, n = 64, 1072
+    m = oracle.fill_philox(n * L // 4, 0, 2).view(np.uint8)
+    clean, _ = oracle.run(oracle.K_SHA256, 1, m, n, unit_bytes=L)
+    tab = np.array([oracle.fault_entry(u % 3, u, (u * 7) % 32) for u in range(n)], dtype=np.uint32)
+    out, st = oracle.run(oracle.K_SHA256, 3, m, n, unit_bytes=L, flags=3 | oracle.F_STORE_DATA_SYNC, plan=oracle.make_plan(oracle.PLAN_TABLE, table=tab))
+    assert out.tobytes() == clean.tobytes() and st["injected"] == n and n <= st["errors_corrected"] <= 3 * n
