@@ -491,7 +491,8 @@ static int launch_gemm_tf32(const coast_launch_desc* d, xmr_args* a, int inj, CU
     const unsigned bn = wide ? 256u : 128u, stages = wide ? 4u : 6u;
     const unsigned GEMM_SMEM = stages * (16384u + 32u * bn * 4u) + 1024u + 256u;
     { const char* g = getenv("COAST_GEMM_GROUP_M"); if (g && atoi(g) > 0 && atoi(g) < 256) a->mode = (a->mode & ~0xFFu) | (unsigned)atoi(g); }
-    { const char* h = getenv("COAST_GEMM_L2_HINTS"); if (h && strcmp(h, "0")) a->mode |= 0x100u; }     /* experiment knob, xmr_gemm_tf32.cuh */
+    /* L2 eviction priorities (A evict_last, B and C evict_first): 5 % fewer DRAM reads at 4096^3, same time (profiles/r02_gemm_l2_sweep.txt) */
+    { const char* h = getenv("COAST_GEMM_L2_HINTS"); if (!(h && !strcmp(h, "0"))) a->mode |= 0x100u; }
     CUfunction fn; int occ = 1;
     int rc = get_fn(name, GEMM_SMEM, &fn, &occ); if (rc) return rc;
     CUtensorMap ma, mb;
@@ -1015,7 +1016,10 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int* dwc_
     const char* hp = getenv("COAST_HOST_PATH");
     const int streams_once = d->kernel == COAST_K_CRC16 || d->kernel == COAST_K_SHA256 || d->kernel == COAST_K_AES128 ||
                              d->kernel == COAST_K_CHSTONE_SHA || d->kernel == COAST_K_CHSTONE_AES;
-    const int want = hp ? (!strcmp(hp, "zerocopy") ? 2 : !strcmp(hp, "hybrid") ? 1 : 0) : G.host_path_default;
+    /* default (measured, profiles/r02_e2e_*.json): staged -- except when the output is tiny next to the input (crc16: 2 of 64 bytes,
+     * CHStone sha: 20 bytes per stream), where one zero-copy launch on pinned buffers beats the chunk pipeline (1.59 vs 2.77 ms) */
+    const int tiny_out = ob * 8u <= ib;
+    const int want = hp ? (!strcmp(hp, "zerocopy") ? 2 : !strcmp(hp, "hybrid") ? 1 : 0) : (tiny_out ? 2 : G.host_path_default);
     CUdeviceptr zin = 0;
     if (streams_once && want && ib) zin = host_alias(d->d_in, (size_t)(d->n_units * ib));
     if (want == 2 && streams_once) {
@@ -1033,6 +1037,7 @@ static int run_host_impl(const coast_launch_desc* d, coast_stats* out, int* dwc_
             return sync_impl(G.hs[2], out, dwc_fired);
         }
         if (hp) return fail(COAST_ERR_BAD_ARG, "COAST_HOST_PATH=zerocopy needs pinned (mapped) host buffers");
+        zin = 0;                                                   /* the default policy falls back to staged copies for pageable memory */
     }
     if (hp && want == 1 && streams_once && ib && !zin) return fail(COAST_ERR_BAD_ARG, "COAST_HOST_PATH=hybrid needs a pinned (mapped) input buffer");
     rc = run_host_staged(d, ib, ob, per_unit_key, want ? zin : 0); if (rc) return rc;

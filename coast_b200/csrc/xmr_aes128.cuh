@@ -124,10 +124,14 @@ __device__ __forceinline__ void aes_vote_store(const uint32_t (&c)[4], uint8_t* 
 
 // The ten iterations of J blocks.  HOOKS = this warp has at least one block with a mid-round fault: the flip of block j is
 // fbit[j] in column fcol[j] at the bottom of iteration frd[j].  PERKEY: k[j] is the block's running round key.
-template <int J, bool DEC, bool PERKEY, bool HOOKS>
+// ROLLED = keep the round loop a loop (PERKEY only: the round keys are then computed, not indexed): the rare hook path of the
+// one-key kernels must stay SMALL -- a second fully unrolled copy of the rounds doubled the kernel to 82 KB and the two copies
+// evicted each other from the instruction cache (r02 call 2b: +11 % instructions but +29 % time, issue rate 0.62 -> 0.55).
+template <int J, bool DEC, bool PERKEY, bool HOOKS, bool ROLLED = false>
 __device__ __forceinline__ void aes_rounds(const AesLaneBases& L, uint32_t (&s)[J][4], uint32_t (&k)[PERKEY ? J : 1][4], const uint32_t (&rk)[PERKEY ? 4 : 44],
                                            const uint32_t (&fbit)[J], const int (&frd)[J], const int (&fcol)[J]) {
-#pragma unroll
+    static_assert(!ROLLED || PERKEY, "a rolled round loop cannot index the register-resident round keys");
+#pragma unroll (ROLLED ? 1 : 10)
     for (int rd = 0; rd < 10; ++rd) {
 #pragma unroll
         for (int j = 0; j < J; ++j) {
@@ -317,8 +321,21 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
 #pragma unroll
             for (int c = 0; c < 4; ++c) s[j][c] ^= PERKEY ? k[j][c] : rk[c];      // first half of :143-146 / :127-129
         }
-        if (INJECT && hooks) aes_rounds<J, DEC, PERKEY, true>(L, s, k, rk, fbit, frd, fcol);
-        else aes_rounds<J, DEC, PERKEY, false>(L, s, k, rk, fbit, frd, fcol);
+        if (INJECT && hooks) {
+            if constexpr (PERKEY) {
+                aes_rounds<J, DEC, true, true, true>(L, s, k, rk, fbit, frd, fcol);
+            } else {
+                // one-key kernels: the hook path recomputes the round keys on the fly from the first one (rk[0..3] = round key 0 for
+                // encrypt, round key 10 for decrypt) in a ROLLED loop, so it adds ~5 KB of code instead of a second 35 KB copy
+                uint32_t kk[J][4];
+                const uint32_t none[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int j = 0; j < J; ++j) { kk[j][0] = rk[0]; kk[j][1] = rk[1]; kk[j][2] = rk[2]; kk[j][3] = rk[3]; }
+                aes_rounds<J, DEC, true, true, true>(L, s, kk, none, fbit, frd, fcol);
+            }
+        } else {
+            aes_rounds<J, DEC, PERKEY, false>(L, s, k, rk, fbit, frd, fcol);
+        }
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             aes_vote_store<NC>(s[j], static_cast<uint8_t*>(a.out), local[j], a.unit_base + local[j], valid[j], lane, a.flags, tally);
@@ -400,7 +417,7 @@ __device__ __forceinline__ void chstone_aes_body(const xmr_args& a) {
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) s[0][c] ^= k[0][c];                           // AddRoundKey(0) / AddRoundKey(10)
-        if (INJECT && hooks) aes_rounds<1, DEC, true, true>(L, s, k, rk_unused, fbit, frd, fcol);
+        if (INJECT && hooks) aes_rounds<1, DEC, true, true, true>(L, s, k, rk_unused, fbit, frd, fcol);
         else aes_rounds<1, DEC, true, false>(L, s, k, rk_unused, fbit, frd, fcol);
         uint32_t o[4], bad = 0;
 #pragma unroll

@@ -372,6 +372,18 @@ def test_pinned_buffers_take_the_zero_copy_host_call(mock_dir, tmp_path):
     _contiguous([(e["host"] - r["host_out"], e["bytes"]) for e in ev if e["op"] == "d2h" and 0 <= e["host"] - r["host_out"] < 32 * n], 32 * n)
 
 
+def test_default_host_path_is_zero_copy_only_for_tiny_outputs(mock_dir, tmp_path):
+    """measured policy (profiles/r02_e2e_*.json): staged by default; pinned buffers + an output of at most 1/8 of the input (crc16: 2 of 64
+    bytes) -> one zero-copy launch; the same call with pageable memory falls back to the staged pipeline"""
+    n = 200000
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="run_host_pinned", kernel=K_CRC16, nc=3, n=n, unit_bytes=64, in_bytes=64 * n, out_bytes=2 * n),
+                                             dict(op="shutdown")])
+    la = [e for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
+    assert res["ops"][0]["rc"] == 0 and len(la) == 1 and args_of(la[0]).inp == res["ops"][0]["host_in"] and not [e for e in ev if e["op"] == "h2d"]
+    res, ev = run_child(mock_dir, tmp_path / "..", [dict(op="run_host", kernel=K_CRC16, nc=3, n=n, unit_bytes=64, in_bytes=64 * n, out_bytes=2 * n)])
+    assert res["ops"][0]["rc"] == 0 and [e for e in ev if e["op"] == "h2d"]
+
+
 def test_zero_copy_is_refused_for_pageable_buffers_only_when_forced(mock_dir, tmp_path):
     op = dict(op="run_host", kernel=K_SHA256, nc=3, n=1000, unit_bytes=64, in_bytes=64000, out_bytes=32000)
     res, ev = run_child(mock_dir, tmp_path, [op], env_extra={"COAST_HOST_PATH": "zerocopy"})
