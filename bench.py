@@ -334,13 +334,13 @@ def workload_table(cb):
         "aes": dict(kernel=cb.K_AES128, nc=2, flags=0, unit_bytes=0, in_b=16, alg_b=32,
                     plan=dict(seed=33, p=2.0 ** -10), key=bytes(16),
                     kname="xmr_aes128_enc_nc2_inj1", bound="hbm", sets=2, profile="r02_aes_nc2_inj1.json", profile_units=1 << 24,
-                    traffic="r01_aes_traffic.json"),
+                    traffic="r02_aes_traffic.json"),
         "crc16": dict(kernel=cb.K_CRC16, nc=3, flags=F, unit_bytes=64, in_b=64, alg_b=66, plan=None,
                       kname="xmr_crc16_b64_nc3_inj0", bound="hbm", sets=4, profile="r01_crc16_nc3_v2.json", profile_units=1 << 20,
                       traffic="r01_crc16_traffic.json"),
         "gemm": dict(kernel=cb.K_GEMM_TF32, nc=3, flags=F, side=4096, plan=None,
                      kname="xmr_gemm_tf32_nc3_inj0", bound="tensor", sets=2, profile="r02_gemm_nc3.json", profile_units=4096 * 4096,
-                     traffic="r01_gemm_traffic.json"),
+                     traffic="r02_gemm_traffic.json"),
     }
 
 
