@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--side", type=int, default=1024)
     ap.add_argument("--stream-bytes", type=int, default=16384, help="chsha: bytes per stream (the benchmark's is 2 x 8192)")
     ap.add_argument("--flags", type=lambda x: int(x, 0), default=0, help="extra COAST_F_* bits, e.g. 0x8 = -i, 0x10 = -s")
+    ap.add_argument("--table-density", type=float, default=-1.0, help="use a TABLE plan with this fraction of units faulted (0 = all-zero table)")
+    ap.add_argument("--threshold", type=int, default=-1, help="Bernoulli plan with this raw threshold (0 = the injector kernel never hits)")
     ap.add_argument("--aes-mode", type=lambda x: int(x, 0), default=0, help="aes: COAST_AES_* bits (1 decrypt, 2 per-unit keys, 4 key write-back)")
     ap.add_argument("--time", action="store_true", help="print CUDA-event ms per launch (outside any profiler)")
     a = ap.parse_args()
@@ -30,6 +32,20 @@ def main():
     rt = cb.Runtime(0)
     n = 1 << a.log2n
     plan = cb.FaultPlan(mode=cb.PLAN_BERNOULLI, seed=7, p=a.inject) if a.inject > 0 else None
+    if a.threshold >= 0:
+        plan = cb.FaultPlan(mode=cb.PLAN_BERNOULLI, seed=7, threshold=a.threshold)
+    if a.table_density >= 0:
+        nn = 1 << a.log2n
+        tab = torch.zeros(nn, dtype=torch.int32, device="cuda")
+        if a.table_density > 0:
+            g = torch.Generator(device="cuda"); g.manual_seed(3)
+            hit = torch.rand(nn, device="cuda", generator=g) < a.table_density
+            site = torch.randint(0, 176, (nn,), device="cuda", generator=g, dtype=torch.int32)
+            rep = torch.randint(0, max(a.nc, 1), (nn,), device="cuda", generator=g, dtype=torch.int32)
+            bit = torch.randint(0, 8, (nn,), device="cuda", generator=g, dtype=torch.int32)
+            ent = (torch.full((nn,), -2 ** 31, dtype=torch.int32, device="cuda") | (rep << 29) | (site << 5) | bit)
+            tab = torch.where(hit, ent, tab)
+        plan = cb.FaultPlan(mode=cb.PLAN_TABLE, table=tab)
     flags = cb.F_COUNT_ERRORS | cb.F_COUNT_SYNCS | a.flags
     if a.kernel == "sha256":
         d_in = torch.empty(n * 64, dtype=torch.uint8, device="cuda"); rt.fill_philox(d_in, 2)
