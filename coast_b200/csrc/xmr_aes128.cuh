@@ -41,6 +41,54 @@ constexpr uint32_t AES_TAB01 = 0x10000u, AES_TAB23 = 0x20000u, AES_SIS = 0x30000
 constexpr uint32_t AES_WINDOW_END_ENC = 0x30000u, AES_WINDOW_END_DEC = 0x38000u;
 template <int NC> struct AesGeom { static constexpr int J = NC == 1 ? 2 : 4; static constexpr int TROWS = AES_WARPS * Lanes<NC>::kUnitsPerWarp * J; };
 
+// Input ring of the AES kernels: 3 stages, full[] (TMA -> warps) and empty[] (warps -> the issuing thread) mbarriers and NO
+// CTA-wide barrier in the tile loop.  r02 ablation (profiles/r02_aes_injector_ablation.txt): with the r01 ring's __syncthreads()
+// per tile the 16 warps of a CTA advance in lock-step, so (a) the ALU-only Philox phase of the injector ran while the
+// shared-memory pipe idled (+14.5 % with a plan that never hits) and (b) ONE warp on the rare hook path stalled the other 15
+// for ~2 400 cycles at the next barrier (+0.13 ms at p = 2^-10).  Here a warp releases a stage as soon as its rows are in
+// registers and runs up to two tiles ahead of the slowest warp; thread 0 refills a stage once all 16 warps have released it.
+constexpr int AES_STAGES = 3;
+template <int TILE_ROWS>
+struct AesRing {
+    static constexpr int pick_loads() { int l = (TILE_ROWS + 255) / 256; while (TILE_ROWS % l) ++l; return l; }
+    static constexpr int LOADS = pick_loads();
+    static constexpr int BOX_ROWS = TILE_ROWS / LOADS;
+    static constexpr uint32_t TILE_BYTES = (uint32_t)TILE_ROWS * 16u;
+    static constexpr uint32_t STAGE_STRIDE = (TILE_BYTES + 1023u) & ~1023u;
+    static constexpr uint32_t SMEM_BYTES = AES_STAGES * STAGE_STRIDE + 128;
+    uint8_t* tiles; uint64_t* full; uint64_t* empty; const CUtensorMap* tmap; uint32_t pack_shift;
+    __device__ __forceinline__ void init(uint8_t* smem, const CUtensorMap* map, uint32_t row_pack_shift) {
+        tiles = smem; tmap = map; pack_shift = row_pack_shift;
+        full = reinterpret_cast<uint64_t*>(smem + AES_STAGES * STAGE_STRIDE);
+        empty = full + AES_STAGES;
+        if (threadIdx.x == 0) {
+            tma_prefetch_desc(map);
+#pragma unroll
+            for (int s = 0; s < AES_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], AES_WARPS); }
+            fence_barrier_init();
+        }
+        __syncthreads();
+    }
+    __device__ __forceinline__ void issue(uint32_t it, uint32_t tile) {           // thread 0 only
+        const uint32_t stage = it % AES_STAGES;
+        mbar_arrive_expect_tx(&full[stage], TILE_BYTES);
+#pragma unroll
+        for (int l = 0; l < LOADS; ++l)
+            tma_load_2d(tiles + stage * STAGE_STRIDE + l * BOX_ROWS * 16, tmap, &full[stage], 0, (int)((tile * TILE_ROWS + l * BOX_ROWS) >> pack_shift));
+    }
+    __device__ __forceinline__ const uint8_t* wait_full(uint32_t it) {
+        mbar_wait(&full[it % AES_STAGES], (it / AES_STAGES) & 1u);
+        return tiles + (it % AES_STAGES) * STAGE_STRIDE;
+    }
+    __device__ __forceinline__ void release(uint32_t it, int lane) {              // whole warp: its rows of tile `it` are in registers
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[it % AES_STAGES])) : "memory");
+    }
+    __device__ __forceinline__ void wait_empty(uint32_t it) {                     // every warp has released the stage tile `it` used
+        mbar_wait(&empty[it % AES_STAGES], (it / AES_STAGES) & 1u);
+    }
+};
+
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
 // table row of byte k of t: splice that byte into byte 1 of the lane's base address
 template <int K> __device__ __forceinline__ uint32_t tab(uint32_t lb, uint32_t t) { return lds32(__byte_perm(t, lb, 0x7604u | (K << 4))); }
@@ -196,7 +244,8 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
     constexpr int UPW = Lanes<NC>::kUnitsPerWarp;
     constexpr int J = AesGeom<NC>::J;
     constexpr int TROWS = AesGeom<NC>::TROWS;
-    using Ring = TileRing<TROWS, 16>;
+    using Ring = AesRing<TROWS>;
+    static_assert(Ring::SMEM_BYTES + 1024u + 1024u <= AES_TAB01, "the ring must end below the first table window");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t win = smem_u32(smem_raw);                    // shared-window address of the dynamic region
     uint8_t* ring_mem = smem_raw + ((1024u - (win & 1023u)) & 1023u);
@@ -241,20 +290,29 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
 
     const uint32_t n_tiles = a.n_tiles;
     uint32_t tile = blockIdx.x;
-    if (tile < n_tiles) ring.issue(0, tile);
+    if (tid == 0) {                                             // prologue: AES_STAGES - 1 tiles in flight
+#pragma unroll
+        for (uint32_t i = 0; i + 1u < (uint32_t)AES_STAGES; ++i)
+            if (tile + i * gridDim.x < n_tiles) ring.issue(i, tile + i * gridDim.x);
+    }
     Tally tally(a);
     uint32_t it = 0;
     for (; tile < n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t next = tile + gridDim.x;
-        if (next < n_tiles) ring.issue((it + 1u) & 1u, next);
-        const uint8_t* base = ring.wait(it);
+        const uint8_t* base = ring.wait_full(it);
         uint32_t s[J][4];
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             uint4 q = *reinterpret_cast<const uint4*>(base + ((warp * J + j) * UPW + u) * 16);
             s[j][0] = q.x; s[j][1] = q.y; s[j][2] = q.z; s[j][3] = q.w;
         }
-        __syncthreads();
+        ring.release(it, lane);
+        if (tid == 0) {                                         // refill: tile it + STAGES - 1 goes where tile it - 1 was
+            const uint32_t ahead = tile + (uint32_t)(AES_STAGES - 1) * gridDim.x;
+            if (ahead < n_tiles) {
+                if (it >= 1u) ring.wait_empty(it - 1u);
+                ring.issue(it + (uint32_t)(AES_STAGES - 1), ahead);
+            }
+        }
 
         unsigned long long local[J];
         bool valid[J];
