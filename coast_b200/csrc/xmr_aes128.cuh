@@ -380,17 +380,21 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
             for (int c = 0; c < 4; ++c) s[j][c] ^= PERKEY ? k[j][c] : rk[c];      // first half of :143-146 / :127-129
         }
         if (INJECT && hooks) {
+            // hook path.  XMR_AES_HOOKS_ROLLED selects a rolled loop that recomputes the round keys (small code, slow: measured 3x a
+            // normal tile, profiles/r02_aes_injector_ablation_ring3.txt); the default is a second unrolled copy of the rounds.
+#ifdef XMR_AES_HOOKS_ROLLED
             if constexpr (PERKEY) {
                 aes_rounds<J, DEC, true, true, true>(L, s, k, rk, fbit, frd, fcol);
             } else {
-                // one-key kernels: the hook path recomputes the round keys on the fly from the first one (rk[0..3] = round key 0 for
-                // encrypt, round key 10 for decrypt) in a ROLLED loop, so it adds ~5 KB of code instead of a second 35 KB copy
                 uint32_t kk[J][4];
                 const uint32_t none[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                 for (int j = 0; j < J; ++j) { kk[j][0] = rk[0]; kk[j][1] = rk[1]; kk[j][2] = rk[2]; kk[j][3] = rk[3]; }
                 aes_rounds<J, DEC, true, true, true>(L, s, kk, none, fbit, frd, fcol);
             }
+#else
+            aes_rounds<J, DEC, PERKEY, true>(L, s, k, rk, fbit, frd, fcol);
+#endif
         } else {
             aes_rounds<J, DEC, PERKEY, false>(L, s, k, rk, fbit, frd, fcol);
         }

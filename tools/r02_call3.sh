@@ -21,7 +21,7 @@ timeout 600 ncu --set full --clock-control none -k regex:xmr_aes128_enc_nc2_inj1
 python tools/ncu_summary.py "$out/aes_nc2_inj1.ncu-rep" "$out/aes_nc2_inj1.json" > /dev/null 2>&1; rm -f "$out/aes_nc2_inj1.ncu-rep"
 timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > "$out/bench_default.json" 2> "$out/bench_default.err"; echo "bench rc=$?" | tee -a "$out/summary.txt"
 timeout 300 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 --ref-budget-s 25 > "$out/bench_reference.json" 2> "$out/bench_reference.err"; echo "ref rc=$?" | tee -a "$out/summary.txt"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file "$out/launches_bench.csv" \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 5000 --csv --log-file "$out/launches_bench.csv" \
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline > "$out/bench_under_ncu.log" 2>&1; echo "ncu launch list rc=$?" | tee -a "$out/summary.txt"
 {
 run() { echo "=== $*"; timeout 300 compute-sanitizer --tool $1 --error-exitcode 9 python tools/profile_target.py "${@:2}" 2>&1 | tail -4; echo "--- exit $?"; }
