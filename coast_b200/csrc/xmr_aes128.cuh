@@ -210,6 +210,32 @@ __device__ __forceinline__ void aes_rounds(const AesLaneBases& L, uint32_t (&s)[
     }
 }
 
+// Hook path of the one-key kernels: the ten iterations as a ROLLED loop whose round keys come from a 176-byte copy in shared
+// memory (broadcast reads).  Why this shape (profiles/r02_aes_injector_ablation_*.txt, DWC, 2^24 blocks, p = 2^-10):
+//   second unrolled copy of the rounds (register keys) : 1.122 ms -- 35 KB more code; every execution evicts the fast path from the
+//                                                         instruction cache of all 16 warps (issue rate 0.49)
+//   rolled loop recomputing the key schedule            : 0.865 ms -- small, but 3x a normal tile per execution
+//   rolled loop, keys from shared memory                : this one
+template <int J, bool DEC>
+__device__ __forceinline__ void aes_rounds_hooked(const AesLaneBases& L, uint32_t (&s)[J][4], uint32_t rk_saddr,
+                                               const uint32_t (&fbit)[J], const int (&frd)[J], const int (&fcol)[J]) {
+#pragma unroll 1
+    for (int rd = 0; rd < 10; ++rd) {
+        uint32_t kr[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) kr[c] = lds32(rk_saddr + 16u * (uint32_t)(rd + 1) + 4u * c);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            uint32_t n[4];
+            if (rd < 9) aes_round_cols<DEC, false>(L, s[j], n); else aes_round_cols<DEC, true>(L, s[j], n);
+            uint32_t hit = frd[j] == rd ? fbit[j] : 0u;
+            if (DEC && rd < 9) hit = inv_mix_column(hit);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s[j][c] = n[c] ^ (fcol[j] == c ? hit : 0u) ^ kr[c];
+        }
+    }
+}
+
 // the shared-memory tables of one direction (all threads of the CTA; the caller synchronises)
 template <bool DEC>
 __device__ __forceinline__ void aes_build_tables(uint8_t* smem_raw, uint32_t win, int tid) {
@@ -262,6 +288,7 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
     //   encrypt: rk[4i..] = round key i.   decrypt: rk[0..3] = round key 10 (the first AddRoundKey, :127-129),
     //   rk[4(rd+1)..] = InvMixColumns(round key 9-rd) for rd < 9, rk[40..43] = round key 0.
     uint32_t rk[PERKEY ? 4 : 44];
+    __shared__ uint32_t rk_shared[44];                          // INJECT && !PERKEY: the hook path reads its round keys here
     if (!PERKEY) {
         uint32_t k[4];
 #pragma unroll
@@ -288,6 +315,13 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
         }
     }
 
+    if (INJECT && !PERKEY) {
+        if (tid == 0) {
+#pragma unroll
+            for (int i = 0; i < 44; ++i) rk_shared[i] = rk[i];
+        }
+        __syncthreads();
+    }
     const uint32_t n_tiles = a.n_tiles;
     uint32_t tile = blockIdx.x;
     if (tid == 0) {                                             // prologue: AES_STAGES - 1 tiles in flight
@@ -350,6 +384,10 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
                 packed[t] = (f.active && ok) ? (0x80000000u | (f.replica << 29) | (f.site << 5) | f.bit) : 0u;
             }
             bool mid = false;
+            uint32_t any_packed = 0u;
+#pragma unroll
+            for (int t = 0; t < PASSES; ++t) any_packed |= packed[t];
+            if (__any_sync(0xFFFFFFFFu, any_packed != 0u)) {    // 94 % of warp-tiles at p = 2^-10 have no hit at all: skip the distribution
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const uint32_t e = NC == 1 ? packed[j] : __shfl_sync(0xFFFFFFFFu, packed[j / NC], u * NC + j % NC);
@@ -369,6 +407,7 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
                 }
             }
             hooks = __any_sync(0xFFFFFFFFu, mid);               // warp-uniform: a warp without a mid-round hit runs the plain rounds
+            }
         }
 #pragma unroll
         for (int j = 0; j < J; ++j) {
@@ -380,21 +419,8 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
             for (int c = 0; c < 4; ++c) s[j][c] ^= PERKEY ? k[j][c] : rk[c];      // first half of :143-146 / :127-129
         }
         if (INJECT && hooks) {
-            // hook path.  XMR_AES_HOOKS_ROLLED selects a rolled loop that recomputes the round keys (small code, slow: measured 3x a
-            // normal tile, profiles/r02_aes_injector_ablation_ring3.txt); the default is a second unrolled copy of the rounds.
-#ifdef XMR_AES_HOOKS_ROLLED
-            if constexpr (PERKEY) {
-                aes_rounds<J, DEC, true, true, true>(L, s, k, rk, fbit, frd, fcol);
-            } else {
-                uint32_t kk[J][4];
-                const uint32_t none[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                for (int j = 0; j < J; ++j) { kk[j][0] = rk[0]; kk[j][1] = rk[1]; kk[j][2] = rk[2]; kk[j][3] = rk[3]; }
-                aes_rounds<J, DEC, true, true, true>(L, s, kk, none, fbit, frd, fcol);
-            }
-#else
-            aes_rounds<J, DEC, PERKEY, true>(L, s, k, rk, fbit, frd, fcol);
-#endif
+            if constexpr (PERKEY) aes_rounds<J, DEC, true, true, true>(L, s, k, rk, fbit, frd, fcol);     // per-unit keys: rolled, keys recomputed
+            else aes_rounds_hooked<J, DEC>(L, s, smem_u32(rk_shared), fbit, frd, fcol);
         } else {
             aes_rounds<J, DEC, PERKEY, false>(L, s, k, rk, fbit, frd, fcol);
         }
