@@ -418,11 +418,38 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
 #pragma unroll
             for (int c = 0; c < 4; ++c) s[j][c] ^= PERKEY ? k[j][c] : rk[c];      // first half of :143-146 / :127-129
         }
-        if (INJECT && hooks) {
-            if constexpr (PERKEY) aes_rounds<J, DEC, true, true, true>(L, s, k, rk, fbit, frd, fcol);     // per-unit keys: rolled, keys recomputed
-            else aes_rounds_hooked<J, DEC>(L, s, smem_u32(rk_shared), fbit, frd, fcol);
+        if constexpr (PERKEY) {
+            if (INJECT && hooks) aes_rounds<J, DEC, true, true, true>(L, s, k, rk, fbit, frd, fcol);     // per-unit keys: rolled, keys recomputed
+            else aes_rounds<J, DEC, true, false>(L, s, k, rk, fbit, frd, fcol);
         } else {
-            aes_rounds<J, DEC, PERKEY, false>(L, s, k, rk, fbit, frd, fcol);
+            aes_rounds<J, DEC, false, false>(L, s, k, rk, fbit, frd, fcol);      // every block through the plain rounds ...
+            if (INJECT && hooks) {
+                // ... then the (rare) blocks with a mid-round flip are RECOMPUTED alone, from their input, by a small rolled
+                // one-block loop with the hook.  The cold code a hit drags in is ~2 KB instead of a whole hooked tile: measured per
+                // execution of the J-block hook path 3 470 / 1 500 / 640 SM cycles at p = 2^-13 / 2^-10 / 2^-7 -- instruction
+                // fetch of code that is cold because it is rare (profiles/r02_aes_injector_ablation_smemkeys.txt).
+                uint32_t pend = 0u;
+#pragma unroll
+                for (int j = 0; j < J; ++j) pend |= frd[j] >= 0 ? (1u << j) : 0u;
+                while (__any_sync(0xFFFFFFFFu, pend != 0u)) {
+                    const int jj = pend ? (__ffs(pend) - 1) : -1;
+                    uint32_t x[1][4] = {{0u, 0u, 0u, 0u}}, fb1[1] = {0u};
+                    int fr1[1] = {-2}, fc1[1] = {0};
+                    unsigned long long loc = 0ull;
+#pragma unroll
+                    for (int j = 0; j < J; ++j)
+                        if (j == jj) { loc = local[j]; fb1[0] = fbit[j]; fr1[0] = frd[j]; fc1[0] = fcol[j]; }
+                    if (jj >= 0) {
+                        const uint4 q = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(a.in) + loc * 16ull));
+                        x[0][0] = q.x ^ rk[0]; x[0][1] = q.y ^ rk[1]; x[0][2] = q.z ^ rk[2]; x[0][3] = q.w ^ rk[3];
+                    }
+                    aes_rounds_hooked<1, DEC>(L, x, smem_u32(rk_shared), fb1, fr1, fc1);
+#pragma unroll
+                    for (int j = 0; j < J; ++j)
+                        if (j == jj) { s[j][0] = x[0][0]; s[j][1] = x[0][1]; s[j][2] = x[0][2]; s[j][3] = x[0][3]; }
+                    pend &= pend - 1u;
+                }
+            }
         }
 #pragma unroll
         for (int j = 0; j < J; ++j) {
