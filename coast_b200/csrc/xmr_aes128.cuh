@@ -265,6 +265,42 @@ __device__ __forceinline__ AesLaneBases aes_lane_bases(int lane) {
     return L;
 }
 
+// Deferred units of the one-key injector kernels.  A unit whose plan has a MID-ROUND flip is rare (p per block), and the code that
+// applies such a flip is therefore cold; executing it inside the tile loop cost 1 000 - 3 500 SM cycles per hit in instruction
+// fetch (profiles/r02_aes_injector_ablation_*.txt: the per-hit cost falls 9x when hits are 8x more frequent).  So the tile loop only
+// QUEUES those units (per warp, in shared memory) and this pass -- run once per warp after its last tile -- does them: each group of
+// NC adjacent lanes takes one queued unit, reloads its block, runs the ten iterations in a rolled one-block loop (round keys from
+// shared memory) with the hook on the faulted replica's lane, votes and stores exactly as the tile loop would have.
+constexpr int AES_QCAP = 128;
+template <int NC, bool DEC>
+__device__ __noinline__ void aes_drain_deferred(const xmr_args& a, uint32_t rk_saddr, uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3,
+                                                const uint32_t* q_unit, const uint32_t* q_fault, uint32_t count, int lane) {
+    constexpr int UPW = Lanes<NC>::kUnitsPerWarp;
+    if (count == 0u) return;
+    const AesLaneBases L = aes_lane_bases(lane);
+    const int r = Lanes<NC>::replica(lane), g = Lanes<NC>::unit(lane);
+    Tally tally(a);                                             // its own tally (flushed below): nothing of the caller's lives across this call
+    __syncwarp();                                               // the voter lanes' queue writes are visible to the whole warp
+    for (uint32_t base = 0; base < count; base += UPW) {
+        const uint32_t idx = base + (uint32_t)g;
+        const bool have = idx < count && (NC != 3 || lane < 30);
+        const uint32_t lu = have ? q_unit[idx] : 0u, e = have ? q_fault[idx] : 0u;
+        uint32_t x[1][4] = {{0u, 0u, 0u, 0u}}, fb[1] = {0u};
+        int fr[1] = {-2}, fc[1] = {0};
+        if (have) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(a.in) + (unsigned long long)lu * 16ull));
+            x[0][0] = q.x ^ k0; x[0][1] = q.y ^ k1; x[0][2] = q.z ^ k2; x[0][3] = q.w ^ k3;
+            if ((int)((e >> 29) & 3u) == r) {
+                const uint32_t site = (e >> 5) & 0xFFFFFFu, i = (site - 16u) & 15u;
+                fr[0] = (int)((site - 16u) >> 4); fc[0] = (int)(i >> 2); fb[0] = (1u << (e & 31u)) << (8u * (i & 3u));
+            }
+        }
+        aes_rounds_hooked<1, DEC>(L, x, rk_saddr, fb, fr, fc);
+        aes_vote_store<NC>(x[0], static_cast<uint8_t*>(a.out), (unsigned long long)lu, a.unit_base + lu, have, lane, a.flags, tally);
+    }
+    tally.flush(a.counters);
+}
+
 template <int NC, bool INJECT, bool DEC, bool PERKEY>
 __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap* tmap) {
     constexpr int UPW = Lanes<NC>::kUnitsPerWarp;
@@ -288,7 +324,10 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
     //   encrypt: rk[4i..] = round key i.   decrypt: rk[0..3] = round key 10 (the first AddRoundKey, :127-129),
     //   rk[4(rd+1)..] = InvMixColumns(round key 9-rd) for rd < 9, rk[40..43] = round key 0.
     uint32_t rk[PERKEY ? 4 : 44];
-    __shared__ uint32_t rk_shared[44];                          // INJECT && !PERKEY: the hook path reads its round keys here
+    __shared__ uint32_t rk_shared[44];                          // INJECT && !PERKEY: the deferred pass reads its round keys here
+    __shared__ uint32_t q_unit[INJECT && !PERKEY ? AES_WARPS : 1][INJECT && !PERKEY ? AES_QCAP : 1];     // per-warp queue of deferred units
+    __shared__ uint32_t q_fault[INJECT && !PERKEY ? AES_WARPS : 1][INJECT && !PERKEY ? AES_QCAP : 1];
+    uint32_t q_count = 0u;                                      // warp-uniform
     if (!PERKEY) {
         uint32_t k[4];
 #pragma unroll
@@ -365,6 +404,7 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
         // (frd = -1: the replica's input copy, before the first AddRoundKey; -2: none)
         uint32_t fbit[J]; int frd[J], fcol[J];
         bool hooks = false;
+        uint32_t defer = 0u;                                    // one-key kernels: bit j = unit of block j has a mid-round flip -> deferred (below)
 #pragma unroll
         for (int j = 0; j < J; ++j) { fbit[j] = 0u; frd[j] = -2; fcol[j] = 0; }
         if (INJECT) {
@@ -389,12 +429,24 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
             for (int t = 0; t < PASSES; ++t) any_packed |= packed[t];
             if (__any_sync(0xFFFFFFFFu, any_packed != 0u)) {    // 94 % of warp-tiles at p = 2^-10 have no hit at all: skip the distribution
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const uint32_t e = NC == 1 ? packed[j] : __shfl_sync(0xFFFFFFFFu, packed[j / NC], u * NC + j % NC);
-                if (e & 0x80000000u) {
-                    if (Lanes<NC>::voter(lane)) tally.injected++;
-                    if ((int)((e >> 29) & 3u) == r) {
-                        const uint32_t site = (e >> 5) & 0xFFFFFFu, bit = e & 31u;
+                for (int j = 0; j < J; ++j) {
+                    const uint32_t e = NC == 1 ? packed[j] : __shfl_sync(0xFFFFFFFFu, packed[j / NC], u * NC + j % NC);
+                    const uint32_t site = (e >> 5) & 0xFFFFFFu, bit = e & 31u;
+                    const bool hit = (e & 0x80000000u) != 0u;
+                    if (hit && Lanes<NC>::voter(lane)) tally.injected++;
+                    if (!PERKEY) {
+                        // ONE-KEY KERNELS: a unit with a MID-ROUND flip is not finished here.  All its replica lanes skip the vote/store
+                        // of that block; the voter lane queues (unit, fault) for the pass after the tile loop (aes_drain_deferred).
+                        const bool dq = hit && site >= 16u;
+                        if (dq) defer |= 1u << j;
+                        const uint32_t pushers = __ballot_sync(0xFFFFFFFFu, dq && Lanes<NC>::voter(lane));
+                        if (dq && Lanes<NC>::voter(lane)) {
+                            const uint32_t pos = q_count + __popc(pushers & ((1u << lane) - 1u));
+                            if (pos < (uint32_t)AES_QCAP) { q_unit[warp][pos] = (uint32_t)local[j]; q_fault[warp][pos] = e; }
+                        }
+                        q_count += __popc(pushers);             // warp-uniform
+                    }
+                    if (hit && (PERKEY || site < 16u) && (int)((e >> 29) & 3u) == r) {
                         const uint32_t i = site < 16u ? site : ((site - 16u) & 15u);
                         frd[j] = site < 16u ? -1 : (int)((site - 16u) >> 4);
                         fcol[j] = (int)(i >> 2);
@@ -405,8 +457,7 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
                         } else mid = true;
                     }
                 }
-            }
-            hooks = __any_sync(0xFFFFFFFFu, mid);               // warp-uniform: a warp without a mid-round hit runs the plain rounds
+                hooks = __any_sync(0xFFFFFFFFu, mid);           // per-unit-key kernels: a warp without a mid-round hit runs the plain rounds
             }
         }
 #pragma unroll
@@ -422,42 +473,20 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
             if (INJECT && hooks) aes_rounds<J, DEC, true, true, true>(L, s, k, rk, fbit, frd, fcol);     // per-unit keys: rolled, keys recomputed
             else aes_rounds<J, DEC, true, false>(L, s, k, rk, fbit, frd, fcol);
         } else {
-            aes_rounds<J, DEC, false, false>(L, s, k, rk, fbit, frd, fcol);      // every block through the plain rounds ...
-            if (INJECT && hooks) {
-                // ... then the (rare) blocks with a mid-round flip are RECOMPUTED alone, from their input, by a small rolled
-                // one-block loop with the hook.  The cold code a hit drags in is ~2 KB instead of a whole hooked tile: measured per
-                // execution of the J-block hook path 3 470 / 1 500 / 640 SM cycles at p = 2^-13 / 2^-10 / 2^-7 -- instruction
-                // fetch of code that is cold because it is rare (profiles/r02_aes_injector_ablation_smemkeys.txt).
-                uint32_t pend = 0u;
-#pragma unroll
-                for (int j = 0; j < J; ++j) pend |= frd[j] >= 0 ? (1u << j) : 0u;
-                while (__any_sync(0xFFFFFFFFu, pend != 0u)) {
-                    const int jj = pend ? (__ffs(pend) - 1) : -1;
-                    uint32_t x[1][4] = {{0u, 0u, 0u, 0u}}, fb1[1] = {0u};
-                    int fr1[1] = {-2}, fc1[1] = {0};
-                    unsigned long long loc = 0ull;
-#pragma unroll
-                    for (int j = 0; j < J; ++j)
-                        if (j == jj) { loc = local[j]; fb1[0] = fbit[j]; fr1[0] = frd[j]; fc1[0] = fcol[j]; }
-                    if (jj >= 0) {
-                        const uint4 q = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(a.in) + loc * 16ull));
-                        x[0][0] = q.x ^ rk[0]; x[0][1] = q.y ^ rk[1]; x[0][2] = q.z ^ rk[2]; x[0][3] = q.w ^ rk[3];
-                    }
-                    aes_rounds_hooked<1, DEC>(L, x, smem_u32(rk_shared), fb1, fr1, fc1);
-#pragma unroll
-                    for (int j = 0; j < J; ++j)
-                        if (j == jj) { s[j][0] = x[0][0]; s[j][1] = x[0][1]; s[j][2] = x[0][2]; s[j][3] = x[0][3]; }
-                    pend &= pend - 1u;
-                }
-            }
+            aes_rounds<J, DEC, false, false>(L, s, k, rk, fbit, frd, fcol);
         }
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            aes_vote_store<NC>(s[j], static_cast<uint8_t*>(a.out), local[j], a.unit_base + local[j], valid[j], lane, a.flags, tally);
+            aes_vote_store<NC>(s[j], static_cast<uint8_t*>(a.out), local[j], a.unit_base + local[j], valid[j] && !((defer >> j) & 1u), lane, a.flags, tally);
             if (PERKEY && (a.mode & 4u) && valid[j] && Lanes<NC>::voter(lane))       // COAST_AES_KEY_WRITEBACK: replica 0's mutated key[]
                 *reinterpret_cast<uint4*>(static_cast<uint8_t*>(const_cast<void*>(a.aux)) + local[j] * 16ull) = make_uint4(k[j][0], k[j][1], k[j][2], k[j][3]);
         }
+        if (INJECT && !PERKEY && q_count > (uint32_t)(AES_QCAP - J * UPW)) {        // the next tile might not fit: drain now (rare)
+            aes_drain_deferred<NC, DEC>(a, smem_u32(rk_shared), rk[0], rk[1], rk[2], rk[3], q_unit[warp], q_fault[warp], q_count, lane);
+            q_count = 0u;
+        }
     }
+    if (INJECT && !PERKEY) aes_drain_deferred<NC, DEC>(a, smem_u32(rk_shared), rk[0], rk[1], rk[2], rk[3], q_unit[warp], q_fault[warp], q_count, lane);
     tally.flush(a.counters);
 }
 
