@@ -271,10 +271,10 @@ __device__ __forceinline__ AesLaneBases aes_lane_bases(int lane) {
 // QUEUES those units (per warp, in shared memory) and this pass -- run once per warp after its last tile -- does them: each group of
 // NC adjacent lanes takes one queued unit, reloads its block, runs the ten iterations in a rolled one-block loop (round keys from
 // shared memory) with the hook on the faulted replica's lane, votes and stores exactly as the tile loop would have.
-constexpr int AES_QCAP = 128;
+constexpr int AES_QCAP = 96;                                  // entries per warp: 16 warps x 96 x 8 B = 12 KiB, placed after the ring below the first table window
 template <int NC, bool DEC>
 __device__ __noinline__ void aes_drain_deferred(const xmr_args& a, uint32_t rk_saddr, uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3,
-                                                const uint32_t* q_unit, const uint32_t* q_fault, uint32_t count, int lane) {
+                                                const uint32_t* q, uint32_t count, int lane) {
     constexpr int UPW = Lanes<NC>::kUnitsPerWarp;
     if (count == 0u) return;
     const AesLaneBases L = aes_lane_bases(lane);
@@ -284,7 +284,7 @@ __device__ __noinline__ void aes_drain_deferred(const xmr_args& a, uint32_t rk_s
     for (uint32_t base = 0; base < count; base += UPW) {
         const uint32_t idx = base + (uint32_t)g;
         const bool have = idx < count && (NC != 3 || lane < 30);
-        const uint32_t lu = have ? q_unit[idx] : 0u, e = have ? q_fault[idx] : 0u;
+        const uint32_t lu = have ? q[2u * idx] : 0u, e = have ? q[2u * idx + 1u] : 0u;
         uint32_t x[1][4] = {{0u, 0u, 0u, 0u}}, fb[1] = {0u};
         int fr[1] = {-2}, fc[1] = {0};
         if (have) {
@@ -307,12 +307,15 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
     constexpr int J = AesGeom<NC>::J;
     constexpr int TROWS = AesGeom<NC>::TROWS;
     using Ring = AesRing<TROWS>;
-    static_assert(Ring::SMEM_BYTES + 1024u + 1024u <= AES_TAB01, "the ring must end below the first table window");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t win = smem_u32(smem_raw);                    // shared-window address of the dynamic region
     uint8_t* ring_mem = smem_raw + ((1024u - (win & 1023u)) & 1023u);
     Ring ring;
     ring.init(ring_mem, tmap, (a.mode >> 8) & 15u);             // XMR_AES_ROWPACK: 16-byte blocks described as 64- or 256-byte rows
+    // per-warp queue of deferred units (INJECT, one-key kernels): {unit, fault} pairs right after the ring, still below the tables
+    constexpr uint32_t Q_OFF = (Ring::SMEM_BYTES + 127u) & ~127u;
+    static_assert(Q_OFF + (uint32_t)AES_WARPS * AES_QCAP * 8u + 2048u + 1024u <= AES_TAB01, "ring + queues must end below the first table window");
+    uint32_t* const q_mine = reinterpret_cast<uint32_t*>(ring_mem + Q_OFF) + (size_t)(threadIdx.x >> 5) * AES_QCAP * 2u;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     aes_build_tables<DEC>(smem_raw, win, tid);
     __syncthreads();
@@ -325,9 +328,7 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
     //   rk[4(rd+1)..] = InvMixColumns(round key 9-rd) for rd < 9, rk[40..43] = round key 0.
     uint32_t rk[PERKEY ? 4 : 44];
     __shared__ uint32_t rk_shared[44];                          // INJECT && !PERKEY: the deferred pass reads its round keys here
-    __shared__ uint32_t q_unit[INJECT && !PERKEY ? AES_WARPS : 1][INJECT && !PERKEY ? AES_QCAP : 1];     // per-warp queue of deferred units
-    __shared__ uint32_t q_fault[INJECT && !PERKEY ? AES_WARPS : 1][INJECT && !PERKEY ? AES_QCAP : 1];
-    uint32_t q_count = 0u;                                      // warp-uniform
+    uint32_t q_count = 0u;                                      // entries in this warp's queue of deferred units (warp-uniform)
     if (!PERKEY) {
         uint32_t k[4];
 #pragma unroll
@@ -442,7 +443,7 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
                         const uint32_t pushers = __ballot_sync(0xFFFFFFFFu, dq && Lanes<NC>::voter(lane));
                         if (dq && Lanes<NC>::voter(lane)) {
                             const uint32_t pos = q_count + __popc(pushers & ((1u << lane) - 1u));
-                            if (pos < (uint32_t)AES_QCAP) { q_unit[warp][pos] = (uint32_t)local[j]; q_fault[warp][pos] = e; }
+                            if (pos < (uint32_t)AES_QCAP) { q_mine[2u * pos] = (uint32_t)local[j]; q_mine[2u * pos + 1u] = e; }
                         }
                         q_count += __popc(pushers);             // warp-uniform
                     }
@@ -482,11 +483,11 @@ __device__ __forceinline__ void aes128_body(const xmr_args& a, const CUtensorMap
                 *reinterpret_cast<uint4*>(static_cast<uint8_t*>(const_cast<void*>(a.aux)) + local[j] * 16ull) = make_uint4(k[j][0], k[j][1], k[j][2], k[j][3]);
         }
         if (INJECT && !PERKEY && q_count > (uint32_t)(AES_QCAP - J * UPW)) {        // the next tile might not fit: drain now (rare)
-            aes_drain_deferred<NC, DEC>(a, smem_u32(rk_shared), rk[0], rk[1], rk[2], rk[3], q_unit[warp], q_fault[warp], q_count, lane);
+            aes_drain_deferred<NC, DEC>(a, smem_u32(rk_shared), rk[0], rk[1], rk[2], rk[3], q_mine, q_count, lane);
             q_count = 0u;
         }
     }
-    if (INJECT && !PERKEY) aes_drain_deferred<NC, DEC>(a, smem_u32(rk_shared), rk[0], rk[1], rk[2], rk[3], q_unit[warp], q_fault[warp], q_count, lane);
+    if (INJECT && !PERKEY) aes_drain_deferred<NC, DEC>(a, smem_u32(rk_shared), rk[0], rk[1], rk[2], rk[3], q_mine, q_count, lane);
     tally.flush(a.counters);
 }
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-out=gpurun_out/r02aes6
+out=gpurun_out/r02aes7
 mkdir -p "$out"
 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_chstone_aes.py -m gpu -x -q -k "aes or host_call or fuzz or reference_entry" > "$out/pytest.log" 2>&1; echo "pytest rc=$?"; tail -3 "$out/pytest.log"
 {
