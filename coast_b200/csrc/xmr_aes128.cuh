@@ -17,9 +17,10 @@
 // Fault sites (identical in oracle/): 0..15 = state byte as loaded; 16+16r+i = state[i] at the bottom of main-loop
 // iteration r (:132-223).  A flip there is XOR-linear through the following AddRoundKey (and, for decrypt, through the
 // following InvMixColumns), which is why the kernel can apply it to its fused values.
-// Injector cost (r02): the Philox decision of a unit is evaluated by ONE of its replica lanes and shuffled to the others,
-// and the per-round hooks sit behind a warp-uniform branch, so a warp none of whose blocks is hit runs the instruction
-// stream of the injector-free kernel.
+// Injector (r02, profiles/r02_aes_injector.md): the Philox draw of a unit is evaluated by ONE of its replica lanes and shuffled to the
+// others; a unit whose flip lands mid-round is not finished in the tile loop but queued per warp and done in one pass after the
+// last tile (aes_drain_deferred), because the code that applies such a flip is cold exactly because it is rare; the tile ring has no
+// CTA-wide barrier (AesRing), so warps do not advance in lock-step.  DWC, 2^24 blocks, p = 2^-10: 0.740 ms vs 0.6845 ms without.
 #pragma once
 #include "xmr_common.cuh"
 #include "aes_tables.inc"
