@@ -14,8 +14,11 @@ with its own roofline / e2e / cpu_baseline):
   python bench.py --impl reference ...                      # the reference's own C sources (oracle/_ref, else the
                                                             # oracle port) under CPU xMR, all host threads
 Under torchrun (N>1) every rank works on its own shard (no data-path collective).  The ranks rendezvous ON THE GPU
-(a 1-element all-reduce on the compute stream) right before the start event, and the only exchange of the path --
-the 4 fault counters -- happens ONCE per timed region, where the program would read them (coast_sync), inside the region.
+(a 1-element all-reduce on the compute stream) right before the start event.  The only exchange of the path -- the fault
+counters -- is done BY THE KERNELS: ranks 1..N-1 map rank 0's counter block over NVLink (coast_counters_attach) and every
+kernel's closing tally is a handful of system-scope atomics into it, so the timed region holds no collective at all and
+rank 0's coast_sync() reads the whole job's TMR_ERROR_CNT / __SYNC_COUNT.  (Without peer access the fallback is ONE NCCL
+all-reduce of the 4 counters per timed region, inside the region; `collectives.counter_fold` says which ran.)
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -446,10 +449,17 @@ def measure(cx, wl: str, steps: int, warmup: int, *, cpu_budget_s: float = 0.0, 
 
     sampler = cx.sampler
     sampler.reset()
-    rt.sync()
+    peer_fold = dist is not None and cx.peer_handle is not None
+    if peer_fold:
+        fence()
+        if rank != 0:
+            rt.counters_attach(cx.peer_handle)             # from here on this rank's kernels tally into rank 0's block over NVLink
+    rt.sync()                                              # (rank 0 resets the shared block; an attached rank's sync only drains its stream)
+    if peer_fold:
+        fence()                                            # nobody launches before the owner's reset has landed
     for i in range(warmup):
         step(i)
-    if dist is not None:
+    if dist is not None and not peer_fold:
         exchange_counters()
     fence()
     launches = 0
@@ -460,16 +470,27 @@ def measure(cx, wl: str, steps: int, warmup: int, *, cpu_budget_s: float = 0.0, 
     e0.record()
     for i in range(steps):
         step(i)
-    if dist is not None:
-        exchange_counters()                                # inside the timed region, once -- where coast_sync() would fold them
+    if dist is not None and not peer_fold:
+        exchange_counters()                                # fallback: inside the timed region, once -- where coast_sync() would fold them
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     timed_launches = launches
-    st = rt.sync()                                         # fold this rank's counters (outside the timed region)
+    if peer_fold:
+        dist.barrier()                                     # every rank's kernels (and their remote atomics) have retired
+    st = rt.sync()                                         # rank 0: the counters of the whole job (peer fold) / of this rank
+    if peer_fold:
+        units_all = torch.tensor([n], dtype=torch.int64, device=dev)
+        dist.all_reduce(units_all)                         # units of all ranks, for the check below (outside the timed region)
+        n_counted = int(units_all[0]) if rank == 0 else 0
+        fence()
+        if rank != 0:
+            rt.counters_detach()                           # the single-launch loop and the host calls below tally locally again
+    else:
+        n_counted = n
     if wl.startswith("sha256"):
-        assert st.errors_corrected == 0 and st.syncs == 32 * n * (steps + warmup), st
-    if wl == "aes":
+        assert st.errors_corrected == 0 and st.syncs == 32 * n_counted * (steps + warmup), (st, n_counted)
+    if wl == "aes" and (rank == 0 or not peer_fold):
         assert st.dwc_detected == st.injected > 0, st      # detect-rate parity: every state flip is detected
 
     # kernel-only duration (cross-check of the roofline's average) and enough GPU-busy time for >= 20 clock samples:
@@ -491,7 +512,7 @@ def measure(cx, wl: str, steps: int, warmup: int, *, cpu_budget_s: float = 0.0, 
     k_ms = statistics.median(kms) if kms else 0.0
 
     coll_in_value_ms = 0.0
-    if dist is not None:                                   # what the one counter exchange costs, measured on its own
+    if dist is not None and not peer_fold:                 # what the one counter exchange costs, measured on its own
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.all_reduce(go)
         a.record()
@@ -654,8 +675,12 @@ def measure(cx, wl: str, steps: int, warmup: int, *, cpu_budget_s: float = 0.0, 
         "stats_last_sync": st.as_dict(),
     }
     if world > 1:
-        line["collectives"] = {"in_value": "GPU-side rendezvous before the start event + ONE all-reduce of the 4 counters per timed region "
-                                           "(where coast_sync() folds them); no per-step collective",
+        line["collectives"] = {"counter_fold": "nvlink-peer-atomics" if peer_fold else "nccl-allreduce",
+                               "in_value": ("GPU-side rendezvous before the start event; NO collective in the timed region: ranks 1..N-1 map rank 0's "
+                                            "counter block over NVLink (coast_counters_attach) and every kernel's closing tally is a few system-scope "
+                                            "atomics into it; stats_last_sync is the whole job's fold read by rank 0's coast_sync()") if peer_fold else
+                                           ("GPU-side rendezvous before the start event + ONE all-reduce of the 4 counters per timed region "
+                                            "(where coast_sync() folds them); no per-step collective"),
                                "in_value_ms": round(coll_in_value_ms, 4), "in_value_ms_per_step": round(coll_in_value_ms / steps, 5),
                                "allgather_outputs_ms": round(coll_ms[0], 4) if coll_ms[0] else None,
                                "allgather_bytes": world * total_out_bytes // world if coll_ms[0] else None,
@@ -689,6 +714,24 @@ def run_ours(args):
         cx.dist = dist
     cx.dev = f"cuda:{local}"
     cx.sampler = ClockSampler(local)
+    cx.peer_handle = None
+    if cx.dist is not None and os.environ.get("COAST_BENCH_COUNTER_FOLD", "peer") == "peer":
+        # rank 0 exports its counter block (a 64-byte CUDA IPC handle), everyone else will map it over NVLink
+        h = torch.zeros(64, dtype=torch.uint8, device=cx.dev)
+        if cx.rank == 0:
+            h.copy_(torch.frombuffer(bytearray(cx.rt.counters_export()), dtype=torch.uint8))
+        cx.dist.broadcast(h, src=0)
+        handle = bytes(h.cpu().numpy().tobytes())
+        ok = torch.ones(1, dtype=torch.int32, device=cx.dev)
+        if cx.rank != 0:
+            try:                                           # probe: attach + detach once; no peer access -> every rank falls back together
+                cx.rt.counters_attach(handle); cx.rt.counters_detach()
+            except Exception as exc:
+                print(f"bench: peer counter block unavailable on rank {cx.rank}: {exc}", file=sys.stderr)
+                ok.zero_()
+        cx.dist.all_reduce(ok, op=cx.dist.ReduceOp.MIN)
+        if int(ok[0]) == 1:
+            cx.peer_handle = handle
 
     main_cpu = 0.0 if args.no_cpu_baseline else 10.0
     line = measure(cx, args.workload, args.steps, args.warmup, cpu_budget_s=main_cpu)

@@ -79,6 +79,9 @@ __attribute__((weak)) void FAULT_DETECTED_DWC(void) { /* synchronization.cpp:125
     X(cuEventDestroy_v2, (CUevent))                                                                          \
     X(cuStreamWaitEvent, (CUstream, CUevent, unsigned int))                                                  \
     X(cuGetErrorString, (CUresult, const char**))                                                            \
+    X(cuIpcGetMemHandle, (CUipcMemHandle*, CUdeviceptr))                                                     \
+    X(cuIpcOpenMemHandle_v2, (CUdeviceptr*, CUipcMemHandle, unsigned int))                                   \
+    X(cuIpcCloseMemHandle, (CUdeviceptr))                                                                    \
     X(cuTensorMapEncodeTiled, (CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,      \
                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, \
                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill))
@@ -97,6 +100,7 @@ static struct {
     CUmodule mod;
     int sm_count;
     CUdeviceptr counters;            /* XMR_CTR_COUNT x u64 */
+    CUdeviceptr peer_counters;       /* coast_counters_attach(): ANOTHER GPU's counter block, mapped over NVLink (0: not attached) */
     uint64_t* h_counters;            /* pinned mirror */
     struct { char name[64]; CUfunction fn; int ctas_per_sm; unsigned smem; } fns[MAX_FN];
     int n_fns;
@@ -328,6 +332,7 @@ static int shutdown_impl(void) {
         G.h_in_cap[i] = G.h_out_cap[i] = G.h_aux_cap[i] = G.h_stat_cap[i] = 0; G.hs[i] = NULL;
     }
     G.n_tmaps = G.tmap_next = 0;
+    if (G.peer_counters) { p_cuIpcCloseMemHandle(G.peer_counters); G.peer_counters = 0; }
     p_cuMemFree_v2(G.counters);
     if (G.pool) { p_cuMemPoolDestroy(G.pool); G.pool = NULL; }
     p_cuMemFreeHost(G.h_counters);
@@ -518,7 +523,7 @@ static int launch_gemm_tf32(const coast_launch_desc* d, xmr_args* a, int inj, CU
     unsigned grid = tiles < (unsigned)G.sm_count ? tiles : (unsigned)G.sm_count;
     void* params[3] = { a, &ma, &mb };
     if (d->flags & COAST_F_VERBOSE) fprintf(stderr, "coast_rt: %s grid=%u smem=%u tiles=%u\n", name, grid, GEMM_SMEM, tiles);
-    DRV(p_cuLaunchKernel(fn, grid, 1, 1, 256, 1, 1, GEMM_SMEM, stream, params, NULL));
+    DRV(p_cuLaunchKernel(fn, grid, 1, 1, 384, 1, 1, GEMM_SMEM, stream, params, NULL));
     return COAST_OK;
 }
 
@@ -593,7 +598,7 @@ static int launch_impl(const coast_launch_desc* d, void* stream) {
     xmr_args a; memset(&a, 0, sizeof a);
     a.in = d->d_in; a.out = d->d_out; a.aux = d->d_aux;
     a.n_units = d->n_units; a.unit_base = d->unit_base;
-    a.counters = (unsigned long long*)G.counters;
+    a.counters = (unsigned long long*)(G.peer_counters ? G.peer_counters : G.counters);
     a.status = (unsigned char*)d->d_status;
     a.unit_bytes = d->unit_bytes; a.flags = d->flags; a.mode = d->mode;
     a.M = d->M; a.N = d->N; a.K = d->K;
@@ -782,6 +787,12 @@ static int launch_impl(const coast_launch_desc* d, void* stream) {
  * handler AFTER the single-caller guard is released (a user handler may longjmp or call back into the library). */
 static int sync_impl(void* stream, coast_stats* out, int* dwc_fired) {
     int rc = ensure_ctx(); if (rc) return rc;
+    if (G.peer_counters) {           /* this GPU's tallies live in the owner's block: wait for the kernels, report nothing */
+        DRV(p_cuStreamSynchronize((CUstream)stream));
+        if (out) { memset(out, 0, sizeof *out); out->first_fault_unit = ~0ull; }
+        if (dwc_fired) *dwc_fired = 0;
+        return COAST_OK;
+    }
     DRV(p_cuMemcpyDtoHAsync_v2(G.h_counters, G.counters, XMR_CTR_COUNT * sizeof(uint64_t), (CUstream)stream));
     rc = stats_reset_impl(stream); if (rc) return rc;
     DRV(p_cuStreamSynchronize((CUstream)stream));
@@ -807,6 +818,43 @@ static int sync_guarded(void* stream, coast_stats* out, int call_handler) {
 int coast_sync(void* stream, coast_stats* out) { return sync_guarded(stream, out, 1); }
 int coast_sync_noabort(void* stream, coast_stats* out) { return sync_guarded(stream, out, 0); }
 int coast_launch(const coast_launch_desc* d, void* stream) { ENTER(); LEAVE(launch_impl(d, stream)); }
+
+/* Multi-GPU counter fold in the kernels themselves (no collective): the owner exports its counter block, the other ranks
+ * map it (CUDA IPC, peer access over NVLink) and every later kernel of theirs adds its tallies there with system-scope
+ * atomics (Tally::flush).  The owner's coast_sync() then reads the sum over all attached GPUs; the caller orders it after
+ * the other ranks' stream synchronisation (a barrier).  An attached rank's coast_sync() waits for its stream and reports zeros. */
+int coast_counters_export(void* handle) {
+    ENTER();
+    int rc = ensure_ctx(); if (rc) LEAVE(rc);
+    if (!handle) LEAVE(fail(COAST_ERR_BAD_ARG, "null handle"));
+    CUipcMemHandle h;
+    CUresult r = p_cuIpcGetMemHandle(&h, G.counters);
+    if (r != CUDA_SUCCESS) LEAVE(drv_fail(r, "cuIpcGetMemHandle(counters)"));
+    memcpy(handle, &h, sizeof h);
+    LEAVE(COAST_OK);
+}
+int coast_counters_attach(const void* handle) {
+    ENTER();
+    int rc = ensure_ctx(); if (rc) LEAVE(rc);
+    if (!handle) LEAVE(fail(COAST_ERR_BAD_ARG, "null handle"));
+    if (G.peer_counters) LEAVE(fail(COAST_ERR_BAD_ARG, "already attached to a peer's counter block (coast_counters_detach first)"));
+    CUipcMemHandle h; memcpy(&h, handle, sizeof h);
+    CUdeviceptr p = 0;
+    CUresult r = p_cuIpcOpenMemHandle_v2(&p, h, CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS);
+    if (r != CUDA_SUCCESS) LEAVE(drv_fail(r, "cuIpcOpenMemHandle(peer counters): no peer access to the owner's GPU?"));
+    G.peer_counters = p;
+    LEAVE(COAST_OK);
+}
+int coast_counters_detach(void) {
+    ENTER();
+    int rc = ensure_ctx(); if (rc) LEAVE(rc);
+    if (G.peer_counters) {
+        CUresult r = p_cuIpcCloseMemHandle(G.peer_counters);
+        G.peer_counters = 0;
+        if (r != CUDA_SUCCESS) LEAVE(drv_fail(r, "cuIpcCloseMemHandle(peer counters)"));
+    }
+    LEAVE(COAST_OK);
+}
 
 int coast_stats_snapshot(void* stream, void* d_stats_out) {
     ENTER();

@@ -182,12 +182,13 @@ struct Tally {
         uint32_t fhi = __reduce_min_sync(0xFFFFFFFFu, (uint32_t)(first >> 32));
         uint32_t flo = __reduce_min_sync(0xFFFFFFFFu, (uint32_t)(first >> 32) == fhi ? (uint32_t)first : 0xFFFFFFFFu);
         if ((threadIdx.x & 31) == 0) {
-            if (e) atomicAdd(ctr + XMR_CTR_ERRORS, (unsigned long long)e);
-            if (d) atomicAdd(ctr + XMR_CTR_DWC, (unsigned long long)d);
-            if (s) atomicAdd(ctr + XMR_CTR_SYNCS, (unsigned long long)s);
-            if (j) atomicAdd(ctr + XMR_CTR_INJECTED, (unsigned long long)j);
+            // system scope: the block may be ANOTHER GPU's, mapped over NVLink (coast_counters_attach) -- the multi-GPU fold
+            if (e) atomicAdd_system(ctr + XMR_CTR_ERRORS, (unsigned long long)e);
+            if (d) atomicAdd_system(ctr + XMR_CTR_DWC, (unsigned long long)d);
+            if (s) atomicAdd_system(ctr + XMR_CTR_SYNCS, (unsigned long long)s);
+            if (j) atomicAdd_system(ctr + XMR_CTR_INJECTED, (unsigned long long)j);
             unsigned long long f = ((unsigned long long)fhi << 32) | flo;
-            if (f != ~0ull) atomicMin(ctr + XMR_CTR_FIRST, f);
+            if (f != ~0ull) atomicMin_system(ctr + XMR_CTR_FIRST, f);
         }
     }
 };

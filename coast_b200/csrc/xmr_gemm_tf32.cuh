@@ -17,8 +17,8 @@
 // Unit = one C element (the `mm_t` store, mm_common_tmr.c:16); local unit index = i*N + j.
 // Fault site 0 = the replica's final accumulator value (32 bits) as read back for the vote.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4..7 = epilogue (TMEM lane quarter = warp % 4).  Persistent CTAs, one per SM.
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4..11 = epilogue (TMEM lane quarter = warp % 4, column half = (warp - 4) / 4).  Persistent CTAs, one per SM.
 //
 // r02: an SS-mode kind::tf32 MMA of 128 x 128 x 8 reads 8 KiB of operands from shared memory for 64 tensor-pipe cycles =
 // 128 B/clk, exactly the SM's shared-memory bandwidth -- the r01 kernels were shared-memory-read bound (ncu: tensor pipe
@@ -38,6 +38,7 @@ constexpr int BM = 128, BK = 32;                     // BK fp32 = 128 bytes = on
 constexpr int UMMA_K = 8;                            // 32 bytes of tf32
 constexpr uint32_t A_STAGE = BM * BK * 4;            // 16 KiB
 constexpr uint32_t TMEM_COLS = 512;
+constexpr int CTA_THREADS = 384, EPI_THREADS = 256;     // warps 0-2 = TMA / MMA / TMEM alloc, warp 3 idle, warps 4-11 = epilogue
 template <int NC, bool WIDE = (NC == 1)> struct Geom {         // WIDE: 128 x 256 tiles (unprotected, N % 256 == 0)
     static constexpr int BN = WIDE ? 256 : 128;
     static constexpr int STAGES = WIDE ? 4 : 6;
@@ -168,7 +169,7 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(map_a); tma_prefetch_desc(map_b);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < ACC_BUFS; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+        for (int b = 0; b < ACC_BUFS; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_THREADS); }
         fence_barrier_init();
     }
     if (warp == 2) {                                            // one warp allocates TMEM and later frees it
@@ -247,6 +248,7 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers, vote, count, ONE store =====
         const int q = warp & 3;                                 // TMEM lane quarter this warp may touch
+        const int half = (warp - 4) >> 2;                       // two warps per quarter, each takes half of the tile's columns
         const uint32_t flags = a.flags;
         const bool majority = flags & COAST_F_MAJORITY_D;
         float* C = static_cast<float*>(a.out);
@@ -263,7 +265,7 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
             const uint32_t row = m0 + q * 32 + lane;
             const uint32_t lane_addr = tmem_base + buf * (uint32_t)(NC * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                 uint32_t v[3][32];
 #pragma unroll
                 for (int r = 0; r < NC; ++r) tc_ld_32x32(lane_addr + r * BN + c0, v[r]);
@@ -300,7 +302,7 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tmem_empty[buf]);                      // 128 arrivals release this accumulator set
+            mbar_arrive(&tmem_empty[buf]);                      // EPI_THREADS arrivals release this accumulator set
         }
         tally.flush(a.counters);
     }
@@ -316,7 +318,7 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
 }  // namespace xmr
 
 #define XMR_GEMM_KERNEL(NC, INJ)                                                                         \
-    extern "C" __global__ void __launch_bounds__(256, 1)                                                 \
+    extern "C" __global__ void __launch_bounds__(xmr::gemm::CTA_THREADS, 1)                                                 \
     xmr_gemm_tf32_nc##NC##_inj##INJ(const __grid_constant__ xmr_args a, const __grid_constant__ CUtensorMap map_a, \
                                     const __grid_constant__ CUtensorMap map_b) {                         \
         xmr::gemm::gemm_body<NC, INJ != 0>(a, &map_a, &map_b);                                           \
@@ -325,7 +327,7 @@ XMR_GEMM_KERNEL(1, 0) XMR_GEMM_KERNEL(2, 0) XMR_GEMM_KERNEL(3, 0)
 XMR_GEMM_KERNEL(1, 1) XMR_GEMM_KERNEL(2, 1) XMR_GEMM_KERNEL(3, 1)
 // unprotected, N a multiple of 128 but not of 256: 128 x 128 tiles (shared-memory operands, two accumulator buffers)
 #define XMR_GEMM_KERNEL_NARROW(INJ)                                                                      \
-    extern "C" __global__ void __launch_bounds__(256, 1)                                                 \
+    extern "C" __global__ void __launch_bounds__(xmr::gemm::CTA_THREADS, 1)                                                 \
     xmr_gemm_tf32n_nc1_inj##INJ(const __grid_constant__ xmr_args a, const __grid_constant__ CUtensorMap map_a, \
                                 const __grid_constant__ CUtensorMap map_b) {                             \
         xmr::gemm::gemm_body<1, INJ != 0, false>(a, &map_a, &map_b);                                     \

@@ -242,6 +242,22 @@ int  coast_sync_noabort(void* stream, coast_stats* out);
  * `d_stats_out` variant: enqueue a D2D copy of the 5 counters (5 x u64) on `stream`, for
  * callers that all-reduce them across GPUs (NCCL) before looking at them. */
 int  coast_stats_snapshot(void* stream, void* d_stats_out /* 5 x uint64_t on device */);
+
+/* Multi-GPU fold of the counters inside the kernels, over NVLink peer memory, instead of a collective (the
+ * only exchange of the sharded path is the 40-byte counter block).  One process per GPU:
+ *   owner  : coast_counters_export(handle)         -> 64 opaque bytes (a CUDA IPC handle of its counter block); ship them
+ *            to the other ranks any way you like (a file, a pipe, torch.distributed);
+ *   others : coast_counters_attach(handle)         -> every later kernel of this process adds its TMR_ERROR_CNT /
+ *            __SYNC_COUNT / DWC / injected tallies (and min-folds first_fault_unit) into the OWNER's block with
+ *            system-scope atomics; coast_sync() here waits for the stream and reports zeros, coast_stats_reset() is the
+ *            owner's business;
+ *   owner  : coast_sync() AFTER the others' streams have drained (a barrier of the caller's) reads the sum over all GPUs,
+ *            folds it into TMR_ERROR_CNT / __SYNC_COUNT and calls FAULT_DETECTED_DWC() if any GPU saw a DWC mismatch.
+ * Needs peer access between the GPUs (NVLink/NVSwitch or PCIe P2P); attach fails loudly otherwise. */
+#define COAST_COUNTERS_HANDLE_BYTES 64
+int  coast_counters_export(void* handle /* COAST_COUNTERS_HANDLE_BYTES */);
+int  coast_counters_attach(const void* handle);
+int  coast_counters_detach(void);
 int  coast_stats_reset(void* stream);
 
 /* --- fault-site geometry (shared by oracle and kernels) ------------- */

@@ -173,6 +173,32 @@ def main():
             r["second"] = [st2.errors_corrected, st2.dwc_detected, st2.syncs, st2.injected, st2.first_fault_unit]
             L.coast_free(buf)
             out.append(r)
+        elif kind == "peer_counters":                       # multi-GPU fold over peer memory: a second block stands in for the owner's
+            L.coast_counters_export.argtypes = [C.c_void_p]
+            L.coast_counters_attach.argtypes = [C.c_void_p]
+            own = C.create_string_buffer(64)
+            r = {"export": L.coast_counters_export(own)}
+            peer = dmalloc(40)                              # "the owner's block" (the mock's IPC handle is the pointer itself)
+            C.memmove(peer, bytes(32) + b"\xff" * 8, 40)
+            h = C.create_string_buffer(bytes(C.c_uint64(peer)) + bytes(56), 64)
+            r["attach"] = L.coast_counters_attach(h); r["attach_err"] = L.coast_last_error().decode() if r["attach"] else ""
+            r["attach_twice"] = L.coast_counters_attach(h) if r["attach"] == 0 else None
+            buf = dmalloc(1 << 16)
+            d.kernel, d.num_clones, d.n_units, d.unit_bytes, d.flags = 1, 3, 100, 64, 3
+            d.d_in, d.d_out = buf, buf
+            r["launch"] = L.coast_launch(C.byref(d), None)
+            st = R._Stats()
+            r["sync_attached"] = L.coast_sync_noabort(None, C.byref(st))
+            r["stats_attached"] = [st.errors_corrected, st.dwc_detected, st.syncs, st.injected, st.first_fault_unit]
+            r["peer_block"] = list((C.c_uint64 * 5).from_address(peer))
+            r["peer_ptr"] = peer
+            r["detach"] = L.coast_counters_detach()
+            r["launch_local"] = L.coast_launch(C.byref(d), None)
+            r["sync_local"] = L.coast_sync_noabort(None, C.byref(st))
+            r["stats_local"] = [st.errors_corrected, st.dwc_detected, st.syncs, st.injected, st.first_fault_unit]
+            r["peer_block_after"] = list((C.c_uint64 * 5).from_address(peer))
+            L.coast_free(buf); L.coast_free(peer)
+            out.append(r)
         elif kind == "shutdown":
             out.append({"rc": L.coast_shutdown()})
     res["ops"] = out

@@ -192,6 +192,13 @@ CUresult cuEventRecord(CUevent e, CUstream s) { (void)e; LOG("{\"op\":\"event_re
 CUresult cuEventDestroy_v2(CUevent e) { (void)e; return CUDA_SUCCESS; }
 CUresult cuStreamWaitEvent(CUstream s, CUevent e, unsigned int f) { (void)e; (void)f; LOG("{\"op\":\"wait_event\",\"stream\":%d}", stream_id(s)); return CUDA_SUCCESS; }
 CUresult cuGetErrorString(CUresult r, const char** s) { (void)r; *s = "mock driver error"; return CUDA_SUCCESS; }
+/* IPC: the "handle" is the pointer itself; MOCK_IPC_FAIL=1 makes the open fail (no peer access) */
+CUresult cuIpcGetMemHandle(CUipcMemHandle* h, CUdeviceptr p) { memset(h, 0, sizeof *h); memcpy(h, &p, sizeof p); LOG("{\"op\":\"ipc_get\",\"ptr\":%llu}", (unsigned long long)p); return CUDA_SUCCESS; }
+CUresult cuIpcOpenMemHandle_v2(CUdeviceptr* p, CUipcMemHandle h, unsigned int flags) {
+    if (getenv("MOCK_IPC_FAIL")) return CUDA_ERROR_PEER_ACCESS_UNSUPPORTED;
+    memcpy(p, &h, sizeof *p); LOG("{\"op\":\"ipc_open\",\"ptr\":%llu,\"flags\":%u}", (unsigned long long)*p, flags); return CUDA_SUCCESS;
+}
+CUresult cuIpcCloseMemHandle(CUdeviceptr p) { LOG("{\"op\":\"ipc_close\",\"ptr\":%llu}", (unsigned long long)p); return CUDA_SUCCESS; }
 
 CUresult cuTensorMapEncodeTiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank, void* addr, const cuuint64_t* gdim,
                                 const cuuint64_t* gstr, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapInterleave il,

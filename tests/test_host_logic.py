@@ -183,7 +183,7 @@ def test_tf32_gemm_launch(mock_dir, tmp_path):
                                                   aux_bytes=s * s * 4, out_bytes=s * s * 4, flags=3)])
     assert res["ops"][0]["rc"] == 0 and not [e for e in ev if e["op"] == "error"]
     la = [e for e in ev if e["op"] == "launch" and "_nc" in e["name"]][0]
-    assert la["name"] == "xmr_gemm_tf32_nc3_inj0" and la["block"] == 256 and la["grid"] == 16 and la["smem"] <= 232448
+    assert la["name"] == "xmr_gemm_tf32_nc3_inj0" and la["block"] == 384 and la["grid"] == 16 and la["smem"] <= 232448
     tm = [e for e in ev if e["op"] == "tmap"]
     assert [t["rank"] for t in tm] == [2, 3] and tm[1]["swizzle"] != tm[0]["swizzle"]      # B: the 32-byte-atom swizzle of the MN-major operand
     bad, _ = run_child(mock_dir, tmp_path, [dict(op="launch", kernel=K_GEMM_TF32, nc=3, n=100 * 128, M=100, N=128, K=64, in_bytes=100 * 64 * 4,
@@ -319,6 +319,27 @@ def test_sync_folds_counters_into_the_reference_symbols(mock_dir, tmp_path):
     assert a["launch"] == 0 and a["sync"] == 0 and a["stats"] == [2 ** 32 + 5, 0, 3200, 7, 41]
     assert a["TMR_ERROR_CNT"] == 5 and a["SYNC_COUNT"] == 3200 and a["second"] == [0, 0, 0, 0, 2 ** 64 - 1]
     assert b["TMR_ERROR_CNT"] == 10 and b["SYNC_COUNT"] == 6400         # the symbols accumulate over the program, like the pass's globals
+
+
+def test_peer_counter_block_receives_the_tallies_of_an_attached_process(mock_dir, tmp_path):
+    """coast_counters_attach(): every later kernel's argument block points at the OWNER's counters (the multi-GPU fold over NVLink
+    peer memory, no collective); the attached process's coast_sync() reports zeros and never resets the owner's block; detach
+    restores the local block; no peer access -> a loud error, not a silent local tally"""
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="peer_counters"), dict(op="shutdown")], env_extra={"MOCK_CUDA_TALLY": "4,0,3200,7,41"})
+    r = res["ops"][0]
+    assert r["export"] == 0 and r["attach"] == 0 and r["attach_twice"] != 0 and r["launch"] == 0 and r["sync_attached"] == 0
+    launches = [e for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
+    assert len(launches) == 2
+    assert args_of(launches[0]).counters == r["peer_ptr"] != args_of(launches[1]).counters
+    assert r["stats_attached"] == [0, 0, 0, 0, 2 ** 64 - 1]
+    assert r["peer_block"] == [4, 0, 3200, 7, 41] == r["peer_block_after"]          # attached sync did not reset it; the local run did not touch it
+    assert r["detach"] == 0 and r["stats_local"] == [4, 0, 3200, 7, 41]
+    opens = [e for e in ev if e["op"] == "ipc_open"]
+    assert len(opens) == 1 and opens[0]["flags"] == 1                                # CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS
+    assert [e for e in ev if e["op"] == "ipc_close"]
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="peer_counters")], env_extra={"MOCK_IPC_FAIL": "1"})
+    r = res["ops"][0]
+    assert r["attach"] != 0 and "peer" in r["attach_err"]
 
 
 def test_dwc_detection_calls_the_handler_which_aborts_by_default(mock_dir, tmp_path):
