@@ -498,6 +498,8 @@ static int launch_gemm_tf32(const coast_launch_desc* d, xmr_args* a, int inj, CU
     { const char* g = getenv("COAST_GEMM_GROUP_M"); if (g && atoi(g) > 0 && atoi(g) < 256) a->mode = (a->mode & ~0xFFu) | (unsigned)atoi(g); }
     /* L2 eviction priorities (A evict_last, B and C evict_first): 5 % fewer DRAM reads at 4096^3, same time (profiles/r02_gemm_l2_sweep.txt) */
     { const char* h = getenv("COAST_GEMM_L2_HINTS"); if (!(h && !strcmp(h, "0"))) a->mode |= 0x100u; }
+    /* the unprotected kernel halves the tiles of a short last round (xmr_gemm_tf32.cuh); COAST_GEMM_TAIL_SPLIT=0 keeps whole tiles */
+    { const char* h = getenv("COAST_GEMM_TAIL_SPLIT"); if (h && !strcmp(h, "0")) a->mode |= 0x200u; }
     CUfunction fn; int occ = 1;
     int rc = get_fn(name, GEMM_SMEM, &fn, &occ); if (rc) return rc;
     CUtensorMap ma, mb;
@@ -513,7 +515,7 @@ static int launch_gemm_tf32(const coast_launch_desc* d, xmr_args* a, int inj, CU
     {
         cuuint64_t gdim[3] = { 32, d->K, d->N / 32u };
         cuuint64_t gstr[2] = { (cuuint64_t)d->N * 4u, 128u };
-        cuuint32_t box[3] = { 32, 32, bn / 32u };
+        cuuint32_t box[3] = { 32, 32, 4 };                  /* 128 columns per load; a 256-wide tile takes two */
         cuuint32_t estr[3] = { 1, 1, 1 };
         DRV(p_cuTensorMapEncodeTiled(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)d->d_aux, gdim, gstr, box, estr,
                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,

@@ -165,6 +165,21 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
     const uint32_t tiles_n = a.N / BN, tiles_m = a.M / BM, n_tiles = tiles_m * tiles_n, kblocks = a.K / BK;
     const uint32_t group_m = (a.mode & 0xFFu) ? (a.mode & 0xFFu) : GROUP_M_DEFAULT;
     const bool hints = (a.mode & 0x100u) != 0;
+    // Wave quantisation (WIDE only): 512 tiles on 148 CTAs are 3.46 rounds = 4 rounds of time.  When the last, partial round holds at
+    // most grid/2 tiles, each of them is split into two 128 x 128 halves (MMA N = 128, one TMA of B instead of two), so the tail costs
+    // half a round: virtual tile ids [0, sched_full) are whole tiles, [sched_full, n_virtual) are halves (two consecutive ids per tile).
+    uint32_t sched_full = n_tiles, n_virtual = n_tiles;
+    if (WIDE) {
+        const uint32_t whole = (n_tiles / gridDim.x) * gridDim.x, rem = n_tiles - whole;
+        if (rem && 2u * rem <= gridDim.x && !(a.mode & 0x200u)) { sched_full = whole; n_virtual = whole + 2u * rem; }
+    }
+    auto decode = [&](uint32_t v, uint32_t& tm, uint32_t& n_off, uint32_t& bn_t) {
+        uint32_t w = v, h = 0, tn;
+        bn_t = BN;
+        if (v >= sched_full) { w = sched_full + ((v - sched_full) >> 1); h = (v - sched_full) & 1u; bn_t = BN / 2; }
+        tile_coords(w, tiles_m, tiles_n, group_m, tm, tn);
+        n_off = tn * BN + h * (BN / 2);
+    };
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(map_a); tma_prefetch_desc(map_b);
@@ -186,20 +201,21 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
         // ===== TMA producer =====
         uint32_t it = 0;
         const uint64_t pol_a = l2_policy_evict_last(), pol_b = l2_policy_evict_first();
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            uint32_t tm, tn;
-            tile_coords(tile, tiles_m, tiles_n, group_m, tm, tn);
-            const int m0 = (int)tm * BM, n0 = (int)tn * BN;
+        for (uint32_t tile = blockIdx.x; tile < n_virtual; tile += gridDim.x) {
+            uint32_t tm, n_off, bn_t;
+            decode(tile, tm, n_off, bn_t);
+            const int m0 = (int)tm * BM, n0 = (int)n_off;
+            const int b_loads = (int)bn_t / 128;                // the B box is {32 n, 32 k, 4 chunks} = 128 columns: two loads per wide tile
             for (uint32_t kb = 0; kb < kblocks; ++kb, ++it) {
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
-                mbar_arrive_expect_tx(&full[s], A_STAGE + B_STAGE);
-                if (hints) {
-                    tma_load_2d_hint(sA + s * A_STAGE, map_a, &full[s], (int)(kb * BK), m0, pol_a);
-                    tma_load_3d_hint(sB + s * B_STAGE, map_b, &full[s], 0, (int)(kb * BK), n0 / 32, pol_b);
-                } else {
-                    tma_load_2d(sA + s * A_STAGE, map_a, &full[s], (int)(kb * BK), m0);              // box {32 k, 128 m}
-                    tma_load_3d(sB + s * B_STAGE, map_b, &full[s], 0, (int)(kb * BK), n0 / 32);      // box {32 n, 32 k, BN/32 chunks}
+                mbar_arrive_expect_tx(&full[s], A_STAGE + bn_t * BK * 4u);
+                if (hints) tma_load_2d_hint(sA + s * A_STAGE, map_a, &full[s], (int)(kb * BK), m0, pol_a);
+                else tma_load_2d(sA + s * A_STAGE, map_a, &full[s], (int)(kb * BK), m0);             // box {32 k, 128 m}
+                for (int c = 0; c < b_loads; ++c) {
+                    uint8_t* dst = sB + s * B_STAGE + c * (4 * BK * 128);
+                    if (hints) tma_load_3d_hint(dst, map_b, &full[s], 0, (int)(kb * BK), n0 / 32 + 4 * c, pol_b);
+                    else tma_load_3d(dst, map_b, &full[s], 0, (int)(kb * BK), n0 / 32 + 4 * c);
                 }
             }
         }
@@ -209,8 +225,10 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
         // descriptors per instruction; hoisting the descriptor arithmetic leaves one UTCHMMA + one 64-bit add per MMA.)
         const bool leader = elect_one();
         uint32_t it = 0, tcount = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        for (uint32_t tile = blockIdx.x; tile < n_virtual; tile += gridDim.x, ++tcount) {
             const uint32_t buf = tcount % ACC_BUFS, use = tcount / ACC_BUFS;
+            const uint32_t bn_t = tile >= sched_full ? BN / 2 : BN;
+            const uint32_t idesc = (G::IDESC & ~(0x3Fu << 17)) | ((bn_t >> 3) << 17);      // MMA N of this tile
             mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);       // epilogue drained this accumulator set
             tc_fence_after();
             const uint32_t acc0 = tmem_base + buf * (uint32_t)(NC * BN);
@@ -234,8 +252,8 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
                         const uint64_t da = da0 + (uint64_t)((k * UMMA_K * 4) >> 4), db = db0 + (uint64_t)((k * 1024) >> 4);
 #pragma unroll
                         for (int r = 0; r < NC; ++r) {
-                            if (G::ATMEM) tc_mma_tf32_ts(acc0 + r * BN, tmem_a + k * UMMA_K, db, G::IDESC, (kb | (uint32_t)k) ? 1u : 0u);
-                            else tc_mma_tf32(acc0 + r * BN, da, db, G::IDESC, (kb | (uint32_t)k) ? 1u : 0u);
+                            if (G::ATMEM) tc_mma_tf32_ts(acc0 + r * BN, tmem_a + k * UMMA_K, db, idesc, (kb | (uint32_t)k) ? 1u : 0u);
+                            else tc_mma_tf32(acc0 + r * BN, da, db, idesc, (kb | (uint32_t)k) ? 1u : 0u);
                         }
                     }
                     tc_commit(&empty[s]);                       // smem slot free once these MMAs (and the copy) retire
@@ -255,17 +273,17 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
         const uint64_t pol_c = l2_policy_evict_first();
         Tally tally(a);
         uint32_t tcount = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-            uint32_t tm, tn;
-            tile_coords(tile, tiles_m, tiles_n, group_m, tm, tn);
-            const uint32_t m0 = tm * BM, n0 = tn * BN;
+        for (uint32_t tile = blockIdx.x; tile < n_virtual; tile += gridDim.x, ++tcount) {
+            uint32_t tm, n0, bn_t;
+            decode(tile, tm, n0, bn_t);
+            const uint32_t m0 = tm * BM;
             const uint32_t buf = tcount % ACC_BUFS, use = tcount / ACC_BUFS;
             mbar_wait(&tmem_full[buf], use & 1u);
             tc_fence_after();
             const uint32_t row = m0 + q * 32 + lane;
             const uint32_t lane_addr = tmem_base + buf * (uint32_t)(NC * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-            for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+            for (int c0 = half * (int)(bn_t / 2); c0 < (half + 1) * (int)(bn_t / 2); c0 += 32) {
                 uint32_t v[3][32];
 #pragma unroll
                 for (int r = 0; r < NC; ++r) tc_ld_32x32(lane_addr + r * BN + c0, v[r]);

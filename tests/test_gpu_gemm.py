@@ -50,6 +50,21 @@ def test_gemm_tf32_matches_truncated_fp64_reference(rt, oracle, M, N, K):
     assert np.abs(o.view(np.float32).reshape(M, N) - outs[3]).max() <= 2e-6 * K
 
 
+@pytest.mark.parametrize("M,N,K", [(2432, 2048, 64), (2560, 2048, 96)])
+def test_gemm_unprotected_tail_split_is_bit_identical(rt, oracle, M, N, K, monkeypatch):
+    """152 / 160 tiles of 128 x 256 on 148 CTAs: the 4 / 12 tiles of the short last round run as 128 x 128 halves (xmr_gemm_tf32.cuh,
+    `decode`); every element accumulates over K in the same order, so the output equals the whole-tile schedule's and the TMR kernel's"""
+    A, B = operands(oracle, M, N, K, seed=12)
+    split, _ = run(rt, 1, A, B)
+    monkeypatch.setenv("COAST_GEMM_TAIL_SPLIT", "0")
+    whole, _ = run(rt, 1, A, B)
+    monkeypatch.delenv("COAST_GEMM_TAIL_SPLIT")
+    tmr, st = run(rt, 3, A, B)
+    assert split.tobytes() == whole.tobytes() == tmr.tobytes() and st.errors_corrected == 0
+    ref = tf32(A).astype(np.float64) @ tf32(B).astype(np.float64)
+    assert np.abs(split - ref).max() <= 2e-6 * K
+
+
 def test_gemm_faults_are_voted_out_and_counted(rt, oracle):
     import coast_b200 as cb
     M, N, K = 256, 384, 128
