@@ -10,6 +10,7 @@
 #include "xmr_mm.cuh"
 #include "xmr_mm_tiled.cuh"
 #include "xmr_gemm_tf32.cuh"
+#include "xmr_gemm_tf32_pair.cuh"
 #include "xmr_mm_tc.cuh"
 #include "xmr_qsort.cuh"
 #include "xmr_chstone_sha.cuh"

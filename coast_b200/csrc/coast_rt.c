@@ -493,8 +493,19 @@ static int launch_gemm_tf32(const coast_launch_desc* d, xmr_args* a, int inj, CU
     const int wide = d->num_clones == 1 && d->N % 256u == 0;
     if (d->num_clones == 1 && !wide) snprintf(name, sizeof name, "xmr_gemm_tf32n_nc1_inj%d", inj);
     else snprintf(name, sizeof name, "xmr_gemm_tf32_nc%u_inj%d", d->num_clones, inj);
-    const unsigned bn = wide ? 256u : 128u, stages = wide ? 4u : 6u;
-    const unsigned GEMM_SMEM = stages * (16384u + 32u * bn * 4u) + 1024u + 256u;
+    unsigned bn = wide ? 256u : 128u, stages = wide ? 4u : 6u;
+    unsigned GEMM_SMEM = stages * (16384u + 32u * bn * 4u) + 1024u + 256u;
+    /* CTA-pair kernels (xmr_gemm_tf32_pair.cuh, tcgen05 cta_group::2): 256 x BN pair tiles, each CTA stages half of B.
+     * COAST_GEMM_PAIR=1 selects them when the shape allows (M % 256, N % BN). */
+    unsigned b_box_chunks = 4u;
+    int pair = 0;
+    { const char* e = getenv("COAST_GEMM_PAIR");
+      const unsigned pbn = d->num_clones == 3 ? 128u : 256u;
+      if (e && !strcmp(e, "1") && d->M % 256u == 0 && d->N % pbn == 0 && G.sm_count >= 2) {
+          pair = 1; bn = pbn; stages = d->num_clones == 3 ? 8u : 6u; b_box_chunks = bn / 2u / 32u;
+          GEMM_SMEM = stages * (16384u + 32u * (bn / 2u) * 4u) + 1024u + 256u;
+          snprintf(name, sizeof name, "xmr_gemm_tf32p_nc%u_inj%d", d->num_clones, inj);
+      } }
     { const char* g = getenv("COAST_GEMM_GROUP_M"); if (g && atoi(g) > 0 && atoi(g) < 256) a->mode = (a->mode & ~0xFFu) | (unsigned)atoi(g); }
     /* L2 eviction priorities (A evict_last, B and C evict_first): 5 % fewer DRAM reads at 4096^3, same time (profiles/r02_gemm_l2_sweep.txt) */
     { const char* h = getenv("COAST_GEMM_L2_HINTS"); if (!(h && !strcmp(h, "0"))) a->mode |= 0x100u; }
@@ -515,14 +526,15 @@ static int launch_gemm_tf32(const coast_launch_desc* d, xmr_args* a, int inj, CU
     {
         cuuint64_t gdim[3] = { 32, d->K, d->N / 32u };
         cuuint64_t gstr[2] = { (cuuint64_t)d->N * 4u, 128u };
-        cuuint32_t box[3] = { 32, 32, 4 };                  /* 128 columns per load; a 256-wide tile takes two */
+        cuuint32_t box[3] = { 32, 32, b_box_chunks };       /* 128 columns per load; a 256-wide tile takes two (pair kernels: one half tile) */
         cuuint32_t estr[3] = { 1, 1, 1 };
         DRV(p_cuTensorMapEncodeTiled(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)d->d_aux, gdim, gstr, box, estr,
                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
     }
-    unsigned tiles = (d->M / 128u) * (d->N / bn);
+    unsigned tiles = (d->M / 128u) * (d->N / bn);           /* pair kernels: CTAs = 2 x pair tiles, an even grid (cluster 2 x 1 x 1) */
     unsigned grid = tiles < (unsigned)G.sm_count ? tiles : (unsigned)G.sm_count;
+    if (pair) grid &= ~1u;
     void* params[3] = { a, &ma, &mb };
     if (d->flags & COAST_F_VERBOSE) fprintf(stderr, "coast_rt: %s grid=%u smem=%u tiles=%u\n", name, grid, GEMM_SMEM, tiles);
     DRV(p_cuLaunchKernel(fn, grid, 1, 1, 384, 1, 1, GEMM_SMEM, stream, params, NULL));

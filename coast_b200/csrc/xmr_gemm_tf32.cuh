@@ -145,6 +145,53 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)swizzle << 61);
 }
+// Epilogue of one accumulator row: columns [c_begin, c_end) of a tile whose replica r lives at TMEM columns lane_addr + r * rep_stride.
+// TMEM -> registers, (inject), vote with the reference's select voter / `fcmp oeq`, count, ONE store of the voted row segment.
+template <int NC, bool INJECT>
+__device__ __forceinline__ void epilogue_cols(const xmr_args& a, Tally& tally, uint32_t lane_addr, uint32_t rep_stride, uint32_t row, uint32_t n0,
+                                              int c_begin, int c_end, bool hints, uint64_t pol_c) {
+    const uint32_t flags = a.flags;
+    const bool majority = flags & COAST_F_MAJORITY_D;
+    float* C = static_cast<float*>(a.out);
+#pragma unroll 1
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        uint32_t v[3][32];
+#pragma unroll
+        for (int r = 0; r < NC; ++r) tc_ld_32x32(lane_addr + r * rep_stride + c0, v[r]);
+        tc_wait_ld();
+        float* dst = C + (size_t)row * a.N + n0 + c0;
+        const unsigned long long local0 = (unsigned long long)row * a.N + n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint32_t r0 = v[0][j + e], r1 = NC > 1 ? v[1][j + e] : r0, r2 = NC > 2 ? v[2][j + e] : r0;
+                if (INJECT) {
+                    Fault f = fault_for_unit(a, NC, local0 + j + e, [](uint32_t) { return 32u; });
+                    if (f.active) {
+                        tally.injected++;
+                        uint32_t mk = 1u << f.bit;
+                        if (f.replica == 0) r0 ^= mk; else if (f.replica == 1) r1 ^= mk; else r2 ^= mk;
+                    }
+                }
+                const float f0 = __uint_as_float(r0), f1 = __uint_as_float(r1), f2 = __uint_as_float(r2);
+                uint32_t vote = r0, bad = 0;
+                if (NC == 2) bad = (f0 == f1) ? 0u : 1u;
+                if (NC == 3) {
+                    const bool c01 = (f0 == f1), c02 = (f0 == f2);       // fcmp oeq
+                    vote = majority ? ((r0 & r1) | (r0 & r2) | (r1 & r2)) : (c01 ? r0 : r2);
+                    bad = (c01 && c02) ? 0u : 1u;
+                }
+                o[e] = vote;
+                tally.unit_exit<NC>(bad, 1u, flags, a.unit_base + local0 + j + e);
+            }
+            if (hints) st_v4_hint(dst + j, make_uint4(o[0], o[1], o[2], o[3]), pol_c);
+            else *reinterpret_cast<uint4*>(dst + j) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
 template <int NC, bool INJECT, bool WIDE = (NC == 1)>
 __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* map_a, const CUtensorMap* map_b) {
     using G = Geom<NC, WIDE>;
@@ -267,9 +314,6 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
         // ===== epilogue: TMEM -> registers, vote, count, ONE store =====
         const int q = warp & 3;                                 // TMEM lane quarter this warp may touch
         const int half = (warp - 4) >> 2;                       // two warps per quarter, each takes half of the tile's columns
-        const uint32_t flags = a.flags;
-        const bool majority = flags & COAST_F_MAJORITY_D;
-        float* C = static_cast<float*>(a.out);
         const uint64_t pol_c = l2_policy_evict_first();
         Tally tally(a);
         uint32_t tcount = 0;
@@ -282,43 +326,7 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
             tc_fence_after();
             const uint32_t row = m0 + q * 32 + lane;
             const uint32_t lane_addr = tmem_base + buf * (uint32_t)(NC * BN) + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-            for (int c0 = half * (int)(bn_t / 2); c0 < (half + 1) * (int)(bn_t / 2); c0 += 32) {
-                uint32_t v[3][32];
-#pragma unroll
-                for (int r = 0; r < NC; ++r) tc_ld_32x32(lane_addr + r * BN + c0, v[r]);
-                tc_wait_ld();
-                float* dst = C + (size_t)row * a.N + n0 + c0;
-                const unsigned long long local0 = (unsigned long long)row * a.N + n0 + c0;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    uint32_t o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        uint32_t r0 = v[0][j + e], r1 = NC > 1 ? v[1][j + e] : r0, r2 = NC > 2 ? v[2][j + e] : r0;
-                        if (INJECT) {
-                            Fault f = fault_for_unit(a, NC, local0 + j + e, [](uint32_t) { return 32u; });
-                            if (f.active) {
-                                tally.injected++;
-                                uint32_t mk = 1u << f.bit;
-                                if (f.replica == 0) r0 ^= mk; else if (f.replica == 1) r1 ^= mk; else r2 ^= mk;
-                            }
-                        }
-                        const float f0 = __uint_as_float(r0), f1 = __uint_as_float(r1), f2 = __uint_as_float(r2);
-                        uint32_t vote = r0, bad = 0;
-                        if (NC == 2) bad = (f0 == f1) ? 0u : 1u;
-                        if (NC == 3) {
-                            const bool c01 = (f0 == f1), c02 = (f0 == f2);       // fcmp oeq
-                            vote = majority ? ((r0 & r1) | (r0 & r2) | (r1 & r2)) : (c01 ? r0 : r2);
-                            bad = (c01 && c02) ? 0u : 1u;
-                        }
-                        o[e] = vote;
-                        tally.unit_exit<NC>(bad, 1u, flags, a.unit_base + local0 + j + e);
-                    }
-                    if (hints) st_v4_hint(dst + j, make_uint4(o[0], o[1], o[2], o[3]), pol_c);
-                    else *reinterpret_cast<uint4*>(dst + j) = make_uint4(o[0], o[1], o[2], o[3]);
-                }
-            }
+            epilogue_cols<NC, INJECT>(a, tally, lane_addr, (uint32_t)BN, row, n0, half * (int)(bn_t / 2), (half + 1) * (int)(bn_t / 2), hints, pol_c);
             tc_fence_before();
             mbar_arrive(&tmem_empty[buf]);                      // EPI_THREADS arrivals release this accumulator set
         }

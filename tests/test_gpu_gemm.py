@@ -65,6 +65,27 @@ def test_gemm_unprotected_tail_split_is_bit_identical(rt, oracle, M, N, K, monke
     assert np.abs(split - ref).max() <= 2e-6 * K
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 32), (256, 256, 256), (512, 768, 96), (1024, 512, 2048), (2560, 4096, 64)])
+def test_gemm_cta_pair_kernels_are_bit_identical_to_the_single_cta_kernels(rt, oracle, M, N, K, monkeypatch):
+    """xmr_gemm_tf32p_* (tcgen05 cta_group::2, 256 x BN pair tiles, each CTA stages half of B): same operands, same accumulation order
+    over K per element -> the same bits as xmr_gemm_tf32_*, for every replica count, with and without injected faults, same counters"""
+    import coast_b200 as cb
+    A, B = operands(oracle, M, N, K, seed=21)
+    plan = cb.FaultPlan(mode=cb.PLAN_BERNOULLI, seed=3, p=0.01)
+    single = {nc: run(rt, nc, A, B) for nc in (1, 2, 3)}
+    single_f = {nc: run(rt, nc, A, B, plan=plan) for nc in (2, 3)}
+    monkeypatch.setenv("COAST_GEMM_PAIR", "1")
+    for nc in (1, 2, 3):
+        C, st = run(rt, nc, A, B)
+        assert C.tobytes() == single[nc][0].tobytes(), (nc, np.abs(C - single[nc][0]).max())
+        assert st.as_dict() == single[nc][1].as_dict()
+    for nc in (2, 3):
+        C, st = run(rt, nc, A, B, plan=plan)
+        assert C.tobytes() == single_f[nc][0].tobytes() and st.as_dict() == single_f[nc][1].as_dict() and st.injected > 0
+    ref = tf32(A).astype(np.float64) @ tf32(B).astype(np.float64)
+    assert np.abs(single[1][0] - ref).max() <= 2e-6 * K
+
+
 def test_gemm_faults_are_voted_out_and_counted(rt, oracle):
     import coast_b200 as cb
     M, N, K = 256, 384, 128
