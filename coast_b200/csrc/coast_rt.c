@@ -495,14 +495,17 @@ static int launch_gemm_tf32(const coast_launch_desc* d, xmr_args* a, int inj, CU
     else snprintf(name, sizeof name, "xmr_gemm_tf32_nc%u_inj%d", d->num_clones, inj);
     unsigned bn = wide ? 256u : 128u, stages = wide ? 4u : 6u;
     unsigned GEMM_SMEM = stages * (16384u + 32u * bn * 4u) + 1024u + 256u;
-    /* CTA-pair kernels (xmr_gemm_tf32_pair.cuh, tcgen05 cta_group::2): 256 x BN pair tiles, each CTA stages half of B.
-     * COAST_GEMM_PAIR=1 selects them when the shape allows (M % 256, N % BN). */
+    /* CTA-pair kernels (xmr_gemm_tf32_pair.cuh, tcgen05 cta_group::2): 256 x BN pair tiles, each CTA stages half of B.  Bit-identical
+     * to the single-CTA kernels; measured at 4096^3: unprotected 0.190 vs 0.201 ms, DWC 0.320 vs 0.328 ms, TMR 0.465 vs 0.463 ms
+     * (profiles/r02_gemm_pair_timings.txt).  Default: pairs for the unprotected and DWC kernels when the shape allows (M % 256,
+     * N % BN), the single-CTA kernel for TMR; COAST_GEMM_PAIR=0 / 1 forces one or the other for every replica count. */
     unsigned b_box_chunks = 4u;
     int pair = 0;
     { const char* e = getenv("COAST_GEMM_PAIR");
-      const unsigned pbn = d->num_clones == 3 ? 128u : 256u;
-      if (e && !strcmp(e, "1") && d->M % 256u == 0 && d->N % pbn == 0 && G.sm_count >= 2) {
-          pair = 1; bn = pbn; stages = d->num_clones == 3 ? 8u : 6u; b_box_chunks = bn / 2u / 32u;
+      const unsigned pbn = d->num_clones == 1 ? 256u : 128u;
+      const int want = e && (!strcmp(e, "0") || !strcmp(e, "1")) ? e[0] == '1' : d->num_clones < 3;
+      if (want && d->M % 256u == 0 && d->N % pbn == 0 && G.sm_count >= 2) {
+          pair = 1; bn = pbn; stages = d->num_clones == 1 ? 6u : 8u; b_box_chunks = 2u;
           GEMM_SMEM = stages * (16384u + 32u * (bn / 2u) * 4u) + 1024u + 256u;
           snprintf(name, sizeof name, "xmr_gemm_tf32p_nc%u_inj%d", d->num_clones, inj);
       } }

@@ -42,7 +42,7 @@ constexpr int CTA_THREADS = 384, EPI_THREADS = 256;     // warps 0-2 = TMA / MMA
 template <int NC, bool WIDE = (NC == 1)> struct Geom {         // WIDE: 128 x 256 tiles (unprotected, N % 256 == 0)
     static constexpr int BN = WIDE ? 256 : 128;
     static constexpr int STAGES = WIDE ? 4 : 6;
-    static constexpr int ACC_BUFS = NC == 1 ? 2 : 1;             // accumulator sets (double-buffered when TMEM allows)
+    static constexpr int ACC_BUFS = NC == 3 ? 1 : 2;             // accumulator sets: double-buffered when TMEM allows (1 x 256 x 2, 2 x 128 x 2 = 512 columns)
     // Staging A in TMEM (tcgen05.cp + TS-mode MMAs) is built and bit-identical, but measured no faster on the B200 (r02 call 2,
     // 4096^3: TMR 0.498 ms vs 0.495 ms with shared-memory operands; DWC 0.354 ms): the replicated MMAs are bound by the tensor
     // pipe itself (830 TF/s issued = 96 % of the measured cuBLAS-derived TF32 peak), not by shared-memory reads.  Off.

@@ -5,9 +5,11 @@
 // 64 B/clk/SM, the TMR tile 42.7 B/clk/SM: the unprotected and DWC kernels are L2->SM bound, the TMR kernel sits on the edge.
 // Two CTAs of one TPC (cluster 2 x 1 x 1) that share a 256 x BN tile each stage only HALF of the B tile; the pair's MMA
 // (M = 256, issued by the leader CTA) reads A from both CTAs' shared memory and the two B halves from either side:
-//     unprotected  256 x 256 pair tile : 32 KiB per CTA per 512 cycles = 64 B/clk/SM   (was 96)
-//     DWC          256 x 256           : 32 KiB per 1024 cycles        = 32 B/clk/SM   (was 64)
-//     TMR          256 x 128           : 24 KiB per  768 cycles        = 32 B/clk/SM   (was 42.7)
+//     unprotected  256 x 256 pair tile : 32 KiB per CTA per 512 cycles = 64 B/clk/SM   (was 96), two accumulator sets
+//     DWC          256 x 128           : 24 KiB per 512 cycles         = 48 B/clk/SM   (was 64), two accumulator sets (2 x 2 x 128 = 512
+//                                        TMEM columns): the epilogue of tile i overlaps the main loop of tile i+1
+//     TMR          256 x 128           : 24 KiB per 768 cycles         = 32 B/clk/SM   (was 42.7); one accumulator set as before
+// Measured (B200, 4096^3): the TMR kernel does not move (0.465 vs 0.463 ms: tensor-pipe bound), so TMR keeps the single-CTA kernel by default.
 // Everything else is the single-CTA kernel: NC accumulators per CTA in TMEM (each CTA holds its own 128 rows x BN columns x NC),
 // the same voting epilogue (epilogue_cols), the same counters and fault site, the same per-element accumulation order over K --
 // outputs are bit-identical to xmr_gemm_tf32_* (tests/test_gpu_gemm.py).
@@ -26,10 +28,10 @@ namespace xmr {
 namespace gemm {
 
 template <int NC> struct PairGeom {
-    static constexpr int BN = NC == 3 ? 128 : 256;               // pair tile = 256 x BN
+    static constexpr int BN = NC == 1 ? 256 : 128;               // pair tile = 256 x BN
     static constexpr int BNH = BN / 2;                           // B columns each CTA stages
-    static constexpr int ACC_BUFS = NC == 1 ? 2 : 1;
-    static constexpr int STAGES = NC == 3 ? 8 : 6;               // 24 KiB / 32 KiB per stage: 192 KiB either way
+    static constexpr int ACC_BUFS = NC == 3 ? 1 : 2;             // 1 x 256 x 2, 2 x 128 x 2 = 512 columns; 3 x 128 leaves no second set
+    static constexpr int STAGES = NC == 1 ? 6 : 8;               // 32 KiB / 24 KiB per stage: 192 KiB either way
     static constexpr uint32_t B_STAGE = BK * BNH * 4;
     static constexpr uint32_t ACC_COLS = (uint32_t)NC * BN * ACC_BUFS;
     static_assert(ACC_COLS <= TMEM_COLS, "TMEM budget");
@@ -110,6 +112,19 @@ __device__ __forceinline__ void gemm_pair_body(const xmr_args& a, const CUtensor
     const uint32_t gm1 = (a.mode & 0xFFu) ? (a.mode & 0xFFu) : GROUP_M_DEFAULT;
     const uint32_t group_m = gm1 > 1u ? gm1 / 2u : 1u;
     const bool hints = (a.mode & 0x100u) != 0;
+    // short last round (unprotected kernel): its tiles run as two 256 x 128 halves, as in the single-CTA kernel (`decode` there)
+    uint32_t sched_full = n_tiles, n_virtual = n_tiles;
+    if (NC == 1) {
+        const uint32_t whole = (n_tiles / n_pairs) * n_pairs, rem = n_tiles - whole;
+        if (rem && 2u * rem <= n_pairs && !(a.mode & 0x200u)) { sched_full = whole; n_virtual = whole + 2u * rem; }
+    }
+    auto decode = [&](uint32_t v, uint32_t& tm, uint32_t& n_off, uint32_t& bn_t) {
+        uint32_t w = v, h = 0, tn;
+        bn_t = BN;
+        if (v >= sched_full) { w = sched_full + ((v - sched_full) >> 1); h = (v - sched_full) & 1u; bn_t = BN / 2; }
+        tile_coords(w, tiles_m, tiles_n, group_m, tm, tn);
+        n_off = tn * BN + h * (BN / 2);
+    };
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(map_a); tma_prefetch_desc(map_b);
@@ -131,25 +146,30 @@ __device__ __forceinline__ void gemm_pair_body(const xmr_args& a, const CUtensor
         // ===== TMA producer (both CTAs): own 128 rows of A, own half of the B columns; transactions complete on the LEADER's full[s]
         uint32_t it = 0;
         const uint64_t pol_a = hints ? l2_policy_evict_last() : l2_policy_normal(), pol_b = hints ? l2_policy_evict_first() : l2_policy_normal();
-        for (uint32_t tile = pair; tile < n_tiles; tile += n_pairs) {
-            uint32_t tm, tn;
-            tile_coords(tile, tiles_m, tiles_n, group_m, tm, tn);
-            const int m0 = (int)(tm * 256u + rank * 128u), n0 = (int)(tn * BN + rank * BNH);
+        for (uint32_t tile = pair; tile < n_virtual; tile += n_pairs) {
+            uint32_t tm, n_off, bn_t;
+            decode(tile, tm, n_off, bn_t);
+            const uint32_t bnh_t = bn_t / 2u;                   // this CTA's share of the tile's B columns
+            const int m0 = (int)(tm * 256u + rank * 128u), n0 = (int)(n_off + rank * bnh_t);
+            const int b_loads = (int)bnh_t / 64;                // the B box is {32 n, 32 k, 2 chunks} = 64 columns
             for (uint32_t kb = 0; kb < kblocks; ++kb, ++it) {
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                 mbar_wait_or_trap(&empty[s], ph ^ 1u);
-                if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (A_STAGE + B_STAGE));
+                if (rank == 0) mbar_arrive_expect_tx(&full[s], 2u * (A_STAGE + bnh_t * BK * 4u));
                 const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
                 tma2_load_2d(sA + s * A_STAGE, map_a, bar, (int)(kb * BK), m0, pol_a);                  // box {32 k, 128 m}
-                tma2_load_3d(sB + s * B_STAGE, map_b, bar, 0, (int)(kb * BK), n0 / 32, pol_b);          // box {32 n, 32 k, BNH/32 chunks}
+                for (int c = 0; c < b_loads; ++c)
+                    tma2_load_3d(sB + s * B_STAGE + c * (2 * BK * 128), map_b, bar, 0, (int)(kb * BK), n0 / 32 + 2 * c, pol_b);
             }
         }
     } else if (warp == 1 && rank == 0) {
         // ===== MMA issuer (leader CTA): M = 256 across the pair, every MMA issued NC times into NC accumulators
         const bool leader = elect_one();
         uint32_t it = 0, tcount = 0;
-        for (uint32_t tile = pair; tile < n_tiles; tile += n_pairs, ++tcount) {
+        for (uint32_t tile = pair; tile < n_virtual; tile += n_pairs, ++tcount) {
             const uint32_t buf = tcount % ACC_BUFS, use = tcount / ACC_BUFS;
+            const uint32_t bn_t = tile >= sched_full ? BN / 2 : BN;
+            const uint32_t idesc = (G::IDESC & ~(0x3Fu << 17)) | ((bn_t >> 3) << 17);      // MMA N of this tile
             mbar_wait_or_trap(&tmem_empty[buf], (use & 1u) ^ 1u);       // both CTAs' epilogues drained this accumulator set
             tc_fence_after();
             const uint32_t acc0 = tmem_base + buf * (uint32_t)(NC * BN);
@@ -164,7 +184,7 @@ __device__ __forceinline__ void gemm_pair_body(const xmr_args& a, const CUtensor
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t da = da0 + (uint64_t)((k * UMMA_K * 4) >> 4), db = db0 + (uint64_t)((k * 1024) >> 4);
 #pragma unroll
-                        for (int r = 0; r < NC; ++r) tc2_mma_tf32(acc0 + r * BN, da, db, G::IDESC, (kb | (uint32_t)k) ? 1u : 0u);
+                        for (int r = 0; r < NC; ++r) tc2_mma_tf32(acc0 + r * BN, da, db, idesc, (kb | (uint32_t)k) ? 1u : 0u);
                     }
                     tc2_commit_both(&empty[s]);                 // both CTAs' slots are free once these MMAs retire
                 }
@@ -179,16 +199,16 @@ __device__ __forceinline__ void gemm_pair_body(const xmr_args& a, const CUtensor
         const uint64_t pol_c = l2_policy_evict_first();
         Tally tally(a);
         uint32_t tcount = 0;
-        for (uint32_t tile = pair; tile < n_tiles; tile += n_pairs, ++tcount) {
-            uint32_t tm, tn;
-            tile_coords(tile, tiles_m, tiles_n, group_m, tm, tn);
-            const uint32_t m0 = tm * 256u + rank * 128u, n0 = tn * BN;
+        for (uint32_t tile = pair; tile < n_virtual; tile += n_pairs, ++tcount) {
+            uint32_t tm, n0, bn_t;
+            decode(tile, tm, n0, bn_t);
+            const uint32_t m0 = tm * 256u + rank * 128u;
             const uint32_t buf = tcount % ACC_BUFS, use = tcount / ACC_BUFS;
             mbar_wait_or_trap(&tmem_full[buf], use & 1u);
             tc_fence_after();
             const uint32_t row = m0 + q * 32 + lane;
             const uint32_t lane_addr = tmem_base + buf * (uint32_t)(NC * BN) + ((uint32_t)(q * 32) << 16);
-            epilogue_cols<NC, INJECT>(a, tally, lane_addr, (uint32_t)BN, row, n0, half * (BN / 2), (half + 1) * (BN / 2), hints, pol_c);
+            epilogue_cols<NC, INJECT>(a, tally, lane_addr, (uint32_t)BN, row, n0, half * (int)(bn_t / 2), (half + 1) * (int)(bn_t / 2), hints, pol_c);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[buf]), 0));     // one arrival per warp, on the leader's barrier

@@ -72,6 +72,7 @@ def test_gemm_cta_pair_kernels_are_bit_identical_to_the_single_cta_kernels(rt, o
     import coast_b200 as cb
     A, B = operands(oracle, M, N, K, seed=21)
     plan = cb.FaultPlan(mode=cb.PLAN_BERNOULLI, seed=3, p=0.01)
+    monkeypatch.setenv("COAST_GEMM_PAIR", "0")
     single = {nc: run(rt, nc, A, B) for nc in (1, 2, 3)}
     single_f = {nc: run(rt, nc, A, B, plan=plan) for nc in (2, 3)}
     monkeypatch.setenv("COAST_GEMM_PAIR", "1")

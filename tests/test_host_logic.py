@@ -191,6 +191,31 @@ def test_tf32_gemm_launch(mock_dir, tmp_path):
     assert bad["ops"][0]["rc"] != 0 and "multiples of 128" in bad["ops"][0]["err"]
 
 
+@pytest.mark.parametrize("nc,M,N,pair_env,want_name,want_grid", [
+    (1, 512, 512, None, "xmr_gemm_tf32p_nc1_inj0", 8),       # unprotected: CTA pairs, 256 x 256 pair tiles -> 4 pairs
+    (2, 512, 512, None, "xmr_gemm_tf32p_nc2_inj0", 16),      # DWC: pairs, 256 x 128
+    (3, 512, 512, None, "xmr_gemm_tf32_nc3_inj0", 16),       # TMR: single-CTA kernel by default ...
+    (3, 512, 512, "1", "xmr_gemm_tf32p_nc3_inj0", 16),       # ... pairs on request
+    (1, 512, 512, "0", "xmr_gemm_tf32_nc1_inj0", 8),         # single-CTA 128 x 256
+    (1, 384, 512, None, "xmr_gemm_tf32_nc1_inj0", 6),        # M not a multiple of 256: no pair tile
+    (1, 512, 384, None, "xmr_gemm_tf32n_nc1_inj0", 12),      # N % 256 != 0: the narrow single-CTA kernel
+    (2, 512, 384, None, "xmr_gemm_tf32p_nc2_inj0", 12),
+])
+def test_tf32_gemm_kernel_selection_pairs_and_single(mock_dir, tmp_path, nc, M, N, pair_env, want_name, want_grid):
+    """which TF32 GEMM kernel a shape gets (single CTA / CTA pair, wide / narrow), with an EVEN grid for the cluster kernels and the
+    B box matching what each kernel loads per TMA (64 columns for pairs, 128 for single CTAs)"""
+    env = {"COAST_GEMM_PAIR": pair_env} if pair_env is not None else None
+    res, ev = run_child(mock_dir, tmp_path, [dict(op="launch", kernel=K_GEMM_TF32, nc=nc, n=M * N, M=M, N=N, K=64, in_bytes=M * 64 * 4,
+                                                  aux_bytes=64 * N * 4, out_bytes=M * N * 4, flags=3)], env_extra=env)
+    assert res["ops"][0]["rc"] == 0 and not [e for e in ev if e["op"] == "error"], res
+    la = [e for e in ev if e["op"] == "launch" and "_nc" in e["name"]][0]
+    assert (la["name"], la["grid"], la["block"]) == (want_name, want_grid, 384) and la["smem"] <= 232448
+    if "tf32p" in want_name:
+        assert la["grid"] % 2 == 0
+    tm = [e for e in ev if e["op"] == "tmap"]
+    assert tm[1]["box_bytes"] == 32 * 32 * 4 * (2 if "tf32p" in want_name else 4), tm[1]
+
+
 def test_quicksort_through_the_host_call_uses_one_scratch_slot_per_chunk(mock_dir, tmp_path):
     n, L = 3000, 580
     res, ev = run_child(mock_dir, tmp_path, [dict(op="run_host", kernel=K_QSORT, nc=3, n=n, unit_bytes=4 * L, in_bytes=n * 4 * L,
