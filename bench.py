@@ -87,7 +87,7 @@ class ClockSampler:
     """SM clock + throttle reasons via NVML while the timed regions run."""
 
     def __init__(self, index: int):
-        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
         self.period = 0.002
         self._stop = threading.Event()
         self._th = None
@@ -107,6 +107,10 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)      # W (board power, NVML's ~100 ms window)
+                except Exception:
+                    pass
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 for k, bit in names.items():
                     if r & bit:
@@ -116,7 +120,7 @@ class ClockSampler:
             time.sleep(self.period)
 
     def reset(self):
-        self.samples, self.reasons = [], set()
+        self.samples, self.reasons, self.power = [], set(), []
 
     def start(self, period=0.002):
         """period: NVML polling interval.  2 ms inside the device-timed region (GPU-bound, launches are cheap); 25 ms inside
@@ -138,7 +142,7 @@ class ClockSampler:
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
         return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples),
+                "samples": len(self.samples), "power_w_max": round(max(self.power), 1) if self.power else None,
                 "sampled_over": "the timed region and the back-to-back single-launch loop that follows it (same kernel, GPU busy)"}
 
 
