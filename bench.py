@@ -469,17 +469,29 @@ def measure(cx, wl: str, steps: int, warmup: int, *, cpu_budget_s: float = 0.0, 
     launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
+    n_sm = rt.sm_count()
+    probe0 = torch.zeros(2 * n_sm, dtype=torch.int64, device=dev)
+    probe1 = torch.zeros(2 * n_sm, dtype=torch.int64, device=dev)
     if dist is not None:
         dist.all_reduce(go)                                # rendezvous ON THE GPU: every rank's clock starts when the last rank arrives
+    rt.clock_probe(probe0)                                 # {clock64, globaltimer} per SM, just outside the timed region
     e0.record()
     for i in range(steps):
         step(i)
     if dist is not None and not peer_fold:
         exchange_counters()                                # fallback: inside the timed region, once -- where coast_sync() would fold them
     e1.record()
+    rt.clock_probe(probe1)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     timed_launches = launches
+    # the SM clock the region REALLY ran at: cycles / nanoseconds between the two probes, per SM that answered both, median
+    p0, p1 = probe0.view(-1, 2).cpu(), probe1.view(-1, 2).cpu()
+    both = (p0[:, 1] > 0) & (p1[:, 1] > p0[:, 1])
+    sm_clock_mhz = None
+    if int(both.sum()) >= 8:
+        ghz = (p1[both, 0] - p0[both, 0]).double() / (p1[both, 1] - p0[both, 1]).double()
+        sm_clock_mhz = round(float(ghz.median()) * 1e3, 1)
     if peer_fold:
         dist.barrier()                                     # every rank's kernels (and their remote atomics) have retired
     st = rt.sync()                                         # rank 0: the counters of the whole job (peer fold) / of this rank
@@ -512,6 +524,9 @@ def measure(cx, wl: str, steps: int, warmup: int, *, cpu_budget_s: float = 0.0, 
         i += 1
     sampler.stop()
     clocks = sampler.summary()
+    clocks["sm_mhz_in_timed_region"] = sm_clock_mhz
+    clocks["sm_mhz_in_timed_region_how"] = ("clock64() / %globaltimer deltas between two probe kernels bracketing the timed region, median over SMs; "
+                                            "NVML (sm_mhz) reports the requested clock, this is the delivered one")
     rt.sync()
     k_ms = statistics.median(kms) if kms else 0.0
 
@@ -617,7 +632,8 @@ def measure(cx, wl: str, steps: int, warmup: int, *, cpu_budget_s: float = 0.0, 
     # launching stream, CUDA events); the per-launch event pairs measured after it (k_ms) are kept as a cross-check
     k_reg = ms / max(1, timed_launches)
     prof = static_profile(W.get("profile"))
-    sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    sm_hz = (clocks.get("sm_mhz_in_timed_region") or clocks.get("sm_mhz") or 1965.0) * 1e6   # the delivered clock when the probes answered
+    sm_hz_how = "SM clock delivered in the timed region (clock64/globaltimer probes)" if clocks.get("sm_mhz_in_timed_region") else "NVML-sampled SM clock"
     if W["bound"] == "hbm":
         peak, peak_src = hbm_peak()
         achieved, unit = alg_bytes / (k_reg * 1e-3) / 1e9, "GB/s"
@@ -632,7 +648,7 @@ def measure(cx, wl: str, steps: int, warmup: int, *, cpu_budget_s: float = 0.0, 
         hw = 4096.0 * SM_COUNT * sm_hz / 1e12                # tcgen05 kind::tf32: 4096 dense FLOP / clk / SM
         rl_extra = {"issued_flops_per_launch": flops_issued, "useful_flops_per_launch": flops_issued / 3,
                     "frac_of_clock_scaled_hw_rate": round(achieved / hw, 5),
-                    "clock_scaled_hw_rate": {"value": round(hw, 1), "unit": "TFLOP/s", "how": "4096 FLOP/clk/SM x 148 SMs x sampled SM clock"},
+                    "clock_scaled_hw_rate": {"value": round(hw, 1), "unit": "TFLOP/s", "how": "4096 FLOP/clk/SM x 148 SMs x " + sm_hz_how},
                     "note": "issued = 3 replicas x 2MNK; useful = one replica"}
     if prof and prof.get("kernel") == W["kname"] and "warp_insts" in prof:
         # instructions per launch are a property of the CODE (static, from the committed ncu summary, scaled to this launch's
@@ -640,7 +656,7 @@ def measure(cx, wl: str, steps: int, warmup: int, *, cpu_budget_s: float = 0.0, 
         wi = prof["warp_insts"] * (n / float(W["profile_units"]))
         rl_extra["issue_frac"] = round(wi / (k_reg * 1e-3) / (SM_COUNT * 4 * sm_hz), 4)
         rl_extra["issue_frac_how"] = (f"warp instructions per launch ({prof['_file']}, static) / live kernel time / "
-                                      "(148 SMs x 4 schedulers x 1 warp instruction per clock x sampled SM clock)")
+                                      "(148 SMs x 4 schedulers x 1 warp instruction per clock x " + sm_hz_how + ")")
         if W["bound"] == "hbm" and "pipe_alu_pct" in prof:
             rl_extra["alu_frac"] = round(prof["pipe_alu_pct"] / 100.0, 4)
             rl_extra["alu_frac_source"] = f"{prof['_file']} (static): ncu sm__inst_executed_pipe_alu, pct of peak sustained active"

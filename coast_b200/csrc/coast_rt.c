@@ -905,6 +905,17 @@ static int fill_philox_impl(void* d_dst, uint64_t n_words, uint64_t word_base, u
     return launch_small("xmr_fill_philox", (unsigned)(ctas < cap ? ctas : cap), 256, params, (CUstream)stream);
 }
 
+/* {clock64, globaltimer ns} per SM into d_out[2 * smid ..] (2 x u64 x SM count, see coast_sm_count()): two probes around a region
+ * give the SM clock it really ran at.  Measurement helper of bench.py; not part of the protected path. */
+int coast_clock_probe(void* d_out, void* stream) {
+    ENTER();
+    int rc = ensure_ctx(); if (rc) LEAVE(rc);
+    if (!d_out) LEAVE(fail(COAST_ERR_BAD_ARG, "null d_out"));
+    void* params[] = { &d_out };
+    LEAVE(launch_small("xmr_clock_probe", 4u * (unsigned)G.sm_count, 32, params, (CUstream)stream));
+}
+int coast_sm_count(void) { return G.inited ? G.sm_count : 0; }
+
 int coast_fill_philox(void* d_dst, uint64_t n_words, uint64_t word_base, uint32_t seed, void* stream) {
     ENTER(); LEAVE(fill_philox_impl(d_dst, n_words, word_base, seed, stream));
 }

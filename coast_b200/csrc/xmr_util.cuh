@@ -31,3 +31,18 @@ extern "C" __global__ void xmr_counters_reset(unsigned long long* ctr) {
 extern "C" __global__ void xmr_counters_copy(const unsigned long long* ctr, unsigned long long* dst) {
     if (threadIdx.x < XMR_CTR_COUNT) dst[threadIdx.x] = ctr[threadIdx.x];
 }
+
+// One record per SM that gets a CTA: {clock64(), %globaltimer [ns]} at out[2 * smid ..].  Two probes around a region give the
+// AVERAGE SM clock the region really ran at (delta cycles / delta ns per SM) -- NVML's clocks.sm keeps reporting the nominal clock
+// while the tensor kernels run ~15 % below it under the power limit (profiles/r02_gemm_*: ncu smsp__cycles_elapsed.avg.per_second).
+extern "C" __global__ void xmr_clock_probe(unsigned long long* out) {
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        unsigned long long t;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const unsigned long long c = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        out[2 * smid] = c;
+        out[2 * smid + 1] = t;
+    }
+}

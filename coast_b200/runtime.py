@@ -98,7 +98,7 @@ _LIB = None
 EXPORTS = [
     "coast_init", "coast_numa_node", "coast_shutdown", "coast_last_error", "coast_version", "coast_parse_opt_passes", "coast_flags_honoured", "coast_launch",
     "coast_sync", "coast_sync_noabort", "coast_stats_snapshot", "coast_stats_reset", "coast_counters_export", "coast_counters_attach",
-    "coast_counters_detach", "coast_fault_sites",
+    "coast_counters_detach", "coast_sm_count", "coast_clock_probe", "coast_fault_sites",
     "coast_fault_site_bits", "coast_out_bytes_per_unit", "coast_out_bytes", "coast_votes_per_unit", "coast_malloc", "coast_free",
     "coast_memcpy_h2d", "coast_memcpy_d2h", "coast_memset", "coast_host_alloc", "coast_host_free",
     "coast_stream_create", "coast_stream_destroy", "coast_stream_sync", "coast_fill_philox", "coast_run_host",
@@ -133,6 +133,7 @@ def load_library():
         L.coast_stats_snapshot.argtypes = [C.c_void_p, C.c_void_p]
         L.coast_stats_reset.argtypes = [C.c_void_p]
         L.coast_counters_export.argtypes = [C.c_void_p]
+        L.coast_clock_probe.argtypes = [C.c_void_p, C.c_void_p]
         L.coast_counters_attach.argtypes = [C.c_void_p]
         L.coast_fault_sites.argtypes = [C.c_uint32] * 3
         L.coast_fault_sites.restype = C.c_uint32
@@ -211,6 +212,13 @@ class Runtime:
 
     def stats_snapshot(self, d_out, stream=None):
         self._check(self.L.coast_stats_snapshot(self.stream_handle(stream), d_out.data_ptr()))
+
+    def sm_count(self) -> int:
+        return int(self.L.coast_sm_count())
+
+    def clock_probe(self, d_out, stream=None):
+        """d_out: int64 CUDA tensor of 2 * sm_count() elements -> {clock64, globaltimer ns} per SM"""
+        self._check(self.L.coast_clock_probe(C.c_void_p(d_out.data_ptr()), self.stream_handle(stream)))
 
     # multi-GPU fold of the counters over NVLink peer memory (include/coast_rt.h: coast_counters_export / _attach / _detach)
     def counters_export(self) -> bytes:

@@ -243,6 +243,12 @@ int  coast_sync_noabort(void* stream, coast_stats* out);
  * callers that all-reduce them across GPUs (NCCL) before looking at them. */
 int  coast_stats_snapshot(void* stream, void* d_stats_out /* 5 x uint64_t on device */);
 
+/* Measurement helpers (bench.py): number of SMs of the device, and one {clock64(), %globaltimer ns} record per SM written to
+ * d_out[2 * smid], d_out[2 * smid + 1] (2 x uint64_t x coast_sm_count()).  Two probes around a timed region give the average SM
+ * clock the region really ran at; NVML keeps reporting the nominal clock while tensor kernels run below it under the power limit. */
+int  coast_sm_count(void);
+int  coast_clock_probe(void* d_out, void* stream);
+
 /* Multi-GPU fold of the counters inside the kernels, over NVLink peer memory, instead of a collective (the
  * only exchange of the sharded path is the 40-byte counter block).  One process per GPU:
  *   owner  : coast_counters_export(handle)         -> 64 opaque bytes (a CUDA IPC handle of its counter block); ship them

@@ -31,6 +31,9 @@ KEYS = {
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio": "stall_barrier",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum": "smem_bank_conflicts",
     "lts__t_bytes.sum": "l2_bytes",
+    "smsp__cycles_elapsed.avg.per_second": "sm_clock",
+    "smsp__cycles_elapsed.max": "sm_cycles",
+    "lts__t_sectors_srcunit_tex.sum": "l2_sectors_from_sm",
 }
 
 

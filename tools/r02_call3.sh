@@ -19,6 +19,11 @@ for nc in 1 2 3; do python tools/profile_target.py --kernel gemm --nc $nc --side
 cat "$out/timings.txt"
 timeout 600 ncu --set full --clock-control none -k regex:xmr_aes128_enc_nc2_inj1 -c 1 -o "$out/aes_nc2_inj1" python tools/profile_target.py --kernel aes --nc 2 --log2n 24 --iters 2 --inject 0.0009765625 > "$out/ncu_aes.log" 2>&1
 python tools/ncu_summary.py "$out/aes_nc2_inj1.ncu-rep" "$out/aes_nc2_inj1.json" > /dev/null 2>&1; rm -f "$out/aes_nc2_inj1.ncu-rep"
+for cfg in "3 0 gemm_nc3" "1 1 gemm_nc1_pair" "1 0 gemm_nc1_single" "2 1 gemm_nc2_pair"; do
+  set -- $cfg
+  COAST_GEMM_PAIR=$2 timeout 600 ncu --set full --clock-control none -k regex:xmr_gemm_tf32 -c 1 -o "$out/$3" python tools/profile_target.py --kernel gemm --nc $1 --side 4096 --iters 1 > "$out/ncu_$3.log" 2>&1
+  python tools/ncu_summary.py "$out/$3.ncu-rep" "$out/$3.json" > /dev/null 2>&1; rm -f "$out/$3.ncu-rep"
+done
 timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > "$out/bench_default.json" 2> "$out/bench_default.err"; echo "bench rc=$?" | tee -a "$out/summary.txt"
 timeout 300 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 --ref-budget-s 25 > "$out/bench_reference.json" 2> "$out/bench_reference.err"; echo "ref rc=$?" | tee -a "$out/summary.txt"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 5000 --csv --log-file "$out/launches_bench.csv" \
@@ -32,6 +37,9 @@ for tool in memcheck racecheck; do
   run $tool --kernel gemm --nc 3 --side 256 --iters 1 --inject 0.01
   run $tool --kernel gemm --nc 1 --side 256 --iters 1
   run $tool --kernel crc16 --nc 3 --log2n 12 --iters 1 --inject 0.1 --flags 0x200
+  run $tool --kernel gemm --nc 2 --side 512 --iters 1 --inject 0.01
+  COAST_GEMM_PAIR=1 run $tool --kernel gemm --nc 3 --side 512 --iters 1 --inject 0.01
+  run $tool --kernel sha256 --nc 3 --log2n 12 --iters 1 --inject 0.1
 done
 } > "$out/sanitizer.log" 2>&1
 grep -E "^===|--- exit|ERROR SUMMARY|RACECHECK SUMMARY" "$out/sanitizer.log" | head -60
