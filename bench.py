@@ -88,6 +88,7 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self.want_power = False
         self.period = 0.002
         self._stop = threading.Event()
         self._th = None
@@ -107,10 +108,11 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)      # W (board power, NVML's ~100 ms window)
-                except Exception:
-                    pass
+                if self.want_power:                        # a slow NVML query that holds the driver lock: never inside a timed region
+                    try:
+                        self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)  # W (board power, NVML's ~100 ms window)
+                    except Exception:
+                        pass
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 for k, bit in names.items():
                     if r & bit:
@@ -142,7 +144,7 @@ class ClockSampler:
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
         return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples), "power_w_max": round(max(self.power), 1) if self.power else None,
+                "samples": len(self.samples), "power_w_max_single_launch_loop": round(max(self.power), 1) if self.power else None,
                 "sampled_over": "the timed region and the back-to-back single-launch loop that follows it (same kernel, GPU busy)"}
 
 
@@ -474,14 +476,17 @@ def measure(cx, wl: str, steps: int, warmup: int, *, cpu_budget_s: float = 0.0, 
     probe1 = torch.zeros(2 * n_sm, dtype=torch.int64, device=dev)
     if dist is not None:
         dist.all_reduce(go)                                # rendezvous ON THE GPU: every rank's clock starts when the last rank arrives
-    rt.clock_probe(probe0)                                 # {clock64, globaltimer} per SM, just outside the timed region
+    use_probe = os.environ.get("COAST_BENCH_CLOCK_PROBE", "1") != "0"
+    if use_probe:
+        rt.clock_probe(probe0)                             # {clock64, globaltimer} per SM, just outside the timed region
     e0.record()
     for i in range(steps):
         step(i)
     if dist is not None and not peer_fold:
         exchange_counters()                                # fallback: inside the timed region, once -- where coast_sync() would fold them
     e1.record()
-    rt.clock_probe(probe1)
+    if use_probe:
+        rt.clock_probe(probe1)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     timed_launches = launches
@@ -512,6 +517,7 @@ def measure(cx, wl: str, steps: int, warmup: int, *, cpu_budget_s: float = 0.0, 
     # kernel-only duration (cross-check of the roofline's average) and enough GPU-busy time for >= 20 clock samples:
     # single launches bracketed by events, for at least 20 launches and 60 ms
     kms = []
+    sampler.want_power = True                              # board power: sampled in this loop only (same kernel, GPU busy)
     t_loop = time.perf_counter()
     i = 0
     while descs and (i < 20 or time.perf_counter() - t_loop < 0.06) and i < 2000:
@@ -523,6 +529,7 @@ def measure(cx, wl: str, steps: int, warmup: int, *, cpu_budget_s: float = 0.0, 
         kms.append(a.elapsed_time(b))
         i += 1
     sampler.stop()
+    sampler.want_power = False
     clocks = sampler.summary()
     clocks["sm_mhz_in_timed_region"] = sm_clock_mhz
     clocks["sm_mhz_in_timed_region_how"] = ("clock64() / %globaltimer deltas between two probe kernels bracketing the timed region, median over SMs; "
