@@ -385,7 +385,10 @@ static int store_votes_built(uint32_t kernel) { return kernel == COAST_K_CRC16 |
 
 uint32_t coast_flags_honoured(uint32_t kernel, uint32_t nc, uint32_t fl) {
     uint32_t h = fl & (COAST_F_COUNT_ERRORS | COAST_F_COUNT_SYNCS | COAST_F_VERBOSE | COAST_F_MAJORITY_VOTER);
-    if (kernel == COAST_K_SHA256 && nc == 3) h |= fl & (COAST_F_INTERLEAVE | COAST_F_SEGMENT);
+    /* layout: every kernel's native replica placement is the interleaved one (adjacent lanes of a warp; the tensor-core kernels
+     * issue the replicas' MMAs back to back per k-step), so -i is what they do; replicas on separate warps (-s) exist for SHA-256 TMR only */
+    h |= fl & COAST_F_INTERLEAVE;
+    if (kernel == COAST_K_SHA256 && nc == 3) h |= fl & COAST_F_SEGMENT;
     if (store_votes_built(kernel))
         h |= fl & (COAST_F_NO_MEM_REPLICATION | COAST_F_STORE_DATA_SYNC | COAST_F_NO_STORE_DATA_SYNC);
     else if (!store_votes_wanted(fl))

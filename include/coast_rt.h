@@ -85,7 +85,7 @@ typedef enum coast_kernel_id {
 #define COAST_F_COUNT_SYNCS         0x0002u /* -countSyncs   synchronization.cpp:1415-1425 */
 #define COAST_F_NO_MEM_REPLICATION  0x0004u /* -noMemReplication (rule D2, passes.rst "Replication Rules"): variables live ONCE, stores
                                                are voted (synchronization.cpp:205-215) -> in-loop store votes, see below */
-#define COAST_F_INTERLEAVE          0x0008u /* -i : replicas on adjacent LANES of one warp        */
+#define COAST_F_INTERLEAVE          0x0008u /* -i : replicas on adjacent LANES of one warp (every kernel's native placement) */
 #define COAST_F_SEGMENT             0x0010u /* -s : replicas on adjacent WARPS of one CTA (reference default,
                                                interface.cpp:245-247); layout hint only, results identical */
 #define COAST_F_VERBOSE             0x0020u /* -verbose */

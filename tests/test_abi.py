@@ -159,3 +159,18 @@ def test_plain_c_caller_runs_on_the_gpu(built_lib, tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "result: 5ba3" in res.stdout and "C:0 E:0 F:" in res.stdout and "handler_calls=1" in res.stdout and "abi_demo ok" in res.stdout
+
+
+def test_flags_honoured_says_what_each_kernel_really_does(built_lib):
+    """coast_flags_honoured(): counting flags everywhere; in-loop store votes for CRC16 / MM_U32 / SHA256 only; -i is every kernel's native
+    replica placement (adjacent lanes / back-to-back MMAs), -s (separate warps) exists for SHA-256 TMR only"""
+    import coast_b200.runtime as r
+    L = r.load_library()
+    F_CE, F_CS, F_NOMEM, F_I, F_S, F_SDS = 0x1, 0x2, 0x4, 0x8, 0x10, 0x200
+    K_CRC, K_SHA, K_AES, K_MM, K_GEMM, K_QS = 0, 1, 2, 3, 4, 5
+    for k in (K_CRC, K_SHA, K_AES, K_MM, K_GEMM, K_QS):
+        for nc in (2, 3):
+            h = L.coast_flags_honoured(k, nc, F_CE | F_CS | F_I | F_S | F_NOMEM | F_SDS)
+            assert h & F_CE and h & F_CS and h & F_I, (k, nc, hex(h))
+            assert bool(h & F_S) == (k == K_SHA and nc == 3), (k, nc, hex(h))
+            assert bool(h & F_NOMEM) == bool(h & F_SDS) == (k in (K_CRC, K_SHA, K_MM)), (k, nc, hex(h))
