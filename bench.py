@@ -695,7 +695,9 @@ def measure(cx, wl: str, steps: int, warmup: int, *, cpu_budget_s: float = 0.0, 
                 "timer": "host clock around the blocking C-ABI call coast_run_host (pinned host buffers in and out)",
                 "pcie_pinned_copy_gbs": {"h2d": round(pcie_h2d, 1), "d2h": round(pcie_d2h, 1)},
                 "bound_ms": round(bound_s * 1e3, 4), "frac_of_bound": round(bound_s / e2e_s, 4),
-                "bound_how": "max(h2d_bytes / bare pinned H2D copy rate, d2h_bytes / bare pinned D2H copy rate) on this box (full duplex)",
+                "bound_how": "max(h2d_bytes / bare pinned H2D copy rate, d2h_bytes / bare pinned D2H copy rate) on this box (full duplex)"
+                             + ("; the zero-copy path reads the pinned input from the SMs, not through a copy engine, so it can beat this figure"
+                                if host_path == "zerocopy" else ""),
                 "numa_node": rt.numa_node},
         "gpu_launches": timed_launches,
         "clocks": clocks,
