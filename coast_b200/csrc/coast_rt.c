@@ -517,6 +517,9 @@ static int launch_gemm_tf32(const coast_launch_desc* d, xmr_args* a, int inj, CU
     { const char* h = getenv("COAST_GEMM_L2_HINTS"); if (!(h && !strcmp(h, "0"))) a->mode |= 0x100u; }
     /* the unprotected kernel halves the tiles of a short last round (xmr_gemm_tf32.cuh); COAST_GEMM_TAIL_SPLIT=0 keeps whole tiles */
     { const char* h = getenv("COAST_GEMM_TAIL_SPLIT"); if (h && !strcmp(h, "0")) a->mode |= 0x200u; }
+    /* DWC / TMR: the A operand stays in the tensor core's collector across the replicas of a k-step (tcgen05.mma collector::a::fill /
+     * use / lastuse); COAST_GEMM_KEEP_A=0 re-reads it from shared memory for every replica */
+    { const char* h = getenv("COAST_GEMM_KEEP_A"); if (h && !strcmp(h, "0")) a->mode |= 0x400u; }
     CUfunction fn; int occ = 1;
     int rc = get_fn(name, GEMM_SMEM, &fn, &occ); if (rc) return rc;
     CUtensorMap ma, mb;

@@ -106,6 +106,24 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// The replicas of one k-step are NC back-to-back MMAs on the SAME operands.  The A-operand collector of the tensor core can keep A
+// across them (collector::a::fill on the first, ::use in between, ::lastuse on the last; SASS UTCHMMA ...A_KEEP / A_REUSE): A is then read
+// from shared memory once per k-step instead of NC times (TMR: 16 KiB per 3 MMAs instead of 24 = 85 B/clk instead of 128).
+// USAGE: 0 = plain (collector::a::discard, the default), 1 = fill, 2 = use, 3 = lastuse.
+template <int USAGE>
+__device__ __forceinline__ void tc_mma_tf32_col(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if (USAGE == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    else if (USAGE == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32.collector::a::use [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    else if (USAGE == 3)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        tc_mma_tf32(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
 // A operand from TMEM (128 lanes x 8 columns = 128 rows x 8 tf32 of K), B from shared memory
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -212,6 +230,7 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
     const uint32_t tiles_n = a.N / BN, tiles_m = a.M / BM, n_tiles = tiles_m * tiles_n, kblocks = a.K / BK;
     const uint32_t group_m = (a.mode & 0xFFu) ? (a.mode & 0xFFu) : GROUP_M_DEFAULT;
     const bool hints = (a.mode & 0x100u) != 0;
+    const bool keep_a = (a.mode & 0x400u) == 0;               // A-operand collector reuse across the replicas (COAST_GEMM_KEEP_A=0 clears it)
     // Wave quantisation (WIDE only): 512 tiles on 148 CTAs are 3.46 rounds = 4 rounds of time.  When the last, partial round holds at
     // most grid/2 tiles, each of them is split into two 128 x 128 halves (MMA N = 128, one TMA of B instead of two), so the tail costs
     // half a round: virtual tile ids [0, sched_full) are whole tiles, [sched_full, n_virtual) are halves (two consecutive ids per tile).
@@ -297,10 +316,17 @@ __device__ __forceinline__ void gemm_body(const xmr_args& a, const CUtensorMap* 
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t da = da0 + (uint64_t)((k * UMMA_K * 4) >> 4), db = db0 + (uint64_t)((k * 1024) >> 4);
+                        const uint32_t acc = (kb | (uint32_t)k) ? 1u : 0u;
+                        if (G::ATMEM) {
 #pragma unroll
-                        for (int r = 0; r < NC; ++r) {
-                            if (G::ATMEM) tc_mma_tf32_ts(acc0 + r * BN, tmem_a + k * UMMA_K, db, idesc, (kb | (uint32_t)k) ? 1u : 0u);
-                            else tc_mma_tf32(acc0 + r * BN, da, db, idesc, (kb | (uint32_t)k) ? 1u : 0u);
+                            for (int r = 0; r < NC; ++r) tc_mma_tf32_ts(acc0 + r * BN, tmem_a + k * UMMA_K, db, idesc, acc);
+                        } else if (NC == 1 || !keep_a) {
+#pragma unroll
+                            for (int r = 0; r < NC; ++r) tc_mma_tf32(acc0 + r * BN, da, db, idesc, acc);
+                        } else {                                // A stays in the collector across the replicas of this k-step
+                            tc_mma_tf32_col<1>(acc0, da, db, idesc, acc);
+                            if (NC == 3) tc_mma_tf32_col<2>(acc0 + BN, da, db, idesc, acc);
+                            tc_mma_tf32_col<3>(acc0 + (NC - 1) * BN, da, db, idesc, acc);
                         }
                     }
                     tc_commit(&empty[s]);                       // smem slot free once these MMAs (and the copy) retire

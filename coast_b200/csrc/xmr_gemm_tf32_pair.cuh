@@ -64,11 +64,20 @@ __device__ __forceinline__ void tma2_load_3d(void* smem_dst, const CUtensorMap* 
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
 }
 __device__ __forceinline__ uint64_t l2_policy_normal() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); return p; }
+template <int USAGE>                                            // A-operand collector usage, as tc_mma_tf32_col
 __device__ __forceinline__ void tc2_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    if (USAGE == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    else if (USAGE == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32.collector::a::use [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    else if (USAGE == 3)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once all previously issued MMAs have retired
 __device__ __forceinline__ void tc2_commit_both(uint64_t* bar) {
@@ -112,6 +121,7 @@ __device__ __forceinline__ void gemm_pair_body(const xmr_args& a, const CUtensor
     const uint32_t gm1 = (a.mode & 0xFFu) ? (a.mode & 0xFFu) : GROUP_M_DEFAULT;
     const uint32_t group_m = gm1 > 1u ? gm1 / 2u : 1u;
     const bool hints = (a.mode & 0x100u) != 0;
+    const bool keep_a = (a.mode & 0x400u) == 0;
     // short last round (unprotected kernel): its tiles run as two 256 x 128 halves, as in the single-CTA kernel (`decode` there)
     uint32_t sched_full = n_tiles, n_virtual = n_tiles;
     if (NC == 1) {
@@ -183,8 +193,15 @@ __device__ __forceinline__ void gemm_pair_body(const xmr_args& a, const CUtensor
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t da = da0 + (uint64_t)((k * UMMA_K * 4) >> 4), db = db0 + (uint64_t)((k * 1024) >> 4);
+                        const uint32_t acc = (kb | (uint32_t)k) ? 1u : 0u;
+                        if (NC == 1 || !keep_a) {
 #pragma unroll
-                        for (int r = 0; r < NC; ++r) tc2_mma_tf32(acc0 + r * BN, da, db, idesc, (kb | (uint32_t)k) ? 1u : 0u);
+                            for (int r = 0; r < NC; ++r) tc2_mma_tf32<0>(acc0 + r * BN, da, db, idesc, acc);
+                        } else {                                // A stays in the collector across the replicas of this k-step
+                            tc2_mma_tf32<1>(acc0, da, db, idesc, acc);
+                            if (NC == 3) tc2_mma_tf32<2>(acc0 + BN, da, db, idesc, acc);
+                            tc2_mma_tf32<3>(acc0 + (NC - 1) * BN, da, db, idesc, acc);
+                        }
                     }
                     tc2_commit_both(&empty[s]);                 // both CTAs' slots are free once these MMAs retire
                 }

@@ -87,6 +87,25 @@ def test_gemm_cta_pair_kernels_are_bit_identical_to_the_single_cta_kernels(rt, o
     assert np.abs(single[1][0] - ref).max() <= 2e-6 * K
 
 
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_gemm_a_operand_collector_reuse_changes_nothing(rt, oracle, pair, monkeypatch):
+    """DWC / TMR: the replicas of a k-step keep A in the tensor core's collector (tcgen05.mma collector::a::fill / use / lastuse) instead
+    of re-reading it from shared memory -- same products, same accumulation order, same bits and counters, with and without faults"""
+    import coast_b200 as cb
+    M, N, K = 512, 768, 352
+    A, B = operands(oracle, M, N, K, seed=31)
+    plan = cb.FaultPlan(mode=cb.PLAN_BERNOULLI, seed=8, p=0.01)
+    monkeypatch.setenv("COAST_GEMM_PAIR", pair)
+    monkeypatch.setenv("COAST_GEMM_KEEP_A", "0")
+    plain = {nc: run(rt, nc, A, B, plan=plan) for nc in (2, 3)}
+    monkeypatch.delenv("COAST_GEMM_KEEP_A")
+    for nc in (2, 3):
+        C, st = run(rt, nc, A, B, plan=plan)
+        assert C.tobytes() == plain[nc][0].tobytes() and st.as_dict() == plain[nc][1].as_dict() and st.injected > 0
+    ref = tf32(A).astype(np.float64) @ tf32(B).astype(np.float64)
+    assert np.abs(plain[3][0] - ref).max() <= 2e-6 * K
+
+
 def test_gemm_faults_are_voted_out_and_counted(rt, oracle):
     import coast_b200 as cb
     M, N, K = 256, 384, 128
