@@ -564,6 +564,8 @@ static int launch_mm_tc_planes(const coast_launch_desc* d, xmr_args* a, int inj,
         void* params2[] = { &B, &pb, &k32, &n32 };
         DRV(p_cuLaunchKernel(f, (unsigned)G.sm_count * 8u, 1, 1, 256, 1, 1, 0, stream, params2, NULL));
     }
+    /* the MMAs that share an A limb keep it in the tensor core's collector (xmr_mm_tc.cuh); COAST_MM_KEEP_A=0 issues them plain */
+    { const char* h = getenv("COAST_MM_KEEP_A"); if (h && !strcmp(h, "0")) a->mode |= 0x400u; else a->mode &= ~0x400u; }
     const unsigned smem = 2u * (65536u + 4u * bn * 128u) + 1024u + 256u;
     char name[64];
     snprintf(name, sizeof name, "xmr_mm_u32_%s_nc%u_inj%d", atmem ? "tct" : "tc", nc, inj);

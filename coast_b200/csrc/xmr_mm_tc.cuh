@@ -46,6 +46,21 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A-operand collector usage as xmr::gemm::tc_mma_tf32_col: 1 = fill, 2 = use, 3 = lastuse (0 = plain)
+template <int USAGE>
+__device__ __forceinline__ void tc_mma_i8_col(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if (USAGE == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    else if (USAGE == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8.collector::a::use [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    else if (USAGE == 3)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        tc_mma_i8(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
 // A operand from TMEM (128 lanes x 8 columns = 128 rows x 32 bytes of K), B from shared memory
 __device__ __forceinline__ void tc_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -122,6 +137,7 @@ __device__ __forceinline__ void body(const xmr_args& a, const CUtensorMap* map_a
         // converged code leaves one UTCIMMA + one add per MMA.
         constexpr uint32_t IDESC_U8 = IdescU8<BN>::value;
         const bool leader = elect_one();
+        const bool keep_a = (a.mode & 0x400u) == 0;             // COAST_MM_KEEP_A=0 clears it
         uint32_t it = 0, tcount = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
             mbar_wait(tmem_empty, (tcount & 1u) ^ 1u);
@@ -141,6 +157,34 @@ __device__ __forceinline__ void body(const xmr_args& a, const CUtensorMap* map_a
                             for (int k = 0; k < TBK / 32; ++k)
                                 tc_cp_128x256b(tmem_a + (i * (TBK / 32) + k) * 8, da0 + (uint64_t)((i * (TBM * TBK) + k * 32) >> 4));
                     }
+                    if (!ATMEM && keep_a) {
+                        // Limb-major order: the (4 - i) x NC MMAs that multiply A limb i follow each other and keep that A slice in the
+                        // tensor core's collector (fill ... use ... lastuse): 4 KiB of A per k-step and limb instead of per MMA.  The u8 MMA
+                        // of N = BN reads 4 KiB of A + BN x 32 B of B per 16 tensor cycles -- 5x the shared-memory bandwidth without this.
+                        // Integer accumulation is exact modulo 2^32, so the order of the limb products inside S_d does not matter; the
+                        // first product into S_d of a tile is still (i = 0, j = d).
+#pragma unroll
+                        for (int k = 0; k < TBK / 32; ++k) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint64_t da = da0 + (uint64_t)((i * (TBM * TBK) + k * 32) >> 4);
+                                const uint32_t acc = (kb | (uint32_t)k | (uint32_t)i) ? 1u : 0u;
+#pragma unroll
+                                for (int j = 0; j < 4 - i; ++j) {
+                                    const uint64_t db = db0 + (uint64_t)((j * (BN * TBK) + k * 32) >> 4);
+#pragma unroll
+                                    for (int r = 0; r < NC; ++r) {
+                                        const uint32_t dst = tmem_base + (r * 4 + (i + j)) * BN;
+                                        const bool first = j == 0 && r == 0, last = j == 3 - i && r == NC - 1;
+                                        if (first && last) tc_mma_i8(dst, da, db, IDESC_U8, acc);
+                                        else if (first) tc_mma_i8_col<1>(dst, da, db, IDESC_U8, acc);
+                                        else if (last) tc_mma_i8_col<3>(dst, da, db, IDESC_U8, acc);
+                                        else tc_mma_i8_col<2>(dst, da, db, IDESC_U8, acc);
+                                    }
+                                }
+                            }
+                        }
+                    } else
 #pragma unroll
                     for (int k = 0; k < TBK / 32; ++k) {
 #pragma unroll

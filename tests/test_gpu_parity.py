@@ -591,6 +591,10 @@ def test_mm_tensor_core_limb_kernel_is_bit_exact(rt, oracle, nc, M, N, K, monkey
     for variant in ("tc", "tct"):                       # A operand from shared memory / staged in TMEM (tcgen05.cp + TS-mode MMA)
         monkeypatch.setenv("COAST_MM_PATH", variant)
         g_v, _ = both(rt, oracle, oracle.K_MM_U32, nc, A, M * N, M=M, N=N, K=K, aux=B, flags=3, plan_kw=dict(seed=K, p=0.02))
+    monkeypatch.setenv("COAST_MM_PATH", "tc")             # the limb-major order with the A limb kept in the collector (default) vs plain MMAs
+    monkeypatch.setenv("COAST_MM_KEEP_A", "0")
+    g_plain, _ = both(rt, oracle, oracle.K_MM_U32, nc, A, M * N, M=M, N=N, K=K, aux=B, flags=3, plan_kw=dict(seed=K, p=0.02))
+    monkeypatch.delenv("COAST_MM_KEEP_A")
     monkeypatch.setenv("COAST_MM_PATH", "tiled")
     if N % 128 == 0:
         g_tiled, _ = both(rt, oracle, oracle.K_MM_U32, nc, A, M * N, M=M, N=N, K=K, aux=B, flags=3)
