@@ -216,6 +216,23 @@ def test_tf32_gemm_kernel_selection_pairs_and_single(mock_dir, tmp_path, nc, M, 
     assert tm[1]["box_bytes"] == 32 * 32 * 4 * (2 if "tf32p" in want_name else 4), tm[1]
 
 
+def test_gemm_tuning_switches_reach_the_kernel_as_mode_bits(mock_dir, tmp_path):
+    """COAST_GEMM_GROUP_M / _L2_HINTS / _TAIL_SPLIT / _KEEP_A (TF32) and COAST_MM_KEEP_A (integer limb kernel) are read per launch and
+    travel in xmr_args.mode: bits 0-7 group, 0x100 hints on, 0x200 tail split off, 0x400 collector reuse off"""
+    s = 512
+    gemm = dict(op="launch", kernel=K_GEMM_TF32, nc=3, n=s * s, M=s, N=s, K=64, in_bytes=s * 64 * 4, aux_bytes=64 * s * 4, out_bytes=s * s * 4, flags=3)
+    mm = dict(op="launch", kernel=K_MM_U32, nc=3, n=s * s, M=s, N=s, K=128, in_bytes=s * 128 * 4, aux_bytes=128 * s * 4, out_bytes=s * s * 4, flags=3)
+    res, ev = run_child(mock_dir, tmp_path, [gemm, mm], env_extra={"COAST_MM_PATH": "tc"})
+    la = [e for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
+    assert [x["name"] for x in la] == ["xmr_gemm_tf32_nc3_inj0", "xmr_mm_u32_tc_nc3_inj0"]
+    assert args_of(la[0]).mode == 0x100 and args_of(la[1]).mode & 0x400 == 0
+    env = {"COAST_GEMM_GROUP_M": "8", "COAST_GEMM_L2_HINTS": "0", "COAST_GEMM_TAIL_SPLIT": "0", "COAST_GEMM_KEEP_A": "0", "COAST_MM_KEEP_A": "0",
+           "COAST_MM_PATH": "tc"}
+    res, ev = run_child(mock_dir, tmp_path, [gemm, mm], env_extra=env)
+    la = [e for e in ev if e["op"] == "launch" and "_nc" in e["name"]]
+    assert args_of(la[0]).mode == 8 | 0x200 | 0x400 and args_of(la[1]).mode & 0x400
+
+
 def test_quicksort_through_the_host_call_uses_one_scratch_slot_per_chunk(mock_dir, tmp_path):
     n, L = 3000, 580
     res, ev = run_child(mock_dir, tmp_path, [dict(op="run_host", kernel=K_QSORT, nc=3, n=n, unit_bytes=4 * L, in_bytes=n * 4 * L,
