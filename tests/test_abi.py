@@ -174,3 +174,27 @@ def test_flags_honoured_says_what_each_kernel_really_does(built_lib):
             assert h & F_CE and h & F_CS and h & F_I, (k, nc, hex(h))
             assert bool(h & F_S) == (k == K_SHA and nc == 3), (k, nc, hex(h))
             assert bool(h & F_NOMEM) == bool(h & F_SDS) == (k in (K_CRC, K_SHA, K_MM)), (k, nc, hex(h))
+
+
+def _sass(fun):
+    import subprocess
+    cubin = os.path.join(ROOT, "coast_b200", "csrc", "coast_kernels.cubin")
+    return subprocess.run(["cuobjdump", "-sass", "-fun", fun, cubin], capture_output=True, text=True, timeout=300).stdout
+
+
+def test_sass_carries_the_blackwell_instructions_the_design_claims(built_lib):
+    """cuobjdump of the embedded sm_100a cubin: tcgen05 MMAs (UTCHMMA / UTCIMMA), TMA loads (UTMALDG), TMEM loads (LDTM); the
+    replicated TF32 MMAs keep A in the collector (A_KEEP / A_REUSE); the CTA-pair kernels issue .2CTA MMAs, .2CTA TMA loads and multicast
+    commits; the headline SHA-256 kernel has no local-memory traffic"""
+    tmr = _sass("xmr_gemm_tf32_nc3_inj0")
+    assert tmr.count("UTCHMMA") >= 12 and "UTMALDG" in tmr and "LDTM" in tmr
+    assert "A_KEEP" in tmr and "A_REUSE" in tmr and ".2CTA" not in tmr
+    pair = _sass("xmr_gemm_tf32p_nc2_inj0")
+    assert "UTCHMMA.2CTA" in pair and "UTMALDG.2D.2CTA" in pair and "UTMALDG.3D.2CTA" in pair and "UTCBAR.2CTA.MULTICAST" in pair
+    assert "UCGABAR_ARV" in pair and "UCGABAR_WAIT" in pair                     # the cluster barrier around TMEM allocation / teardown
+    limb = _sass("xmr_mm_u32_tc_nc3_inj0")
+    assert limb.count("UTCIMMA") >= 120 and "A_KEEP" in limb
+    sha = _sass("xmr_sha256_b64_seg_nc3_inj1")
+    assert "UTMALDG" in sha and "STL" not in sha and "LDL" not in sha
+    aes = _sass("xmr_aes128_enc_nc2_inj1")
+    assert "UTMALDG" in aes and "SYNCS" in aes and "PRMT" in aes                # TMA ring on mbarriers, byte-permute table addressing
