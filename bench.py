@@ -747,12 +747,17 @@ def run_ours(args):
     if cx.dist is not None and os.environ.get("COAST_BENCH_COUNTER_FOLD", "peer") == "peer":
         # rank 0 exports its counter block (a 64-byte CUDA IPC handle), everyone else will map it over NVLink
         h = torch.zeros(64, dtype=torch.uint8, device=cx.dev)
-        if cx.rank == 0:
-            h.copy_(torch.frombuffer(bytearray(cx.rt.counters_export()), dtype=torch.uint8))
-        cx.dist.broadcast(h, src=0)
-        handle = bytes(h.cpu().numpy().tobytes())
         ok = torch.ones(1, dtype=torch.int32, device=cx.dev)
-        if cx.rank != 0:
+        if cx.rank == 0:
+            try:
+                h.copy_(torch.frombuffer(bytearray(cx.rt.counters_export()), dtype=torch.uint8))
+            except Exception as exc:                       # no CUDA IPC in this environment: every rank falls back together
+                print(f"bench: counter block cannot be exported: {exc}", file=sys.stderr)
+                ok.zero_()
+        cx.dist.broadcast(h, src=0)
+        cx.dist.broadcast(ok, src=0)
+        handle = bytes(h.cpu().numpy().tobytes())
+        if cx.rank != 0 and int(ok[0]) == 1:
             try:                                           # probe: attach + detach once; no peer access -> every rank falls back together
                 cx.rt.counters_attach(handle); cx.rt.counters_detach()
             except Exception as exc:
