@@ -745,27 +745,14 @@ def run_ours(args):
     cx.sampler = ClockSampler(local)
     cx.peer_handle = None
     if cx.dist is not None and os.environ.get("COAST_BENCH_COUNTER_FOLD", "peer") == "peer":
-        # rank 0 exports its counter block (a 64-byte CUDA IPC handle), everyone else will map it over NVLink
-        h = torch.zeros(64, dtype=torch.uint8, device=cx.dev)
-        ok = torch.ones(1, dtype=torch.int32, device=cx.dev)
-        if cx.rank == 0:
-            try:
-                h.copy_(torch.frombuffer(bytearray(cx.rt.counters_export()), dtype=torch.uint8))
-            except Exception as exc:                       # no CUDA IPC in this environment: every rank falls back together
-                print(f"bench: counter block cannot be exported: {exc}", file=sys.stderr)
-                ok.zero_()
-        cx.dist.broadcast(h, src=0)
-        cx.dist.broadcast(ok, src=0)
-        handle = bytes(h.cpu().numpy().tobytes())
-        if cx.rank != 0 and int(ok[0]) == 1:
-            try:                                           # probe: attach + detach once; no peer access -> every rank falls back together
-                cx.rt.counters_attach(handle); cx.rt.counters_detach()
-            except Exception as exc:
-                print(f"bench: peer counter block unavailable on rank {cx.rank}: {exc}", file=sys.stderr)
-                ok.zero_()
-        cx.dist.all_reduce(ok, op=cx.dist.ReduceOp.MIN)
-        if int(ok[0]) == 1:
-            cx.peer_handle = handle
+        # rank 0 exports its counter block (a 64-byte CUDA IPC handle), everyone else maps it over NVLink -- or all ranks fall back
+        from coast_b200.shard import negotiate_peer_counter_block
+
+        def probe(handle):
+            cx.rt.counters_attach(handle)
+            cx.rt.counters_detach()
+        cx.peer_handle = negotiate_peer_counter_block(cx.dist, cx.rank, torch, cx.dev, cx.rt.counters_export, probe,
+                                                      log=lambda m: print("bench: " + m, file=sys.stderr))
 
     main_cpu = 0.0 if args.no_cpu_baseline else 10.0
     line = measure(cx, args.workload, args.steps, args.warmup, cpu_budget_s=main_cpu)

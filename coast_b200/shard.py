@@ -44,3 +44,33 @@ def device_counters_to_stats_tensor(raw):
     out = raw.clone()
     out[4] = _I64_MAX if int(raw[4]) == -1 else raw[4]
     return out
+
+
+def negotiate_peer_counter_block(dist, rank: int, torch, device, export_fn, probe_fn, log=None):
+    """Agree, across all ranks, on folding the counters through rank 0's counter block over NVLink peer memory
+    (include/coast_rt.h: coast_counters_export / coast_counters_attach).
+
+    rank 0 calls ``export_fn() -> 64 bytes``; the handle is broadcast; every other rank calls ``probe_fn(handle)`` (attach + detach
+    once).  Returns the handle if EVERY rank succeeded, else None on every rank -- a failure anywhere (no CUDA IPC, no peer access)
+    makes all ranks fall back together, and no rank is ever left waiting in a collective.  Works for nccl and gloo."""
+    h = torch.zeros(64, dtype=torch.uint8, device=device)
+    ok = torch.ones(1, dtype=torch.int32, device=device)
+    if rank == 0:
+        try:
+            h.copy_(torch.frombuffer(bytearray(export_fn()), dtype=torch.uint8))
+        except Exception as exc:
+            if log:
+                log(f"counter block cannot be exported: {exc}")
+            ok.zero_()
+    dist.broadcast(h, src=0)
+    dist.broadcast(ok, src=0)
+    handle = bytes(h.cpu().numpy().tobytes())
+    if rank != 0 and int(ok[0]) == 1:
+        try:
+            probe_fn(handle)
+        except Exception as exc:
+            if log:
+                log(f"peer counter block unavailable on rank {rank}: {exc}")
+            ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    return handle if int(ok[0]) == 1 else None
