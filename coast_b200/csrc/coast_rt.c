@@ -233,7 +233,7 @@ static int ensure_ctx(void) {
 static int get_fn_b(const char* name, unsigned smem, int block, CUfunction* fn, int* ctas_per_sm) {
     for (int i = 0; i < G.n_fns; ++i)
         if (!strcmp(G.fns[i].name, name) && G.fns[i].smem == smem) { *fn = G.fns[i].fn; if (ctas_per_sm) *ctas_per_sm = G.fns[i].ctas_per_sm; return COAST_OK; }
-    CUfunction f;
+    CUfunction f = NULL;
     CUresult r = p_cuModuleGetFunction(&f, G.mod, name);
     if (r != CUDA_SUCCESS) return drv_fail(r, name);
     if (smem > 48 * 1024) DRV(p_cuFuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
